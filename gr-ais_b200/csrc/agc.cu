@@ -1,0 +1,142 @@
+// agc.cu -- NCO mix (square_and_fft_sync_cc back half) fused with feedforward_agc_cc.
+//
+// Replaces (paths relative to /root/reference):
+//   python/gmsk_sync.py:27-28,33-37   frequency_modulator_fc -> multiply_cc(x, nco)
+//   python/ais_demod.py:35            analog.feedforward_agc_cc(512, 2)
+//
+// One block produces TILE consecutive AGC outputs of one channel.  Output t needs the
+// mixed samples y[t-W+1 .. t] (W = agc window), so the block re-mixes a halo of W-1
+// samples in front of its tile from the phase checkpoints written by k_nco_phase; the
+// mixed stream itself never goes to HBM.
+#include "device_math.cuh"
+#include "internal.h"
+
+namespace b200ais {
+
+namespace {
+
+constexpr int kAgcThreads = 256;
+constexpr int kAgcTile = 2048;
+
+__global__ void __launch_bounds__(kAgcThreads)
+k_mix_agc(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
+          const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, int seg,
+          float sens,
+          int stages, int W, float reference, const float2 *__restrict__ sine,
+          float2 *__restrict__ out, size_t out_stride)
+{
+    extern __shared__ float2 ys[]; // [span] mixed samples, then env[span], then tmp[span]
+    const int c = blockIdx.y;
+    const int t0 = blockIdx.x * kAgcTile;
+    const int tile = min(kAgcTile, n1 - t0);
+    const bool do_mix = stages & B200AIS_STAGE_FREQSYNC;
+    const bool do_agc = stages & B200AIS_STAGE_AGC;
+    const int halo = do_agc ? W - 1 : 0;
+    const int lo = t0 - halo; // first mixed sample index needed (may be negative: zeros)
+    const int span = tile + halo;
+    float *env = reinterpret_cast<float *>(ys + (kAgcTile + halo));
+    const float2 *xc = x + (size_t)c * x_stride;
+
+    if (do_mix) {
+        // segments are aligned to multiples of seg in absolute sample index
+        const int s_first = (lo < 0 ? 0 : lo) / seg;
+        const int s_last = (t0 + tile - 1) / seg;
+        for (int sgi = s_first + threadIdx.x; sgi <= s_last; sgi += blockDim.x) {
+            const int n0 = sgi * seg;
+            float ph = ckpt[(size_t)sgi * channels + c];
+            const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
+            for (int i = 0; i < seg; i++) {
+                ph = nco_step(ph, inc);
+                const int n = n0 + i;
+                if (n >= lo && n < t0 + tile) {
+                    float sn, cs;
+                    fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
+                    ys[n - lo] = cmul_fma(xc[n], make_float2(cs, sn));
+                }
+            }
+        }
+        for (int i = threadIdx.x; i < span; i += blockDim.x)
+            if (lo + i < 0)
+                ys[i] = make_float2(0.0f, 0.0f);
+    } else {
+        for (int i = threadIdx.x; i < span; i += blockDim.x) {
+            const int n = lo + i;
+            ys[i] = n >= 0 ? xc[n] : make_float2(0.0f, 0.0f);
+        }
+    }
+    __syncthreads();
+    float2 *oc = out + (size_t)c * out_stride;
+    if (!do_agc) {
+        for (int i = threadIdx.x; i < tile; i += blockDim.x)
+            oc[t0 + i] = ys[i];
+        return;
+    }
+    for (int i = threadIdx.x; i < span; i += blockDim.x)
+        env[i] = agc_envelope(ys[i].x, ys[i].y);
+    __syncthreads();
+    // sparse-table doubling: after the pass for width k, env[i] = max(env0[i .. i+k-1]) (clipped)
+    int p = 1;
+    constexpr int kMaxPer = (kAgcTile + 2047 + kAgcThreads - 1) / kAgcThreads;
+    while (p * 2 <= W) {
+        float v[kMaxPer];
+#pragma unroll
+        for (int k = 0; k < kMaxPer; k++) {
+            const int i = threadIdx.x + k * kAgcThreads;
+            if (i < span) {
+                float a = env[i];
+                float b = (i + p < span) ? env[i + p] : a;
+                v[k] = fmaxf(a, b);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kMaxPer; k++) {
+            const int i = threadIdx.x + k * kAgcThreads;
+            if (i < span)
+                env[i] = v[k];
+        }
+        __syncthreads();
+        p *= 2;
+    }
+    // out[t] = y[t-W+1] * (reference / max(1e-4, max env over y[t-W+1 .. t]))
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
+        // window starts at local index i (absolute t-W+1) and is W long: two width-p blocks
+        float m = fmaxf(env[i], env[i + W - p]);
+        float max_env = fmaxf(1e-4f, m);
+        float gain = reference / max_env;
+        float2 y = ys[i];
+        oc[t0 + i] = make_float2(gain * y.x, gain * y.y);
+    }
+}
+
+} // namespace
+
+int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int fftlen,
+                   const float *fhat, int vstride, const float *ckpt, int seg, float sens, int stages,
+                   int agc_nsamples, float agc_reference, float2 *out, size_t out_stride,
+                   cudaStream_t s)
+{
+    if (n1 <= 0 || channels <= 0)
+        return B200AIS_OK;
+    if ((stages & B200AIS_STAGE_AGC) && (agc_nsamples < 1 || agc_nsamples > 2048)) {
+        set_error("agc window must be in [1, 2048], got %d", agc_nsamples);
+        return B200AIS_E_INVALID;
+    }
+    Tables tb;
+    int rc = get_tables(&tb);
+    if (rc)
+        return rc;
+    int halo = (stages & B200AIS_STAGE_AGC) ? agc_nsamples - 1 : 0;
+    size_t smem = (size_t)(kAgcTile + halo) * (sizeof(float2) + sizeof(float));
+    B200_CU(cudaFuncSetAttribute(k_mix_agc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((kAgcTile + 2047) * (sizeof(float2) + sizeof(float)))));
+    dim3 grid((n1 + kAgcTile - 1) / kAgcTile, channels);
+    k_mix_agc<<<grid, kAgcThreads, smem, s>>>(x, x_stride, channels, n1, fftlen, fhat, vstride, ckpt, seg,
+                                              sens, stages, agc_nsamples, agc_reference,
+                                              reinterpret_cast<const float2 *>(tb.sine), out,
+                                              out_stride);
+    B200_LAUNCH_CHECK("k_mix_agc");
+    return B200AIS_OK;
+}
+
+} // namespace b200ais

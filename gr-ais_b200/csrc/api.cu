@@ -1,0 +1,1129 @@
+// api.cu -- the C-ABI of libb200ais.so (include/b200ais.h): handle objects, host/device
+// entry points, and the launch sequence of the fused ais_demod chain.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "internal.h"
+
+using namespace b200ais;
+
+namespace {
+
+// ---- small device-buffer helper: grow-only scratch owned by a handle ----
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap)
+            return B200AIS_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        B200_CU(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return B200AIS_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// kernel::fft_filter_ccc block size: fftsize = 2 * 2^ceil(log2 ntaps), nsamples = fftsize - ntaps + 1
+int fft_filter_nsamples(int ntaps)
+{
+    int p = 1;
+    while (p < ntaps)
+        p <<= 1;
+    return 2 * p - ntaps + 1;
+}
+
+int check_stream_status(cudaStream_t s, int *d_status)
+{
+    int st = 0;
+    B200_CU(cudaMemcpyAsync(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaStreamSynchronize(s));
+    if (st) {
+        switch (st) {
+        case B200AIS_E_TAG_OVERFLOW:
+            set_error("a channel produced more tags than max_tags");
+            break;
+        case B200AIS_E_INTERP:
+            set_error("mmse interpolator index out of [0,128] (non-finite input?)");
+            break;
+        case B200AIS_E_OUT_OVERFLOW:
+            set_error("symbol output row too small for the record (raise max_bits)");
+            break;
+        default:
+            set_error("kernel flagged status %d", st);
+        }
+    }
+    return st;
+}
+
+} // namespace
+
+// =========================================================== corr_est_cc
+
+struct b200ais_corr_est {
+    int channels = 0;
+    int L = 0;
+    float sps = 0;
+    unsigned mark_delay = 0;
+    float thresh = 0;
+    int nsamples = 0;
+    std::vector<float> taps; // stored FIR taps, interleaved (what symbols() returns)
+    float2 *d_taps_time = nullptr;
+    int *d_status = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf mask, in, out0, out1, tags, ntags;
+    std::mutex lock; // d_setlock (lib/corr_est_cc_impl.cc:135,169)
+};
+
+static int corr_upload_taps(b200ais_corr_est *h)
+{
+    // time order g[m] pairs with sample t-L+1+m: g[m] = stored[L-1-m]
+    std::vector<float2> g((size_t)h->L);
+    for (int m = 0; m < h->L; m++) {
+        g[m].x = h->taps[2 * (h->L - 1 - m)];
+        g[m].y = h->taps[2 * (h->L - 1 - m) + 1];
+    }
+    if (h->d_taps_time)
+        cudaFree(h->d_taps_time);
+    h->d_taps_time = nullptr;
+    B200_CU(cudaMalloc(&h->d_taps_time, sizeof(float2) * g.size()));
+    B200_CU(cudaMemcpy(h->d_taps_time, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice));
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_corr_est_create(b200ais_corr_est **out, const float *symbols_iq,
+                                       int nsymbols, float sps, unsigned mark_delay,
+                                       float threshold, int channels)
+{
+    if (!out || !symbols_iq || nsymbols < 1 || nsymbols > 4096 || channels < 1) {
+        set_error("corr_est_create: need 1..4096 symbols and channels >= 1");
+        return B200AIS_E_INVALID;
+    }
+    b200ais_corr_est *h = new (std::nothrow) b200ais_corr_est;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->channels = channels;
+    h->L = nsymbols;
+    h->sps = sps;
+    // lib/corr_est_cc_impl.cc:59-63: conjugate, then reverse
+    h->taps.resize(2 * (size_t)nsymbols);
+    for (int i = 0; i < nsymbols; i++) {
+        h->taps[2 * (nsymbols - 1 - i)] = symbols_iq[2 * i];
+        h->taps[2 * (nsymbols - 1 - i) + 1] = -symbols_iq[2 * i + 1];
+    }
+    h->mark_delay = mark_delay >= (unsigned)nsymbols ? (unsigned)nsymbols - 1 : mark_delay; // :65-66
+    float corr = 0; // :71-74, abs(z*conj(z)) = re*re + im*im
+    for (int i = 0; i < nsymbols; i++) {
+        volatile float re = h->taps[2 * i], im = h->taps[2 * i + 1];
+        volatile float rr = re * re, ii = im * im;
+        volatile float s = rr + ii;
+        corr = corr + s;
+    }
+    volatile float tc = threshold * corr;
+    h->thresh = tc * corr;
+    h->nsamples = fft_filter_nsamples(nsymbols);
+    int rc = corr_upload_taps(h);
+    if (!rc) {
+        cudaError_t e = cudaMalloc(&h->d_status, sizeof(int));
+        if (e == cudaSuccess)
+            e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess)
+            rc = cuda_fail(e, "corr_est_create", __FILE__, __LINE__);
+    }
+    if (rc) {
+        b200ais_corr_est_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_corr_est_destroy(b200ais_corr_est *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    if (h->d_taps_time)
+        cudaFree(h->d_taps_time);
+    if (h->d_status)
+        cudaFree(h->d_status);
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    h->mask.release();
+    h->in.release();
+    h->out0.release();
+    h->out1.release();
+    h->tags.release();
+    h->ntags.release();
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_corr_est_set_symbols(b200ais_corr_est *h, const float *symbols_iq,
+                                            int nsymbols)
+{
+    if (!h || !symbols_iq || nsymbols < 1 || nsymbols > 4096) {
+        set_error("set_symbols: need 1..4096 symbols");
+        return B200AIS_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(h->lock);
+    // lib/corr_est_cc_impl.cc:137: d_symbols = symbols -- verbatim, threshold untouched
+    h->taps.assign(symbols_iq, symbols_iq + 2 * (size_t)nsymbols);
+    h->L = nsymbols;
+    h->nsamples = fft_filter_nsamples(nsymbols);
+    h->mark_delay = h->mark_delay >= (unsigned)nsymbols ? (unsigned)nsymbols - 1 : h->mark_delay;
+    B200_CU(cudaStreamSynchronize(h->stream));
+    return corr_upload_taps(h);
+}
+
+extern "C" int b200ais_corr_est_symbols(const b200ais_corr_est *h, float *out_iq, int cap, int *n)
+{
+    if (!h || !n) {
+        set_error("symbols: null argument");
+        return B200AIS_E_INVALID;
+    }
+    *n = h->L;
+    if (out_iq) {
+        if (cap < h->L) {
+            set_error("symbols: buffer holds %d of %d items", cap, h->L);
+            return B200AIS_E_INVALID;
+        }
+        memcpy(out_iq, h->taps.data(), sizeof(float) * 2 * (size_t)h->L);
+    }
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_corr_est_output_multiple(const b200ais_corr_est *h) { return h ? h->nsamples : 0; }
+extern "C" int b200ais_corr_est_history(const b200ais_corr_est *h) { return h ? h->L + 1 : 0; }
+extern "C" unsigned b200ais_corr_est_mark_delay(const b200ais_corr_est *h) { return h ? h->mark_delay : 0; }
+extern "C" float b200ais_corr_est_threshold(const b200ais_corr_est *h) { return h ? h->thresh : 0.0f; }
+
+static size_t mask_stride_for(int n) { return (size_t)((n + 1023) / 1024) * 128; }
+
+extern "C" int b200ais_corr_est_work_dev(b200ais_corr_est *h, int noutput_items, const float *in,
+                                         size_t in_stride, uint64_t nitems_written, float *out0,
+                                         float *out1, size_t out_stride, b200ais_tag *tags,
+                                         int max_tags, int *ntags, void *stream)
+{
+    if (!h || !in || !tags || !ntags || noutput_items < 0 || max_tags < 0 ||
+        in_stride < (size_t)noutput_items + (size_t)h->L) {
+        set_error("corr_est_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(h->lock);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n = noutput_items;
+    const size_t ms = mask_stride_for(n);
+    int rc = h->mask.reserve(ms * (size_t)h->channels);
+    if (rc)
+        return rc;
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), s));
+    const float2 *in2 = reinterpret_cast<const float2 *>(in);
+    const float2 *in_eff = in2 + h->L; // &in[hist_len] (lib/corr_est_cc_impl.cc:188)
+    rc = launch_corr(in_eff, in_stride, h->channels, n, n, h->d_taps_time, h->L, h->thresh,
+                     h->mask.as<uint8_t>(), ms, reinterpret_cast<float2 *>(out1), out_stride, s);
+    if (rc)
+        return rc;
+    const int isps = (int)(h->sps + 0.5f); // :193
+    rc = launch_detect(in_eff, in_stride, h->channels, n, n > 0 ? n : 1, 1, h->d_taps_time, h->L,
+                       h->thresh, isps, h->mark_delay, h->mask.as<uint8_t>(), ms, nitems_written,
+                       out1 != nullptr, tags, max_tags, ntags, nullptr, h->d_status, s);
+    if (rc)
+        return rc;
+    if (out0)
+        rc = launch_copy_delay(in2, in_stride, reinterpret_cast<float2 *>(out0), out_stride,
+                               h->channels, n, s);
+    return rc;
+}
+
+extern "C" int b200ais_corr_est_work(b200ais_corr_est *h, int noutput_items, const float *in,
+                                     size_t in_stride, uint64_t nitems_written, float *out0,
+                                     float *out1, size_t out_stride, b200ais_tag *tags,
+                                     int max_tags, int *ntags)
+{
+    if (!h || !in || !tags || !ntags || noutput_items < 0 || max_tags < 1) {
+        set_error("corr_est_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    const int C = h->channels, n = noutput_items;
+    const size_t row_in = round_up((size_t)n + h->L, 2), row_out = round_up((size_t)std::max(n, 1), 2);
+    int rc;
+    if ((rc = h->in.reserve(row_in * C * sizeof(float2))) ||
+        (rc = h->out0.reserve(row_out * C * sizeof(float2))) ||
+        (rc = h->out1.reserve(row_out * C * sizeof(float2))) ||
+        (rc = h->tags.reserve((size_t)max_tags * C * sizeof(b200ais_tag))) ||
+        (rc = h->ntags.reserve((size_t)C * sizeof(int))))
+        return rc;
+    cudaStream_t s = h->stream;
+    B200_CU(cudaMemcpy2DAsync(h->in.p, row_in * sizeof(float2), in, in_stride * sizeof(float2),
+                              ((size_t)n + h->L) * sizeof(float2), C, cudaMemcpyHostToDevice, s));
+    rc = b200ais_corr_est_work_dev(h, n, h->in.as<float>(), row_in, nitems_written,
+                                   out0 ? h->out0.as<float>() : nullptr,
+                                   out1 ? h->out1.as<float>() : nullptr, row_out,
+                                   h->tags.as<b200ais_tag>(), max_tags, h->ntags.as<int>(), s);
+    if (rc)
+        return rc;
+    if (out0 && n > 0)
+        B200_CU(cudaMemcpy2DAsync(out0, out_stride * sizeof(float2), h->out0.p,
+                                  row_out * sizeof(float2), (size_t)n * sizeof(float2), C,
+                                  cudaMemcpyDeviceToHost, s));
+    if (out1 && n > 0)
+        B200_CU(cudaMemcpy2DAsync(out1, out_stride * sizeof(float2), h->out1.p,
+                                  row_out * sizeof(float2), (size_t)n * sizeof(float2), C,
+                                  cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaMemcpyAsync(tags, h->tags.p, (size_t)max_tags * C * sizeof(b200ais_tag),
+                            cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaMemcpyAsync(ntags, h->ntags.p, (size_t)C * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return check_stream_status(s, h->d_status);
+}
+
+// =============================================== msk_timing_recovery_cc
+
+struct b200ais_msk {
+    int channels = 0;
+    float sps_arg = 0; // the sps handed to make()/set_sps()
+    MskParams p{};
+    MskState *d_state = nullptr;
+    int *d_status = nullptr;
+    cudaStream_t stream = nullptr;
+    DevBuf in, tags, ntags, out, err, mu, nprod, ncons;
+};
+
+extern "C" int b200ais_msk_create(b200ais_msk **out, float sps, float gain, float limit, int osps,
+                                  int channels)
+{
+    if (!out || channels < 1) {
+        set_error("msk_create: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    // lib/msk_timing_recovery_cc_impl.cc:45-62: set_sps, then set_gain (throws), then the osps check
+    if (!(gain > 0)) {
+        set_error("Gain must be positive");
+        return B200AIS_E_RANGE;
+    }
+    if (osps != 1 && osps != 2) {
+        set_error("osps must be 1 or 2");
+        return B200AIS_E_RANGE;
+    }
+    b200ais_msk *h = new (std::nothrow) b200ais_msk;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->channels = channels;
+    h->sps_arg = sps;
+    h->p.sps_half = (float)((double)sps / 2.0);
+    h->p.gain = gain;
+    h->p.gain_omega = (float)((double)(gain * gain) * 0.25);
+    h->p.limit = limit;
+    h->p.osps = osps;
+    cudaError_t e = cudaMalloc(&h->d_state, sizeof(MskState) * (size_t)channels);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_status, sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    int rc = e == cudaSuccess ? B200AIS_OK : cuda_fail(e, "msk_create", __FILE__, __LINE__);
+    if (!rc)
+        rc = launch_msk_reset(h->d_state, channels, h->p.sps_half, h->stream);
+    if (!rc) {
+        e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess)
+            rc = cuda_fail(e, "msk_create sync", __FILE__, __LINE__);
+    }
+    if (rc) {
+        b200ais_msk_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_msk_destroy(b200ais_msk *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    if (h->d_state)
+        cudaFree(h->d_state);
+    if (h->d_status)
+        cudaFree(h->d_status);
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    h->in.release();
+    h->tags.release();
+    h->ntags.release();
+    h->out.release();
+    h->err.release();
+    h->mu.release();
+    h->nprod.release();
+    h->ncons.release();
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_msk_set_gain(b200ais_msk *h, float gain)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    h->p.gain = gain; // the reference stores first, then throws (:81-82)
+    if (!(gain > 0)) {
+        set_error("Gain must be positive");
+        return B200AIS_E_RANGE;
+    }
+    h->p.gain_omega = (float)((double)(gain * gain) * 0.25);
+    return B200AIS_OK;
+}
+extern "C" float b200ais_msk_get_gain(const b200ais_msk *h) { return h ? h->p.gain : 0.0f; }
+extern "C" int b200ais_msk_set_limit(b200ais_msk *h, float limit)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    h->p.limit = limit;
+    return B200AIS_OK;
+}
+extern "C" float b200ais_msk_get_limit(const b200ais_msk *h) { return h ? h->p.limit : 0.0f; }
+extern "C" float b200ais_msk_get_sps(const b200ais_msk *h) { return h ? h->p.sps_half : 0.0f; }
+
+extern "C" int b200ais_msk_forecast(const b200ais_msk *h, int noutput_items)
+{
+    if (!h)
+        return 0;
+    // :103: (int)ceil((noutput_items*d_sps*2) + 3.0*d_sps + ntaps)
+    volatile float a = (float)noutput_items * h->p.sps_half;
+    volatile float b = a * 2.0f;
+    return (int)std::ceil((double)b + 3.0 * (double)h->p.sps_half + 8.0);
+}
+
+extern "C" int b200ais_msk_reset(b200ais_msk *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    int rc = launch_msk_reset(h->d_state, h->channels, h->p.sps_half, h->stream);
+    if (rc)
+        return rc;
+    B200_CU(cudaStreamSynchronize(h->stream));
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_msk_set_sps(b200ais_msk *h, float sps)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    // :69-74: d_sps = sps/2; d_omega = d_sps (every channel's loop restarts at nominal rate)
+    h->sps_arg = sps;
+    h->p.sps_half = (float)((double)sps / 2.0);
+    int rc = launch_msk_set_omega(h->d_state, h->channels, h->p.sps_half, h->stream);
+    if (rc)
+        return rc;
+    B200_CU(cudaStreamSynchronize(h->stream));
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_msk_general_work_dev(b200ais_msk *h, int noutput_items, int ninput_items,
+                                            const float *in, size_t in_stride, uint64_t nitems_read,
+                                            const b200ais_tag *tags, int max_tags, const int *ntags,
+                                            float *out, float *out_err, float *out_mu,
+                                            size_t out_stride, int *nproduced, int *nconsumed,
+                                            void *stream)
+{
+    if (!h || !in || !out || !nproduced || !nconsumed || noutput_items < 0 || ninput_items < 0 ||
+        out_stride < (size_t)noutput_items) {
+        set_error("msk_general_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), s));
+    return launch_msk(reinterpret_cast<const float2 *>(in), in_stride, h->channels, noutput_items,
+                      nullptr, ninput_items, nitems_read, tags, max_tags, ntags, h->p, h->d_state,
+                      reinterpret_cast<float2 *>(out), out_err, out_mu, nullptr, nullptr, out_stride,
+                      nproduced, nconsumed, 0, h->d_status, s);
+}
+
+extern "C" int b200ais_msk_general_work(b200ais_msk *h, int noutput_items, int ninput_items,
+                                        const float *in, size_t in_stride, uint64_t nitems_read,
+                                        const b200ais_tag *tags, int max_tags, const int *ntags,
+                                        float *out, float *out_err, float *out_mu, size_t out_stride,
+                                        int *nproduced, int *nconsumed)
+{
+    if (!h || !in || !out || !nproduced || !nconsumed || noutput_items < 0 || ninput_items < 0) {
+        set_error("msk_general_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    const int C = h->channels;
+    const size_t row_in = round_up((size_t)std::max(ninput_items, 1), 2);
+    const size_t row_out = round_up((size_t)std::max(noutput_items, 1), 2);
+    const int mt = (tags && ntags) ? std::max(max_tags, 0) : 0;
+    int rc;
+    if ((rc = h->in.reserve(row_in * C * sizeof(float2))) ||
+        (rc = h->tags.reserve((size_t)std::max(mt, 1) * C * sizeof(b200ais_tag))) ||
+        (rc = h->ntags.reserve((size_t)C * sizeof(int))) ||
+        (rc = h->out.reserve(row_out * C * sizeof(float2))) ||
+        (rc = h->err.reserve(row_out * C * sizeof(float))) ||
+        (rc = h->mu.reserve(row_out * C * sizeof(float))) ||
+        (rc = h->nprod.reserve((size_t)C * sizeof(int))) ||
+        (rc = h->ncons.reserve((size_t)C * sizeof(int))))
+        return rc;
+    cudaStream_t s = h->stream;
+    if (ninput_items > 0)
+        B200_CU(cudaMemcpy2DAsync(h->in.p, row_in * sizeof(float2), in, in_stride * sizeof(float2),
+                                  (size_t)ninput_items * sizeof(float2), C, cudaMemcpyHostToDevice, s));
+    std::vector<b200ais_tag> sorted;
+    if (mt > 0) {
+        // get_tags_in_range hands the block its tags in offset order; keep insertion order on ties
+        sorted.assign(tags, tags + (size_t)mt * C);
+        for (int c = 0; c < C; c++) {
+            int k = std::min(std::max(ntags[c], 0), mt);
+            std::stable_sort(sorted.begin() + (size_t)c * mt, sorted.begin() + (size_t)c * mt + k,
+                             [](const b200ais_tag &a, const b200ais_tag &b) { return a.offset < b.offset; });
+        }
+        B200_CU(cudaMemcpyAsync(h->tags.p, sorted.data(), sorted.size() * sizeof(b200ais_tag),
+                                cudaMemcpyHostToDevice, s));
+        B200_CU(cudaMemcpyAsync(h->ntags.p, ntags, (size_t)C * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    rc = b200ais_msk_general_work_dev(h, noutput_items, ninput_items, h->in.as<float>(), row_in,
+                                      nitems_read, mt > 0 ? h->tags.as<b200ais_tag>() : nullptr, mt,
+                                      mt > 0 ? h->ntags.as<int>() : nullptr, h->out.as<float>(),
+                                      h->err.as<float>(), h->mu.as<float>(), row_out,
+                                      h->nprod.as<int>(), h->ncons.as<int>(), s);
+    if (rc)
+        return rc;
+    if (noutput_items > 0) {
+        B200_CU(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), h->out.p, row_out * sizeof(float2),
+                                  (size_t)noutput_items * sizeof(float2), C, cudaMemcpyDeviceToHost, s));
+        if (out_err)
+            B200_CU(cudaMemcpy2DAsync(out_err, out_stride * sizeof(float), h->err.p,
+                                      row_out * sizeof(float), (size_t)noutput_items * sizeof(float),
+                                      C, cudaMemcpyDeviceToHost, s));
+        if (out_mu)
+            B200_CU(cudaMemcpy2DAsync(out_mu, out_stride * sizeof(float), h->mu.p,
+                                      row_out * sizeof(float), (size_t)noutput_items * sizeof(float),
+                                      C, cudaMemcpyDeviceToHost, s));
+    }
+    B200_CU(cudaMemcpyAsync(nproduced, h->nprod.p, (size_t)C * sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaMemcpyAsync(nconsumed, h->ncons.p, (size_t)C * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return check_stream_status(s, h->d_status);
+}
+
+// ================================================================ freqest
+
+struct b200ais_freqest {
+    int channels = 0;
+    int fftlen = 0;
+    int offset = 0;
+    float binsize = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf spec, raw, out;
+};
+
+extern "C" int b200ais_freqest_create(b200ais_freqest **out, float sample_rate, int data_rate,
+                                      int fftlen, int channels)
+{
+    if (!out || fftlen < 2 || channels < 1 || !(sample_rate > 0)) {
+        set_error("freqest_create: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    b200ais_freqest *h = new (std::nothrow) b200ais_freqest;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->channels = channels;
+    h->fftlen = fftlen;
+    // lib/freqest_impl.cc:46-47
+    volatile float ratio = (float)data_rate / sample_rate;
+    volatile float off = (float)fftlen * ratio;
+    h->offset = (int)off;
+    h->binsize = sample_rate / (float)fftlen;
+    if (h->offset < 0 || h->offset >= fftlen) {
+        delete h;
+        set_error("freqest_create: data_rate/sample_rate puts the bin offset outside the FFT");
+        return B200AIS_E_INVALID;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "freqest_create", __FILE__, __LINE__);
+    }
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_freqest_destroy(b200ais_freqest *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    h->spec.release();
+    h->raw.release();
+    h->out.release();
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_freqest_work_dev(b200ais_freqest *h, int noutput_items, const float *spec,
+                                        float *out, void *stream)
+{
+    if (!h || !spec || !out || noutput_items < 0) {
+        set_error("freqest_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = h->raw.reserve((size_t)std::max(noutput_items, 1) * h->channels * sizeof(int));
+    if (rc)
+        return rc;
+    rc = launch_freqest_spec(reinterpret_cast<const float2 *>(spec), h->channels, noutput_items,
+                             h->fftlen, h->offset, h->raw.as<int>(), s);
+    if (rc)
+        return rc;
+    return launch_freqest_resolve(h->raw.as<int>(), h->channels, noutput_items, h->fftlen,
+                                  h->binsize, out, s);
+}
+
+extern "C" int b200ais_freqest_work(b200ais_freqest *h, int noutput_items, const float *spec,
+                                    float *out)
+{
+    if (!h || !spec || !out || noutput_items < 0) {
+        set_error("freqest_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    if (noutput_items == 0)
+        return B200AIS_OK;
+    const size_t items = (size_t)noutput_items * h->fftlen * h->channels;
+    int rc;
+    if ((rc = h->spec.reserve(items * sizeof(float2))) ||
+        (rc = h->out.reserve((size_t)noutput_items * h->channels * sizeof(float))))
+        return rc;
+    cudaStream_t s = h->stream;
+    B200_CU(cudaMemcpyAsync(h->spec.p, spec, items * sizeof(float2), cudaMemcpyHostToDevice, s));
+    rc = b200ais_freqest_work_dev(h, noutput_items, h->spec.as<float>(), h->out.as<float>(), s);
+    if (rc)
+        return rc;
+    B200_CU(cudaMemcpyAsync(out, h->out.p, (size_t)noutput_items * h->channels * sizeof(float),
+                            cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaStreamSynchronize(s));
+    return B200AIS_OK;
+}
+
+// ================================================================= invert
+
+extern "C" int b200ais_invert_work_dev(const uint8_t *in, uint8_t *out, size_t nitems, void *stream)
+{
+    if ((!in || !out) && nitems) {
+        set_error("invert_work: null buffer");
+        return B200AIS_E_INVALID;
+    }
+    return launch_invert(in, out, nitems, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200ais_invert_work(const uint8_t *in, uint8_t *out, size_t nitems)
+{
+    if ((!in || !out) && nitems) {
+        set_error("invert_work: null buffer");
+        return B200AIS_E_INVALID;
+    }
+    if (!nitems)
+        return B200AIS_OK;
+    uint8_t *d = nullptr;
+    B200_CU(cudaMalloc(&d, nitems));
+    int rc = B200AIS_OK;
+    cudaError_t e = cudaMemcpy(d, in, nitems, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = launch_invert(d, d, nitems, nullptr);
+        if (!rc)
+            e = cudaMemcpy(out, d, nitems, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "invert_work", __FILE__, __LINE__);
+    return rc;
+}
+
+// =============================================== the fused ais_demod chain
+
+namespace {
+constexpr int kSeg = 16;      // NCO phase checkpoint spacing (samples)
+constexpr int kMaxGroups = 4; // channel groups pipelined over streams in the host variant
+} // namespace
+
+struct b200ais_demod {
+    b200ais_demod_config cfg{};
+    int channels = 0, max_samples = 0, max_tags = 0;
+    int L = 0, nsamples = 0, chunk = 0, isps = 0;
+    unsigned mark_delay = 0;
+    float thresh = 0;
+    int offset = 0;
+    float binsize = 0, sens = 0;
+    MskParams mp{};
+    int HP = 0;          // zero history items in front of every corr_est input row
+    size_t a_stride = 0; // items per row of the corr_est input stream
+    size_t mask_stride = 0;
+    int nvec_max = 0;
+    float2 *d_taps_time = nullptr;
+    float2 *d_x = nullptr; // staging for the host variant [channels][max_samples]
+    float2 *d_a = nullptr;
+    uint8_t *d_mask = nullptr;
+    int *d_raw = nullptr;
+    float *d_fhat = nullptr, *d_ckpt = nullptr;
+    b200ais_tag *d_tags = nullptr;
+    int *d_ntags = nullptr, *d_nbits = nullptr, *d_ncons = nullptr;
+    MskState *d_state = nullptr;
+    uint8_t *d_bits = nullptr;
+    size_t bits_cap = 0;
+    int *d_status = nullptr; // [kMaxGroups + 1]
+    cudaStream_t streams[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t done[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
+    bool taps_enabled = false;
+    DevBuf t_sym, t_err, t_mu, t_soft;
+    int last_n = 0, last_max_bits = 0, last_n1 = 0;
+};
+
+extern "C" int b200ais_demod_default_config(b200ais_demod_config *cfg)
+{
+    if (!cfg)
+        return B200AIS_E_INVALID;
+    cfg->sample_rate = 48000.0f; // python/radio.py:47-48,62
+    cfg->data_rate = 9600;
+    cfg->fftlen = 1024;          // python/radio.py:60
+    cfg->agc_nsamples = 512;     // python/ais_demod.py:35
+    cfg->agc_reference = 2.0f;
+    cfg->sps = 5.0f;
+    cfg->mark_delay = 1;         // python/ais_demod.py:41
+    cfg->threshold = 0.9f;       // python/ais_demod.py:42
+    cfg->gain = 0.04f;           // python/radio.py:57
+    cfg->limit = 0.01f;          // python/radio.py:58
+    cfg->osps = 1;
+    cfg->corr_chunk = 0;
+    cfg->stages = B200AIS_STAGE_FREQSYNC | B200AIS_STAGE_AGC;
+    return B200AIS_OK;
+}
+
+static int demod_max_bits(const b200ais_demod *h, int nsamples)
+{
+    return (int)((double)nsamples / (double)h->cfg.sps * 1.05) + 64;
+}
+
+extern "C" int b200ais_demod_max_bits(const b200ais_demod *h, int nsamples)
+{
+    return h ? demod_max_bits(h, nsamples) : 0;
+}
+
+extern "C" int b200ais_demod_create(b200ais_demod **out, const b200ais_demod_config *cfg,
+                                    const float *symbols_iq, int nsymbols, int channels,
+                                    int max_samples, int max_tags)
+{
+    if (!out || !cfg || !symbols_iq || nsymbols < 1 || nsymbols > 4096 || channels < 1 ||
+        max_samples < 1 || max_tags < 4) {
+        set_error("demod_create: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    if (!(cfg->gain > 0)) {
+        set_error("Gain must be positive");
+        return B200AIS_E_RANGE;
+    }
+    if (cfg->osps != 1 && cfg->osps != 2) {
+        set_error("osps must be 1 or 2");
+        return B200AIS_E_RANGE;
+    }
+    if ((cfg->stages & B200AIS_STAGE_FREQSYNC) &&
+        (cfg->fftlen < 16 || cfg->fftlen > 4096 || (cfg->fftlen & (cfg->fftlen - 1)) ||
+         cfg->fftlen % kSeg)) {
+        set_error("demod_create: fftlen must be a power of two in [16, 4096]");
+        return B200AIS_E_INVALID;
+    }
+    b200ais_demod *h = new (std::nothrow) b200ais_demod;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->cfg = *cfg;
+    h->channels = channels;
+    h->max_samples = max_samples;
+    h->max_tags = max_tags;
+    h->L = nsymbols;
+    h->nsamples = fft_filter_nsamples(nsymbols);
+    int chunk = cfg->corr_chunk > 0 ? cfg->corr_chunk : (24576 / h->nsamples) * h->nsamples;
+    chunk = (chunk / h->nsamples) * h->nsamples;
+    if (chunk <= 0)
+        chunk = h->nsamples;
+    h->chunk = chunk;
+    h->isps = (int)(cfg->sps + 0.5f);
+    h->mark_delay = cfg->mark_delay >= (unsigned)nsymbols ? (unsigned)nsymbols - 1 : cfg->mark_delay;
+    {
+        // corr_est ctor arithmetic (lib/corr_est_cc_impl.cc:59-74) on the conj-reversed taps
+        float corr = 0;
+        for (int i = nsymbols - 1; i >= 0; i--) {
+            volatile float re = symbols_iq[2 * i], im = -symbols_iq[2 * i + 1];
+            volatile float rr = re * re, ii = im * im;
+            volatile float s = rr + ii;
+            corr = corr + s;
+        }
+        volatile float tc = cfg->threshold * corr;
+        h->thresh = tc * corr;
+    }
+    {
+        volatile float ratio = (float)cfg->data_rate / cfg->sample_rate; // lib/freqest_impl.cc:46-47
+        volatile float off = (float)cfg->fftlen * ratio;
+        h->offset = (int)off;
+        h->binsize = cfg->sample_rate / (float)cfg->fftlen;
+        h->sens = (float)(-1.0 / ((double)cfg->sample_rate / (2 * M_PI))); // python/gmsk_sync.py:27
+    }
+    h->mp.sps_half = (float)((double)cfg->sps / 2.0);
+    h->mp.gain = cfg->gain;
+    h->mp.gain_omega = (float)((double)(cfg->gain * cfg->gain) * 0.25);
+    h->mp.limit = cfg->limit;
+    h->mp.osps = cfg->osps;
+    h->HP = (int)round_up((size_t)nsymbols + 2, 4);
+    h->a_stride = round_up((size_t)h->HP + (size_t)max_samples + 16, 4);
+    h->mask_stride = (size_t)((max_samples + 1023) / 1024) * 128;
+    h->nvec_max = (cfg->stages & B200AIS_STAGE_FREQSYNC) ? max_samples / cfg->fftlen : 0;
+
+    const size_t C = (size_t)channels;
+    std::vector<float2> g((size_t)nsymbols);
+    for (int m = 0; m < nsymbols; m++) { // time order: conj(symbols[m])
+        g[m].x = symbols_iq[2 * m];
+        g[m].y = -symbols_iq[2 * m + 1];
+    }
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess)
+            e = cudaMalloc(p, bytes ? bytes : 16);
+    };
+    alloc((void **)&h->d_taps_time, sizeof(float2) * g.size());
+    alloc((void **)&h->d_a, sizeof(float2) * h->a_stride * C);
+    alloc((void **)&h->d_mask, h->mask_stride * C);
+    alloc((void **)&h->d_raw, sizeof(int) * (size_t)std::max(h->nvec_max, 1) * C);
+    alloc((void **)&h->d_fhat, sizeof(float) * (size_t)std::max(h->nvec_max, 1) * C);
+    alloc((void **)&h->d_ckpt, sizeof(float) * (size_t)std::max(h->nvec_max, 1) * (cfg->fftlen / kSeg + 1) * C);
+    alloc((void **)&h->d_tags, sizeof(b200ais_tag) * (size_t)max_tags * C);
+    alloc((void **)&h->d_ntags, sizeof(int) * C);
+    alloc((void **)&h->d_nbits, sizeof(int) * C);
+    alloc((void **)&h->d_ncons, sizeof(int) * C);
+    alloc((void **)&h->d_state, sizeof(MskState) * C);
+    alloc((void **)&h->d_status, sizeof(int) * (kMaxGroups + 1));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h->d_taps_time, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemset(h->d_a, 0, sizeof(float2) * h->a_stride * C); // the zero history pads
+    if (e == cudaSuccess)
+        e = cudaMemset(h->d_status, 0, sizeof(int) * (kMaxGroups + 1));
+    for (int g2 = 0; g2 < kMaxGroups && e == cudaSuccess; g2++) {
+        e = cudaStreamCreateWithFlags(&h->streams[g2], cudaStreamNonBlocking);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&h->done[g2], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "demod_create", __FILE__, __LINE__);
+        b200ais_demod_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_destroy(b200ais_demod *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    void *ptrs[] = { h->d_taps_time, h->d_x, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
+                     h->d_tags, h->d_ntags, h->d_nbits, h->d_ncons, h->d_state, h->d_bits,
+                     h->d_status };
+    for (void *p : ptrs)
+        if (p)
+            cudaFree(p);
+    for (int g = 0; g < kMaxGroups; g++) {
+        if (h->streams[g])
+            cudaStreamDestroy(h->streams[g]);
+        if (h->done[g])
+            cudaEventDestroy(h->done[g]);
+    }
+    h->t_sym.release();
+    h->t_err.release();
+    h->t_mu.release();
+    h->t_soft.release();
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_enable_taps(b200ais_demod *h, int enable)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    h->taps_enabled = enable != 0;
+    return B200AIS_OK;
+}
+
+// Launch the chain for channels [c0, c0+cn) on stream s.  iq rows: iq + c*iq_stride.
+// in_a != 0 means the samples already sit in the corr_est input rows (host variant with
+// neither freq sync nor AGC enabled).
+static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq, size_t iq_stride,
+                              int n, int in_a, uint8_t *bits, int max_bits, int *nbits,
+                              b200ais_tag *tags, int *ntags, int *d_status, cudaStream_t s)
+{
+    const b200ais_demod_config &cfg = h->cfg;
+    const bool fs = cfg.stages & B200AIS_STAGE_FREQSYNC;
+    const int n1 = fs ? (n / cfg.fftlen) * cfg.fftlen : n;
+    const int nvec = fs ? n1 / cfg.fftlen : 0;
+    float2 *a_rows = h->d_a + (size_t)c0 * h->a_stride + h->HP;
+    uint8_t *mask = h->d_mask + (size_t)c0 * h->mask_stride;
+    int *raw = h->d_raw + (size_t)c0 * std::max(h->nvec_max, 1);
+    float *fhat = h->d_fhat + (size_t)c0 * std::max(h->nvec_max, 1);
+    float *ckpt = h->d_ckpt + (size_t)c0 * std::max(h->nvec_max, 1) * (cfg.fftlen / kSeg + 1);
+    const int vs = std::max(h->nvec_max, 1); // row pitch of raw / fhat
+    int rc;
+    if (fs) {
+        if ((rc = launch_sqfft_freqest(iq, iq_stride, cn, nvec, vs, cfg.fftlen, h->offset, raw, s)))
+            return rc;
+        if ((rc = launch_nco_phase(raw, cn, nvec, vs, cfg.fftlen, h->binsize, h->sens, fhat, ckpt, kSeg, s)))
+            return rc;
+    }
+    if (!in_a) {
+        if ((rc = launch_mix_agc(iq, iq_stride, cn, n1, cfg.fftlen, fhat, vs, ckpt, kSeg, h->sens,
+                                 cfg.stages, cfg.agc_nsamples, cfg.agc_reference, a_rows,
+                                 h->a_stride, s)))
+            return rc;
+    }
+    if ((rc = launch_corr(a_rows, h->a_stride, cn, n1, n1, h->d_taps_time, h->L, h->thresh, mask,
+                          h->mask_stride, nullptr, 0, s)))
+        return rc;
+    if ((rc = launch_detect(a_rows, h->a_stride, cn, n1, h->chunk, h->nsamples, h->d_taps_time,
+                            h->L, h->thresh, h->isps, h->mark_delay, mask, h->mask_stride, 0, 0,
+                            tags, h->max_tags, ntags, nullptr, d_status, s)))
+        return rc;
+    // corr_est covers n2 = whole chunks of its output multiple (the scheduler's view)
+    int n2 = 0;
+    while (n1 - n2 >= h->nsamples) {
+        int nn = n1 - n2;
+        nn = nn > h->chunk ? h->chunk : (nn / h->nsamples) * h->nsamples;
+        n2 += nn;
+    }
+    if ((rc = launch_msk_reset(h->d_state + c0, cn, h->mp.sps_half, s)))
+        return rc;
+    float2 *t_sym = h->taps_enabled ? h->t_sym.as<float2>() + (size_t)c0 * max_bits : nullptr;
+    float *t_err = h->taps_enabled ? h->t_err.as<float>() + (size_t)c0 * max_bits : nullptr;
+    float *t_mu = h->taps_enabled ? h->t_mu.as<float>() + (size_t)c0 * max_bits : nullptr;
+    float *t_soft = h->taps_enabled ? h->t_soft.as<float>() + (size_t)c0 * max_bits : nullptr;
+    // msk reads corr_est output 0: out0[k] = in[k - L] (history delay), zeros for k < L
+    return launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, nullptr, n2, 0, tags, h->max_tags,
+                      ntags, h->mp, h->d_state + c0, t_sym, t_err, t_mu, t_soft, bits,
+                      (size_t)max_bits, nbits, h->d_ncons + c0, 1, d_status, s);
+}
+
+static int demod_prepare(b200ais_demod *h, int n, int max_bits)
+{
+    if (n < 1 || n > h->max_samples) {
+        set_error("demod_work: nsamples %d outside [1, %d]", n, h->max_samples);
+        return B200AIS_E_INVALID;
+    }
+    if (max_bits < 1) {
+        set_error("demod_work: max_bits must be positive");
+        return B200AIS_E_INVALID;
+    }
+    if (h->taps_enabled) {
+        const size_t items = (size_t)h->channels * max_bits;
+        int rc;
+        if ((rc = h->t_sym.reserve(items * sizeof(float2))) || (rc = h->t_err.reserve(items * sizeof(float))) ||
+            (rc = h->t_mu.reserve(items * sizeof(float))) || (rc = h->t_soft.reserve(items * sizeof(float))))
+            return rc;
+    }
+    h->last_n = n;
+    h->last_max_bits = max_bits;
+    h->last_n1 = (h->cfg.stages & B200AIS_STAGE_FREQSYNC) ? (n / h->cfg.fftlen) * h->cfg.fftlen : n;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
+                                      int max_bits, int *nbits, b200ais_tag *tags, int *ntags,
+                                      void *stream)
+{
+    if (!h || !iq || !bits || !nbits) {
+        set_error("demod_work: null argument");
+        return B200AIS_E_INVALID;
+    }
+    int rc = demod_prepare(h, nsamples, max_bits);
+    if (rc)
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), s));
+    rc = demod_launch_group(h, 0, h->channels, reinterpret_cast<const float2 *>(iq), (size_t)nsamples,
+                            nsamples, 0, bits, max_bits, nbits, h->d_tags, h->d_ntags, h->d_status, s);
+    if (rc)
+        return rc;
+    if (tags)
+        B200_CU(cudaMemcpyAsync(tags, h->d_tags, sizeof(b200ais_tag) * (size_t)h->max_tags * h->channels,
+                                cudaMemcpyDeviceToDevice, s));
+    if (ntags)
+        B200_CU(cudaMemcpyAsync(ntags, h->d_ntags, sizeof(int) * (size_t)h->channels,
+                                cudaMemcpyDeviceToDevice, s));
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_status(b200ais_demod *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    int st[kMaxGroups + 1];
+    B200_CU(cudaMemcpy(st, h->d_status, sizeof(st), cudaMemcpyDeviceToHost));
+    for (int v : st)
+        if (v) {
+            set_error("demod kernel flagged status %d", v);
+            return v;
+        }
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
+                                  int max_bits, int *nbits, b200ais_tag *tags, int *ntags)
+{
+    if (!h || !iq || !bits || !nbits) {
+        set_error("demod_work: null argument");
+        return B200AIS_E_INVALID;
+    }
+    int rc = demod_prepare(h, nsamples, max_bits);
+    if (rc)
+        return rc;
+    const int C = h->channels, n = nsamples;
+    const bool direct = (h->cfg.stages & (B200AIS_STAGE_FREQSYNC | B200AIS_STAGE_AGC)) == 0;
+    if (!direct && !h->d_x)
+        B200_CU(cudaMalloc(&h->d_x, sizeof(float2) * (size_t)h->max_samples * C));
+    if (h->bits_cap < (size_t)max_bits * C) {
+        if (h->d_bits)
+            cudaFree(h->d_bits);
+        h->d_bits = nullptr;
+        h->bits_cap = 0;
+        B200_CU(cudaMalloc(&h->d_bits, (size_t)max_bits * C));
+        h->bits_cap = (size_t)max_bits * C;
+    }
+    B200_CU(cudaMemset(h->d_status, 0, sizeof(int) * (kMaxGroups + 1)));
+    // channel groups pipelined over streams: copy-in of group g+1 overlaps compute of group g
+    const int ngroups = C >= 64 ? kMaxGroups : 1;
+    for (int g = 0; g < ngroups; g++) {
+        const int c0 = (int)((long long)C * g / ngroups), c1 = (int)((long long)C * (g + 1) / ngroups);
+        const int cn = c1 - c0;
+        if (cn <= 0)
+            continue;
+        cudaStream_t s = h->streams[g];
+        const float2 *src = reinterpret_cast<const float2 *>(iq) + (size_t)c0 * n;
+        const float2 *dev_iq;
+        size_t dev_stride;
+        if (direct) {
+            float2 *a_rows = h->d_a + (size_t)c0 * h->a_stride + h->HP;
+            B200_CU(cudaMemcpy2DAsync(a_rows, h->a_stride * sizeof(float2), src, (size_t)n * sizeof(float2),
+                                      (size_t)n * sizeof(float2), cn, cudaMemcpyHostToDevice, s));
+            dev_iq = a_rows;
+            dev_stride = h->a_stride;
+        } else {
+            float2 *dx = h->d_x + (size_t)c0 * n;
+            B200_CU(cudaMemcpyAsync(dx, src, sizeof(float2) * (size_t)n * cn, cudaMemcpyHostToDevice, s));
+            dev_iq = dx;
+            dev_stride = (size_t)n;
+        }
+        rc = demod_launch_group(h, c0, cn, dev_iq, dev_stride, n, direct ? 1 : 0,
+                                h->d_bits + (size_t)c0 * max_bits, max_bits, h->d_nbits + c0,
+                                h->d_tags + (size_t)c0 * h->max_tags, h->d_ntags + c0,
+                                h->d_status + 1 + g, s);
+        if (rc)
+            return rc;
+        B200_CU(cudaMemcpyAsync(bits + (size_t)c0 * max_bits, h->d_bits + (size_t)c0 * max_bits,
+                                (size_t)max_bits * cn, cudaMemcpyDeviceToHost, s));
+        B200_CU(cudaMemcpyAsync(nbits + c0, h->d_nbits + c0, sizeof(int) * (size_t)cn,
+                                cudaMemcpyDeviceToHost, s));
+        if (tags)
+            B200_CU(cudaMemcpyAsync(tags + (size_t)c0 * h->max_tags, h->d_tags + (size_t)c0 * h->max_tags,
+                                    sizeof(b200ais_tag) * (size_t)h->max_tags * cn,
+                                    cudaMemcpyDeviceToHost, s));
+        if (ntags)
+            B200_CU(cudaMemcpyAsync(ntags + c0, h->d_ntags + c0, sizeof(int) * (size_t)cn,
+                                    cudaMemcpyDeviceToHost, s));
+    }
+    for (int g = 0; g < ngroups; g++)
+        B200_CU(cudaStreamSynchronize(h->streams[g]));
+    return b200ais_demod_status(h);
+}
+
+extern "C" int b200ais_demod_tap(b200ais_demod *h, int which, void **dev_ptr, size_t *row_items)
+{
+    if (!h || !dev_ptr || !row_items) {
+        set_error("demod_tap: null argument");
+        return B200AIS_E_INVALID;
+    }
+    const bool fs = h->cfg.stages & B200AIS_STAGE_FREQSYNC;
+    switch (which) {
+    case B200AIS_TAP_FHAT:
+        *dev_ptr = h->d_fhat;
+        *row_items = fs ? (size_t)(h->last_n1 / h->cfg.fftlen) : 0;
+        return B200AIS_OK;
+    case B200AIS_TAP_AGC:
+        *dev_ptr = h->d_a + h->HP;
+        *row_items = h->a_stride;
+        return B200AIS_OK;
+    case B200AIS_TAP_MASK:
+        *dev_ptr = h->d_mask;
+        *row_items = h->mask_stride;
+        return B200AIS_OK;
+    case B200AIS_TAP_SYM:
+    case B200AIS_TAP_ERR:
+    case B200AIS_TAP_MU:
+    case B200AIS_TAP_SOFT: {
+        if (!h->taps_enabled) {
+            set_error("demod_tap: call b200ais_demod_enable_taps(h, 1) before the work call");
+            return B200AIS_E_INVALID;
+        }
+        DevBuf *b = which == B200AIS_TAP_SYM ? &h->t_sym
+                    : which == B200AIS_TAP_ERR ? &h->t_err
+                    : which == B200AIS_TAP_MU  ? &h->t_mu
+                                               : &h->t_soft;
+        *dev_ptr = b->p;
+        *row_items = (size_t)h->last_max_bits;
+        return B200AIS_OK;
+    }
+    default:
+        set_error("demod_tap: unknown tap %d", which);
+        return B200AIS_E_INVALID;
+    }
+}
+
+extern "C" int b200ais_demod_read_tap(b200ais_demod *h, int which, void *dst, size_t dst_bytes)
+{
+    void *p = nullptr;
+    size_t row = 0;
+    int rc = b200ais_demod_tap(h, which, &p, &row);
+    if (rc)
+        return rc;
+    size_t item = which == B200AIS_TAP_AGC || which == B200AIS_TAP_SYM ? sizeof(float2)
+                  : which == B200AIS_TAP_MASK                          ? 1
+                                                                       : sizeof(float);
+    const size_t C = (size_t)h->channels;
+    if (which == B200AIS_TAP_FHAT) {
+        const size_t nvec = row, pitch = (size_t)std::max(h->nvec_max, 1);
+        if (dst_bytes < C * nvec * item) {
+            set_error("demod_read_tap: destination too small");
+            return B200AIS_E_INVALID;
+        }
+        B200_CU(cudaDeviceSynchronize());
+        if (nvec)
+            B200_CU(cudaMemcpy2D(dst, nvec * item, p, pitch * item, nvec * item, C, cudaMemcpyDeviceToHost));
+        return B200AIS_OK;
+    }
+    if (dst_bytes < C * row * item) {
+        set_error("demod_read_tap: destination too small (%zu < %zu)", dst_bytes, C * row * item);
+        return B200AIS_E_INVALID;
+    }
+    B200_CU(cudaDeviceSynchronize());
+    if (which == B200AIS_TAP_AGC) {
+        // strided rows: row pitch a_stride, pointer already past the zero history
+        B200_CU(cudaMemcpy2D(dst, row * item, p, row * item, (row - h->HP) * item, C, cudaMemcpyDeviceToHost));
+        return B200AIS_OK;
+    }
+    B200_CU(cudaMemcpy(dst, p, C * row * item, cudaMemcpyDeviceToHost));
+    return B200AIS_OK;
+}

@@ -1,0 +1,109 @@
+// internal.h -- shared declarations of libb200ais.so (not part of the C-ABI).
+//
+// Canonical arithmetic: every kernel is compiled with -fmad=false, so
+// a multiply-add is fused only where the source says fmaf()/__fmaf_rn(); division,
+// sqrt and float<->double conversions are the IEEE round-to-nearest CUDA defaults.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200ais.h"
+
+namespace b200ais {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+void count_launch(int n = 1);
+
+#define B200_CU(x)                                                              \
+    do {                                                                        \
+        cudaError_t e__ = (x);                                                  \
+        if (e__ != cudaSuccess)                                                 \
+            return ::b200ais::cuda_fail(e__, #x, __FILE__, __LINE__);           \
+    } while (0)
+
+#define B200_LAUNCH_CHECK(name)                                                 \
+    do {                                                                        \
+        ::b200ais::count_launch();                                              \
+        cudaError_t e__ = cudaGetLastError();                                   \
+        if (e__ != cudaSuccess)                                                 \
+            return ::b200ais::cuda_fail(e__, name, __FILE__, __LINE__);         \
+    } while (0)
+
+// Regenerated GNU Radio data tables, resident in global memory of the current device.
+struct Tables {
+    const float *mmse; // [129][8]  mmse_fir_interpolator taps
+    const float *atan; // [257]     gr::fast_atan2f
+    const float *sine; // [1024][2] gr::fxpt sine table {slope, intercept}
+};
+int get_tables(Tables *t);
+// FFT twiddles for length n on the current device: n/2 complex, W[k] = exp(-2 pi i k/n)
+// rounded from double, k = 0 and k = n/4 exact.  Cached per (device, n).
+int get_twiddles(int n, const float2 **tw);
+
+// status words written by kernels (device int, 0 = ok, else a B200AIS_E_* code)
+struct MskParams {
+    float sps_half; // d_sps
+    float gain, gain_omega, limit;
+    int osps;
+};
+
+// Per-channel loop state of msk_timing_recovery_cc (lib/msk_timing_recovery_cc_impl.h:37-46)
+struct MskState {
+    float mu, omega;
+    float dly1_re, dly1_im, dly2_re, dly2_im, diff1_re, diff1_im;
+    int div;
+    float prev_re, prev_im; // in[-1]
+    int pad;
+};
+
+// ---- launch wrappers (each returns B200AIS_OK or an error code) ----
+
+// G1 + A8 first half: square -> FFT -> shifted |.| -> argmax, one block per (vector, channel).
+// vstride: row pitch of the per-vector arrays (raw, fhat).
+// raw[c*vstride+b] = maxpos (j + offset/2) or -1 when no bin pair had energy > 0.
+int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nvec, int vstride,
+                         int fftlen, int offset, int *raw, cudaStream_t s);
+// A8 on caller-supplied spectra (stand-alone freqest block)
+int launch_freqest_spec(const float2 *spec, int channels, int nvec, int fftlen, int offset,
+                        int *raw, cudaStream_t s);
+// A8 second half for the stand-alone block: maxpos carry-over + Hz conversion
+int launch_freqest_resolve(const int *raw, int channels, int nvec, int fftlen, float binsize,
+                           float *out, cudaStream_t s);
+// G2 serial part: maxpos carry-over, Hz conversion and the NCO phase recurrence, one thread
+// per channel; phase checkpoints every `seg` samples, ckpt[(n/seg)*channels + c].
+int launch_nco_phase(const int *raw, int channels, int nvec, int vstride, int fftlen, float binsize,
+                     float sens, float *fhat, float *ckpt, int seg, cudaStream_t s);
+// G2 parallel part + G3: mix with the NCO and apply feedforward_agc_cc.
+// stages: B200AIS_STAGE_* mask.  out rows have `out_stride` items; out[c*out_stride + t].
+int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int fftlen,
+                   const float *fhat, int vstride, const float *ckpt, int seg, float sens, int stages,
+                   int agc_nsamples, float agc_reference, float2 *out, size_t out_stride,
+                   cudaStream_t s);
+// A3: sliding correlation, |.|^2 > thresh bitmask (+ optional correlator stream).
+// in rows: in[c*in_stride + t], t in [-(L), n) readable (zeros for history).
+// taps_time: [L] in time order g[m] (pairs with sample t-L+1+m).
+int launch_corr(const float2 *in, size_t in_stride, int channels, int n, int n_valid,
+                const float2 *taps_time, int L, float thresh, uint8_t *mask, size_t mask_stride,
+                float2 *corr_out, size_t corr_stride, cudaStream_t s);
+// A4: the serial detector, one warp per channel.
+int launch_detect(const float2 *in, size_t in_stride, int channels, int n_total, int chunk,
+                  int nsamples_mult, const float2 *taps_time, int L, float thresh, int isps,
+                  unsigned mark_delay, const uint8_t *mask, size_t mask_stride, uint64_t base_offset,
+                  int two_ports, b200ais_tag *tags, int max_tags, int *ntags, int *n2_out,
+                  int *status, cudaStream_t s);
+// A7 (+ G4-G6, A9 when bits != nullptr): timing loop, one thread per channel.
+int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
+               const int *ninput_items_dev, int ninput_items_const, uint64_t nitems_read,
+               const b200ais_tag *tags, int max_tags, const int *ntags, MskParams p, MskState *state,
+               float2 *out, float *out_err, float *out_mu, float *out_soft, uint8_t *bits,
+               size_t out_stride, int *nproduced, int *nconsumed, int require_unbounded,
+               int *status, cudaStream_t s);
+int launch_msk_reset(MskState *state, int channels, float sps_half, cudaStream_t s);
+int launch_msk_set_omega(MskState *state, int channels, float omega, cudaStream_t s);
+int launch_invert(const uint8_t *in, uint8_t *out, size_t n, cudaStream_t s);
+int launch_copy_delay(const float2 *in, size_t in_stride, float2 *out, size_t out_stride,
+                      int channels, int n, cudaStream_t s);
+
+} // namespace b200ais

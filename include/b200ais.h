@@ -1,0 +1,226 @@
+/*
+ * b200ais.h -- C-ABI of libb200ais.so: the gr-ais IQ-demod hot path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Every entry point takes plain pointers and
+ * sizes (no C++ or torch types) and replaces one interface of the reference
+ * (bistromath/gr-ais @ 2162103; paths below are relative to /root/reference):
+ *
+ *   b200ais_corr_est_*   gr::ais::corr_est_cc            include/ais/corr_est_cc.h:85-107,
+ *                                                        lib/corr_est_cc_impl.cc:48-117 (ctor),
+ *                                                        :132-162 (set_symbols), :164-279 (work)
+ *   b200ais_msk_*        gr::ais::msk_timing_recovery_cc include/ais/msk_timing_recovery_cc.h:46-70,
+ *                                                        lib/msk_timing_recovery_cc_impl.cc:45-96
+ *                                                        (ctor/setters), :98-105 (forecast),
+ *                                                        :107-206 (general_work)
+ *   b200ais_freqest_*    gr::ais::freqest                include/ais/freqest.h:37-50,
+ *                                                        lib/freqest_impl.cc:41-48, :57-88 (work)
+ *   b200ais_invert_work  gr::ais::invert                 include/ais/invert.h:37-50,
+ *                                                        lib/invert_impl.cc:54-68 (work)
+ *   b200ais_demod_*      ais_demod hier-block            python/ais_demod.py:21-56 with
+ *                        + square_and_fft_sync_cc        python/gmsk_sync.py:14-37 fused in
+ *
+ * The *_work functions mirror one GNU Radio work()/general_work() call, batched
+ * over `channels` independent streams (the GR adapter calls with channels = 1).
+ * Host-pointer variants copy to/from the device inside the call; *_dev variants
+ * take device pointers and a cudaStream_t (as void*) and do not synchronise.
+ *
+ * Layout: channel-major [channels][stride] rows of interleaved (re, im) float32
+ * (= gr_complex); strides are in items (complex samples / bytes), rows 16-byte
+ * aligned for the device variants.
+ *
+ * All functions return B200AIS_OK (0) or a negative B200AIS_E_* code; the text of
+ * the last error on the calling thread is b200ais_last_error().  There is no CPU
+ * fallback: without a usable sm_100 device every compute call fails with
+ * B200AIS_E_CUDA.
+ */
+#ifndef B200AIS_H
+#define B200AIS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200AIS_API
+#else
+#define B200AIS_API __attribute__((visibility("default")))
+#endif
+
+enum {
+    B200AIS_OK = 0,
+    B200AIS_E_INVALID = -1,      /* bad argument */
+    B200AIS_E_RANGE = -2,        /* the reference throws std::out_of_range here */
+    B200AIS_E_CUDA = -3,         /* CUDA runtime error / no device */
+    B200AIS_E_NOMEM = -4,
+    B200AIS_E_TAG_OVERFLOW = -5, /* more tags than max_tags on some channel */
+    B200AIS_E_INTERP = -6,       /* mmse interpolator index out of [0,128] (reference: runtime_error) */
+    B200AIS_E_OUT_OVERFLOW = -7  /* an output row was too small */
+};
+
+/* stream-tag keys emitted by corr_est_cc (lib/corr_est_cc_impl.cc:213-256) */
+enum {
+    B200AIS_TAG_CORR_START = 0,
+    B200AIS_TAG_PHASE_EST = 1,
+    B200AIS_TAG_TIME_EST = 2,
+    B200AIS_TAG_CORR_EST = 3
+};
+
+/* POD stand-in for gr::tag_t {offset, key, pmt::from_double(value), srcid} */
+typedef struct b200ais_tag {
+    uint64_t offset; /* absolute item offset on corr_est output `port` */
+    int32_t key;     /* B200AIS_TAG_* */
+    int32_t port;    /* 0, or 1 for the debug copies on the optional 2nd output */
+    double value;
+} b200ais_tag;
+
+/* ---------------------------------------------------------------- library */
+B200AIS_API int b200ais_version(void);
+B200AIS_API const char *b200ais_last_error(void);
+B200AIS_API int b200ais_device_count(int *count);
+B200AIS_API int b200ais_set_device(int device);
+/* pinned host memory, so the host-pointer variants overlap copies with kernels */
+B200AIS_API int b200ais_host_alloc(void **ptr, size_t bytes);
+B200AIS_API int b200ais_host_free(void *ptr);
+/* number of kernels this library has launched on the calling process (bench bookkeeping) */
+B200AIS_API uint64_t b200ais_launch_count(void);
+
+/* ------------------------------------------------------------ corr_est_cc */
+typedef struct b200ais_corr_est b200ais_corr_est;
+
+/* corr_est_cc::make(symbols, sps, mark_delay, threshold) for `channels` streams */
+B200AIS_API int b200ais_corr_est_create(b200ais_corr_est **h, const float *symbols_iq, int nsymbols,
+                                        float sps, unsigned mark_delay, float threshold,
+                                        int channels);
+B200AIS_API int b200ais_corr_est_destroy(b200ais_corr_est *h);
+/* set_symbols(): taps replaced verbatim, threshold unchanged (lib/corr_est_cc_impl.cc:132-162) */
+B200AIS_API int b200ais_corr_est_set_symbols(b200ais_corr_est *h, const float *symbols_iq,
+                                             int nsymbols);
+/* symbols(): the stored taps (conj-reversed after the ctor), *n items */
+B200AIS_API int b200ais_corr_est_symbols(const b200ais_corr_est *h, float *out_iq, int cap, int *n);
+B200AIS_API int b200ais_corr_est_output_multiple(const b200ais_corr_est *h); /* fft_filter nsamples */
+B200AIS_API int b200ais_corr_est_history(const b200ais_corr_est *h);         /* nsymbols + 1 */
+B200AIS_API unsigned b200ais_corr_est_mark_delay(const b200ais_corr_est *h);
+B200AIS_API float b200ais_corr_est_threshold(const b200ais_corr_est *h);     /* d_thresh */
+
+/* One work() call.  in: [channels][in_stride], each row noutput_items + nsymbols items
+ * (history first, exactly what GNU Radio hands work()).  out0 (nullable): the delayed
+ * pass-through; out1 (nullable): the correlator output, both [channels][out_stride].
+ * tags: [channels][max_tags], ntags: [channels]. */
+B200AIS_API int b200ais_corr_est_work(b200ais_corr_est *h, int noutput_items, const float *in,
+                                      size_t in_stride, uint64_t nitems_written, float *out0,
+                                      float *out1, size_t out_stride, b200ais_tag *tags,
+                                      int max_tags, int *ntags);
+B200AIS_API int b200ais_corr_est_work_dev(b200ais_corr_est *h, int noutput_items, const float *in,
+                                          size_t in_stride, uint64_t nitems_written, float *out0,
+                                          float *out1, size_t out_stride, b200ais_tag *tags,
+                                          int max_tags, int *ntags, void *stream);
+
+/* ------------------------------------------------ msk_timing_recovery_cc */
+typedef struct b200ais_msk b200ais_msk;
+
+B200AIS_API int b200ais_msk_create(b200ais_msk **h, float sps, float gain, float limit, int osps,
+                                   int channels);
+B200AIS_API int b200ais_msk_destroy(b200ais_msk *h);
+B200AIS_API int b200ais_msk_set_gain(b200ais_msk *h, float gain);
+B200AIS_API float b200ais_msk_get_gain(const b200ais_msk *h);
+B200AIS_API int b200ais_msk_set_limit(b200ais_msk *h, float limit);
+B200AIS_API float b200ais_msk_get_limit(const b200ais_msk *h);
+B200AIS_API int b200ais_msk_set_sps(b200ais_msk *h, float sps);
+B200AIS_API float b200ais_msk_get_sps(const b200ais_msk *h); /* returns sps/2, as the reference */
+B200AIS_API int b200ais_msk_forecast(const b200ais_msk *h, int noutput_items);
+B200AIS_API int b200ais_msk_reset(b200ais_msk *h); /* back to the freshly constructed loop state */
+
+/* One general_work() call.  in: [channels][in_stride] with ninput_items valid items per
+ * row; tags: [channels][max_tags] (time_est tags on port 0 are used, others ignored),
+ * ntags: [channels]; out: [channels][out_stride] complex, out_err/out_mu (nullable) float.
+ * nproduced / nconsumed: [channels] (the return value and consume_each argument). */
+B200AIS_API int b200ais_msk_general_work(b200ais_msk *h, int noutput_items, int ninput_items,
+                                         const float *in, size_t in_stride, uint64_t nitems_read,
+                                         const b200ais_tag *tags, int max_tags, const int *ntags,
+                                         float *out, float *out_err, float *out_mu,
+                                         size_t out_stride, int *nproduced, int *nconsumed);
+B200AIS_API int b200ais_msk_general_work_dev(b200ais_msk *h, int noutput_items, int ninput_items,
+                                             const float *in, size_t in_stride,
+                                             uint64_t nitems_read, const b200ais_tag *tags,
+                                             int max_tags, const int *ntags, float *out,
+                                             float *out_err, float *out_mu, size_t out_stride,
+                                             int *nproduced, int *nconsumed, void *stream);
+
+/* ---------------------------------------------------------------- freqest */
+typedef struct b200ais_freqest b200ais_freqest;
+
+B200AIS_API int b200ais_freqest_create(b200ais_freqest **h, float sample_rate, int data_rate,
+                                       int fftlen, int channels);
+B200AIS_API int b200ais_freqest_destroy(b200ais_freqest *h);
+/* One work() call: spec [channels][noutput_items*fftlen] complex, out [channels][noutput_items] */
+B200AIS_API int b200ais_freqest_work(b200ais_freqest *h, int noutput_items, const float *spec,
+                                     float *out);
+B200AIS_API int b200ais_freqest_work_dev(b200ais_freqest *h, int noutput_items, const float *spec,
+                                         float *out, void *stream);
+
+/* ----------------------------------------------------------------- invert */
+B200AIS_API int b200ais_invert_work(const uint8_t *in, uint8_t *out, size_t nitems);
+B200AIS_API int b200ais_invert_work_dev(const uint8_t *in, uint8_t *out, size_t nitems,
+                                        void *stream);
+
+/* ---------------------------------------------- the fused ais_demod chain */
+enum { B200AIS_STAGE_FREQSYNC = 1, B200AIS_STAGE_AGC = 2 };
+
+typedef struct b200ais_demod_config {
+    float sample_rate;   /* samples_per_symbol * bits_per_sec (python/ais_demod.py:30) */
+    int data_rate;       /* bits_per_sec */
+    int fftlen;          /* options["fftlen"] (python/radio.py:60) */
+    int agc_nsamples;    /* feedforward_agc_cc(512, 2) (python/ais_demod.py:35) */
+    float agc_reference;
+    float sps;
+    unsigned mark_delay; /* 1 (python/ais_demod.py:41) */
+    float threshold;     /* 0.9 (python/ais_demod.py:42) */
+    float gain;          /* clockrec_gain */
+    float limit;         /* omega_relative_limit */
+    int osps;            /* 1 */
+    int corr_chunk;      /* corr_est work-chunk; 0 = largest multiple of nsamples <= 24576 */
+    int stages;          /* B200AIS_STAGE_* mask; corr_est, msk and the bit tail always run */
+} b200ais_demod_config;
+
+typedef struct b200ais_demod b200ais_demod;
+
+B200AIS_API int b200ais_demod_default_config(b200ais_demod_config *cfg);
+B200AIS_API int b200ais_demod_create(b200ais_demod **h, const b200ais_demod_config *cfg,
+                                     const float *symbols_iq, int nsymbols, int channels,
+                                     int max_samples, int max_tags);
+B200AIS_API int b200ais_demod_destroy(b200ais_demod *h);
+B200AIS_API int b200ais_demod_max_bits(const b200ais_demod *h, int nsamples);
+/* One record per channel, every block freshly constructed (ais_demod on a new stream).
+ * iq: [channels][nsamples] complex; bits: [channels][max_bits] unpacked 0/1 bytes;
+ * nbits: [channels]; tags (nullable): [channels][max_tags]; ntags (nullable): [channels]. */
+B200AIS_API int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
+                                   int max_bits, int *nbits, b200ais_tag *tags, int *ntags);
+B200AIS_API int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsamples,
+                                       uint8_t *bits, int max_bits, int *nbits, b200ais_tag *tags,
+                                       int *ntags, void *stream);
+/* after a *_dev call has completed: 0 or the B200AIS_E_* a kernel flagged */
+B200AIS_API int b200ais_demod_status(b200ais_demod *h);
+
+/* Device pointers to the chain's intermediate streams of the last work call (parity
+ * tests and profiling).  which: */
+enum {
+    B200AIS_TAP_FHAT = 0,  /* float  [channels][nsamples/fftlen]  freqest output (Hz) */
+    B200AIS_TAP_AGC = 1,   /* complex[channels][row]              corr_est input stream */
+    B200AIS_TAP_SYM = 2,   /* complex[channels][max_bits]         msk out0 */
+    B200AIS_TAP_ERR = 3,   /* float  [channels][max_bits]         msk out1 */
+    B200AIS_TAP_MU = 4,    /* float  [channels][max_bits]         msk out2 */
+    B200AIS_TAP_SOFT = 5,  /* float  [channels][max_bits]         quadrature_demod output */
+    B200AIS_TAP_MASK = 6   /* uint8  [channels][row/8]            corr_est |corr|^2 > thresh bitmask */
+};
+B200AIS_API int b200ais_demod_enable_taps(b200ais_demod *h, int enable);
+B200AIS_API int b200ais_demod_tap(b200ais_demod *h, int which, void **dev_ptr, size_t *row_items);
+/* copy a tap to host: dst holds channels*row_items items of the tap's type */
+B200AIS_API int b200ais_demod_read_tap(b200ais_demod *h, int which, void *dst, size_t dst_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AIS_H */

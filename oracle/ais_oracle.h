@@ -1,0 +1,186 @@
+/*
+ * ais_oracle.h -- CPU restatement ("oracle") of the gr-ais IQ-demod hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (gr-ais_b200/, the
+ * C-ABI library, bench.py's GPU arm) may include, link or call this.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs use it, and only as the checker / the CPU arm.
+ *
+ * PARITY UNPINNED: the reference (bistromath/gr-ais @ 2162103) ships no tests,
+ * fixtures or golden vectors (lib/qa_ais.cc:30-36 is an empty suite) and cannot
+ * be built here (every hot-path source includes GNU Radio 3.8 / VOLK headers,
+ * which are absent).  This file restates
+ *   [R] the gr-ais C++ it can read:  lib/corr_est_cc_impl.cc:48-117,164-279,
+ *       lib/msk_timing_recovery_cc_impl.cc:45-105,107-206,
+ *       lib/freqest_impl.cc:41-48,57-88, lib/invert_impl.cc:54-68,
+ *       wiring python/ais_demod.py:28-56, python/gmsk_sync.py:22-37;
+ *   [G] the GNU Radio 3.8 blocks between them, from their published
+ *       algorithms.
+ * It is pinned by first-principles known-answer tests (tests/test_oracle_*.py)
+ * and float64 truth versions of each stage, not by reference vectors.
+ *
+ * Canonical arithmetic (DESIGN.md "Canonical arithmetic"): IEEE-754 binary32,
+ * round-to-nearest-even, no implicit contraction (-ffp-contract=off); fused
+ * multiply-adds appear only where written as fmaf().
+ */
+#ifndef AIS_ORACLE_H
+#define AIS_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { AO_TAG_CORR_START = 0, AO_TAG_PHASE_EST = 1, AO_TAG_TIME_EST = 2, AO_TAG_CORR_EST = 3 };
+
+typedef struct ao_tag {
+    uint64_t offset; /* absolute item offset in corr_est output 0 */
+    int32_t key;     /* AO_TAG_* */
+    int32_t port;    /* output port the tag was added to (0, or 1 for the debug copies) */
+    double value;    /* pmt::from_double payload */
+} ao_tag;
+
+/* ---- tables (regenerated GNU Radio data, the .inc files under oracle/tables) ---- */
+const float *ao_mmse_taps(void);   /* [129][8] */
+const float *ao_atan_table(void);  /* [257]    */
+const float *ao_sine_table(void);  /* [1024][2] */
+
+/* ---- scalar helpers ---- */
+float ao_fast_atan2f(float y, float x);
+float ao_hypotf(float re, float im);
+float ao_branchless_clip(float x, float clip);
+int32_t ao_float_to_fixed(float x);
+void ao_fxpt_sincos(int32_t angle, float *s, float *c);
+float ao_agc_envelope(float re, float im);
+
+/* ---- A0 / G7: preamble template ---- */
+/* gmsk_mod(sps, bt) applied to packed bytes (MSB first), as modulate_vector_bc
+ * does (python/ais_demod.py:36-38).  out_iq holds 8*nbytes*sps complex. */
+int ao_gmsk_template_packed(const uint8_t *bytes, int nbytes, int sps, float bt, float *out_iq);
+/* same modulator fed with unpacked bits (north-star 24-bit template). */
+int ao_gmsk_template_bits(const uint8_t *bits, int nbits, int sps, float bt, float *out_iq);
+void ao_firdes_gaussian(double gain, double spb, double bt, int ntaps, float *taps);
+
+/* ---- G1: square, FFT, shift ---- */
+void ao_square(const float *x, float *out, int n);
+int ao_fft_forward(const float *in, float *out, int n); /* radix-2 DIT, canonical order */
+void ao_fft_shift(const float *in, float *out, int n);
+
+/* ---- A8: freqest ---- */
+typedef struct ao_freqest {
+    int offset;
+    float binsize;
+    int fftlen;
+} ao_freqest;
+void ao_freqest_init(ao_freqest *f, float sample_rate, int data_rate, int fftlen);
+/* one work() call over nvec input vectors; returns nvec.  maxpos_out (optional) */
+int ao_freqest_work(const ao_freqest *f, const float *spec, int nvec, float *out, int *maxpos_out);
+
+/* ---- G2: repeat + frequency_modulator_fc + mix ---- */
+/* phase: NCO state carried across calls. freq[b] applies to samples [b*rep,(b+1)*rep) */
+void ao_nco_mix(float *phase, float sensitivity, const float *freq, int rep, const float *x, int n,
+                float *out);
+
+/* ---- G3: feedforward_agc_cc ---- */
+/* in holds n + nsamples - 1 items (history first), out n items. */
+void ao_agc_work(const float *in, int n, int nsamples, float reference, float *out);
+
+/* ---- A1-A4: corr_est_cc ---- */
+typedef struct ao_corr_est {
+    float *taps; /* [L] complex: ctor stores reverse(conj(symbols)); set_symbols stores verbatim */
+    int L;
+    float sps;
+    unsigned mark_delay;
+    float thresh;
+    int nsamples; /* fft_filter block size = output multiple */
+} ao_corr_est;
+int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, unsigned mark_delay,
+                     float threshold);
+void ao_corr_est_set_symbols(ao_corr_est *c, const float *symbols, int L);
+void ao_corr_est_free(ao_corr_est *c);
+/* One work() call.  in holds n+L items (history first).  corr/mag may be NULL.
+ * two_ports != 0 also emits the port-1 debug tags.  Returns n; *ntags = tags written
+ * (tags beyond max_tags are counted but dropped). */
+int ao_corr_est_work(const ao_corr_est *c, int n, const float *in, uint64_t nitems_written,
+                     float *out0, float *corr, float *mag, int two_ports, ao_tag *tags,
+                     int max_tags, int *ntags);
+
+/* ---- A5-A7: msk_timing_recovery_cc ---- */
+typedef struct ao_msk {
+    float sps; /* d_sps = sps/2 */
+    float gain, gain_omega, limit;
+    float mu, omega;
+    float dly1_re, dly1_im, dly2_re, dly2_im, diff1_re, diff1_im;
+    int div;
+    int osps;
+    float prev_re, prev_im; /* in[-1]: last consumed item of the previous call (0 at start) */
+} ao_msk;
+int ao_msk_init(ao_msk *m, float sps, float gain, float limit, int osps); /* <0 on out_of_range */
+int ao_msk_forecast(const ao_msk *m, int noutput_items);
+/* One general_work() call.  tags: time_est tags (any order of keys is filtered; offsets absolute),
+ * nitems_read: absolute offset of in[0].  Returns items produced; *consumed = consume_each arg. */
+int ao_msk_general_work(ao_msk *m, int noutput_items, int ninput_items, const float *in,
+                        uint64_t nitems_read, const ao_tag *tags, int ntags, float *out,
+                        float *out_err, float *out_mu, int *consumed);
+
+/* ---- G4-G6 + A9: demod tail ---- */
+/* prev: v[-1] (2 floats, updated).  Returns soft output y[k] = gain*fast_atan2f(...) */
+void ao_quad_demod(float *prev, const float *in, int n, float gain, float *out);
+void ao_binary_slicer(const float *in, int n, uint8_t *out);
+void ao_diff_decoder(uint8_t *prev, const uint8_t *in, int n, unsigned modulus, uint8_t *out);
+void ao_invert(const uint8_t *in, int n, uint8_t *out);
+
+/* ---- the ais_demod chain over one record from fresh state ---- */
+enum { AO_STAGE_FREQSYNC = 1, AO_STAGE_AGC = 2 };
+typedef struct ao_chain_cfg {
+    float sample_rate;   /* 48000 */
+    int data_rate;       /* 9600 */
+    int fftlen;          /* 1024 */
+    int agc_nsamples;    /* 512 */
+    float agc_reference; /* 2 */
+    float sps;           /* 5 */
+    unsigned mark_delay; /* 1 */
+    float threshold;     /* 0.9 */
+    float gain;          /* 0.04 */
+    float limit;         /* 0.01 */
+    int osps;            /* 1 */
+    int corr_chunk;      /* corr_est work-chunk (0 = largest multiple of nsamples <= 24576) */
+    int stages;          /* AO_STAGE_* mask; corr_est, msk and the bit tail always run */
+} ao_chain_cfg;
+
+typedef struct ao_chain_out {
+    /* required */
+    uint8_t *bits;
+    int max_bits;
+    int nbits;
+    ao_tag *tags;
+    int max_tags;
+    int ntags;
+    /* optional taps into the chain (NULL to skip) */
+    float *fhat;  /* [N/fftlen] */
+    float *mixed; /* [N1] complex */
+    float *agc;   /* [N1] complex */
+    float *corr;  /* [N2] complex */
+    float *mag;   /* [N2] */
+    float *sym;   /* [nbits] complex */
+    float *err;   /* [nbits] */
+    float *mu;    /* [nbits] */
+    float *soft;  /* [nbits] */
+    int n1, n2;   /* samples out of the AGC / processed by corr_est */
+    int consumed; /* msk consume_each */
+} ao_chain_out;
+
+int ao_default_corr_chunk(int L);
+int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x, int n,
+                   ao_chain_out *out);
+/* batch over channels with OpenMP; x is [C][n] complex, bits [C][max_bits], nbits [C],
+ * tags [C][max_tags], ntags [C].  Returns 0 or the first negative status. */
+int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x,
+                         int channels, int n, uint8_t *bits, int max_bits, int *nbits,
+                         ao_tag *tags, int max_tags, int *ntags, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
