@@ -223,6 +223,16 @@ class ais_demod:
                                                int(max_bits), B.ptr(nbits_ptr), B.ptr(tags_ptr),
                                                B.ptr(ntags_ptr), stream))
 
+    def profile(self, on=True):
+        B.check(B.lib().b200ais_demod_profile(self._h, 1 if on else 0))
+
+    def stage_ms(self):
+        """(dict stage -> summed ms, calls) since profiling was enabled / last read."""
+        ms = (C.c_double * 6)()
+        calls = C.c_int(0)
+        B.check(B.lib().b200ais_demod_stage_ms(self._h, ms, C.byref(calls)))
+        return dict(zip(B.STAGE_NAMES, list(ms))), calls.value
+
     def status(self):
         B.check(B.lib().b200ais_demod_status(self._h))
 

@@ -39,8 +39,9 @@ EXPORTS = [
     "b200ais_demod_default_config", "b200ais_demod_create", "b200ais_demod_destroy",
     "b200ais_demod_max_bits", "b200ais_demod_work", "b200ais_demod_work_dev",
     "b200ais_demod_status", "b200ais_demod_enable_taps", "b200ais_demod_tap",
-    "b200ais_demod_read_tap",
+    "b200ais_demod_read_tap", "b200ais_demod_profile", "b200ais_demod_stage_ms",
 ]
+STAGE_NAMES = ["sqfft_freqest", "nco_phase", "mix_agc", "corr", "detect", "msk"]
 
 
 class DemodConfig(C.Structure):
@@ -128,6 +129,8 @@ def lib():
     L.b200ais_demod_enable_taps.argtypes = [vp, i]
     L.b200ais_demod_tap.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz)]
     L.b200ais_demod_read_tap.argtypes = [vp, i, vp, sz]
+    L.b200ais_demod_profile.argtypes = [vp, i]
+    L.b200ais_demod_stage_ms.argtypes = [vp, vp, vp]
     _lib = L
     return L
 

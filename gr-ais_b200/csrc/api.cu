@@ -686,6 +686,10 @@ struct b200ais_demod {
     cudaEvent_t done[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
     bool taps_enabled = false;
     DevBuf t_sym, t_err, t_mu, t_soft;
+    bool profiling = false;
+    std::vector<std::vector<cudaEvent_t>> ev_used, ev_free; // 7 events per profiled call
+    double stage_ms[B200AIS_STAGE_T_COUNT] = { 0, 0, 0, 0, 0, 0 };
+    int prof_calls = 0;
     int last_n = 0, last_max_bits = 0, last_n1 = 0;
 };
 
@@ -850,6 +854,10 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
     h->t_err.release();
     h->t_mu.release();
     h->t_soft.release();
+    for (auto *pool : { &h->ev_used, &h->ev_free })
+        for (auto &set : *pool)
+            for (auto e : set)
+                cudaEventDestroy(e);
     delete h;
     return B200AIS_OK;
 }
@@ -880,25 +888,50 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     float *ckpt = h->d_ckpt + (size_t)c0 * std::max(h->nvec_max, 1) * (cfg.fftlen / kSeg + 1);
     const int vs = std::max(h->nvec_max, 1); // row pitch of raw / fhat
     int rc;
+    std::vector<cudaEvent_t> *ev = nullptr;
+    if (h->profiling && cn == h->channels) {
+        if (h->ev_free.empty()) {
+            std::vector<cudaEvent_t> set(B200AIS_STAGE_T_COUNT + 1);
+            for (auto &e : set)
+                B200_CU(cudaEventCreate(&e));
+            h->ev_free.push_back(set);
+        }
+        h->ev_used.push_back(h->ev_free.back());
+        h->ev_free.pop_back();
+        ev = &h->ev_used.back();
+        B200_CU(cudaEventRecord((*ev)[0], s));
+    }
+#define B200_MARK(k)                                                     \
+    do {                                                                 \
+        if (ev)                                                          \
+            B200_CU(cudaEventRecord((*ev)[(k) + 1], s));                 \
+    } while (0)
     if (fs) {
         if ((rc = launch_sqfft_freqest(iq, iq_stride, cn, nvec, vs, cfg.fftlen, h->offset, raw, s)))
             return rc;
+    }
+    B200_MARK(B200AIS_STAGE_T_SQFFT);
+    if (fs) {
         if ((rc = launch_nco_phase(raw, cn, nvec, vs, cfg.fftlen, h->binsize, h->sens, fhat, ckpt, kSeg, s)))
             return rc;
     }
+    B200_MARK(B200AIS_STAGE_T_NCO);
     if (!in_a) {
         if ((rc = launch_mix_agc(iq, iq_stride, cn, n1, cfg.fftlen, fhat, vs, ckpt, kSeg, h->sens,
                                  cfg.stages, cfg.agc_nsamples, cfg.agc_reference, a_rows,
                                  h->a_stride, s)))
             return rc;
     }
+    B200_MARK(B200AIS_STAGE_T_MIXAGC);
     if ((rc = launch_corr(a_rows, h->a_stride, cn, n1, n1, h->d_taps_time, h->L, h->thresh, mask,
                           h->mask_stride, nullptr, 0, s)))
         return rc;
+    B200_MARK(B200AIS_STAGE_T_CORR);
     if ((rc = launch_detect(a_rows, h->a_stride, cn, n1, h->chunk, h->nsamples, h->d_taps_time,
                             h->L, h->thresh, h->isps, h->mark_delay, mask, h->mask_stride, 0, 0,
                             tags, h->max_tags, ntags, nullptr, d_status, s)))
         return rc;
+    B200_MARK(B200AIS_STAGE_T_DETECT);
     // corr_est covers n2 = whole chunks of its output multiple (the scheduler's view)
     int n2 = 0;
     while (n1 - n2 >= h->nsamples) {
@@ -913,9 +946,47 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     float *t_mu = h->taps_enabled ? h->t_mu.as<float>() + (size_t)c0 * max_bits : nullptr;
     float *t_soft = h->taps_enabled ? h->t_soft.as<float>() + (size_t)c0 * max_bits : nullptr;
     // msk reads corr_est output 0: out0[k] = in[k - L] (history delay), zeros for k < L
-    return launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, nullptr, n2, 0, tags, h->max_tags,
-                      ntags, h->mp, h->d_state + c0, t_sym, t_err, t_mu, t_soft, bits,
-                      (size_t)max_bits, nbits, h->d_ncons + c0, 1, d_status, s);
+    rc = launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, nullptr, n2, 0, tags, h->max_tags,
+                    ntags, h->mp, h->d_state + c0, t_sym, t_err, t_mu, t_soft, bits,
+                    (size_t)max_bits, nbits, h->d_ncons + c0, 1, d_status, s);
+    B200_MARK(B200AIS_STAGE_T_MSK);
+#undef B200_MARK
+    return rc;
+}
+
+extern "C" int b200ais_demod_profile(b200ais_demod *h, int enable)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    h->profiling = enable != 0;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_stage_ms(b200ais_demod *h, double *stage_ms, int *calls)
+{
+    if (!h || !stage_ms) {
+        set_error("demod_stage_ms: null argument");
+        return B200AIS_E_INVALID;
+    }
+    for (auto &set : h->ev_used) {
+        B200_CU(cudaEventSynchronize(set[B200AIS_STAGE_T_COUNT]));
+        for (int k = 0; k < B200AIS_STAGE_T_COUNT; k++) {
+            float ms = 0;
+            B200_CU(cudaEventElapsedTime(&ms, set[k], set[k + 1]));
+            h->stage_ms[k] += ms;
+        }
+        h->prof_calls++;
+        h->ev_free.push_back(set);
+    }
+    h->ev_used.clear();
+    for (int k = 0; k < B200AIS_STAGE_T_COUNT; k++) {
+        stage_ms[k] = h->stage_ms[k];
+        h->stage_ms[k] = 0;
+    }
+    if (calls)
+        *calls = h->prof_calls;
+    h->prof_calls = 0;
+    return B200AIS_OK;
 }
 
 static int demod_prepare(b200ais_demod *h, int n, int max_bits)

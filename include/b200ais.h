@@ -204,6 +204,21 @@ B200AIS_API int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int ns
 /* after a *_dev call has completed: 0 or the B200AIS_E_* a kernel flagged */
 B200AIS_API int b200ais_demod_status(b200ais_demod *h);
 
+/* Per-stage device timing of the *_dev chain (CUDA events around every launch, on the
+ * caller's stream).  stage_ms: sums over the work_dev calls since profiling was enabled
+ * or last read; index = B200AIS_STAGE_T_*.  Reading synchronises the recorded events. */
+enum {
+    B200AIS_STAGE_T_SQFFT = 0,  /* x^2 -> FFT -> freqest argmax */
+    B200AIS_STAGE_T_NCO = 1,    /* NCO phase recurrence */
+    B200AIS_STAGE_T_MIXAGC = 2, /* NCO mix + feedforward AGC */
+    B200AIS_STAGE_T_CORR = 3,   /* corr_est correlator (the dominant kernel) */
+    B200AIS_STAGE_T_DETECT = 4, /* corr_est detector */
+    B200AIS_STAGE_T_MSK = 5,    /* msk_timing_recovery + bit tail */
+    B200AIS_STAGE_T_COUNT = 6
+};
+B200AIS_API int b200ais_demod_profile(b200ais_demod *h, int enable);
+B200AIS_API int b200ais_demod_stage_ms(b200ais_demod *h, double *stage_ms, int *calls);
+
 /* Device pointers to the chain's intermediate streams of the last work call (parity
  * tests and profiling).  which: */
 enum {

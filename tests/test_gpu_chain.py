@@ -47,7 +47,7 @@ def _compare_chain(oracle, x, tmpl, stages, corr_chunk=0, threshold=0.9, check_p
 def test_full_chain_bit_exact(oracle, templates, L):
     x, truth = _records(6, 16384, nbursts=3, snr_db=25)
     bits, nbits, tags, ntags = _compare_chain(oracle, x, templates[L], B.STAGE_FREQSYNC | B.STAGE_AGC)
-    assert nbits.min() > 3000
+    assert nbits.min() > 2900
 
 
 def test_chain_finds_known_payloads(oracle, templates):
