@@ -228,7 +228,7 @@ class ais_demod:
 
     def stage_ms(self):
         """(dict stage -> summed ms, calls) since profiling was enabled / last read."""
-        ms = (C.c_double * 6)()
+        ms = (C.c_double * len(B.STAGE_NAMES))()
         calls = C.c_int(0)
         B.check(B.lib().b200ais_demod_stage_ms(self._h, ms, C.byref(calls)))
         return dict(zip(B.STAGE_NAMES, list(ms))), calls.value

@@ -41,7 +41,7 @@ EXPORTS = [
     "b200ais_demod_status", "b200ais_demod_enable_taps", "b200ais_demod_tap",
     "b200ais_demod_read_tap", "b200ais_demod_profile", "b200ais_demod_stage_ms",
 ]
-STAGE_NAMES = ["sqfft_freqest", "nco_phase", "mix_agc", "corr", "detect", "msk"]
+STAGE_NAMES = ["sqfft_freqest", "nco_phase", "mix_agc", "corr", "detect", "msk", "tail"]
 
 
 class DemodConfig(C.Structure):

@@ -447,9 +447,9 @@ extern "C" int b200ais_msk_general_work_dev(b200ais_msk *h, int noutput_items, i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), s));
     return launch_msk(reinterpret_cast<const float2 *>(in), in_stride, h->channels, noutput_items,
-                      nullptr, ninput_items, nitems_read, tags, max_tags, ntags, h->p, h->d_state,
-                      reinterpret_cast<float2 *>(out), out_err, out_mu, nullptr, nullptr, out_stride,
-                      nproduced, nconsumed, 0, h->d_status, s);
+                      ninput_items, nitems_read, tags, max_tags, ntags, h->p, h->d_state,
+                      reinterpret_cast<float2 *>(out), out_err, out_mu, out_stride, nproduced,
+                      nconsumed, 0, h->d_status, s);
 }
 
 extern "C" int b200ais_msk_general_work(b200ais_msk *h, int noutput_items, int ninput_items,
@@ -688,7 +688,7 @@ struct b200ais_demod {
     DevBuf t_sym, t_err, t_mu, t_soft;
     bool profiling = false;
     std::vector<std::vector<cudaEvent_t>> ev_used, ev_free; // 7 events per profiled call
-    double stage_ms[B200AIS_STAGE_T_COUNT] = { 0, 0, 0, 0, 0, 0 };
+    double stage_ms[B200AIS_STAGE_T_COUNT] = { 0, 0, 0, 0, 0, 0, 0 };
     int prof_calls = 0;
     int last_n = 0, last_max_bits = 0, last_n1 = 0;
 };
@@ -941,15 +941,18 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     }
     if ((rc = launch_msk_reset(h->d_state + c0, cn, h->mp.sps_half, s)))
         return rc;
-    float2 *t_sym = h->taps_enabled ? h->t_sym.as<float2>() + (size_t)c0 * max_bits : nullptr;
+    float2 *t_sym = h->t_sym.as<float2>() + (size_t)c0 * max_bits;
     float *t_err = h->taps_enabled ? h->t_err.as<float>() + (size_t)c0 * max_bits : nullptr;
     float *t_mu = h->taps_enabled ? h->t_mu.as<float>() + (size_t)c0 * max_bits : nullptr;
     float *t_soft = h->taps_enabled ? h->t_soft.as<float>() + (size_t)c0 * max_bits : nullptr;
     // msk reads corr_est output 0: out0[k] = in[k - L] (history delay), zeros for k < L
-    rc = launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, nullptr, n2, 0, tags, h->max_tags,
-                    ntags, h->mp, h->d_state + c0, t_sym, t_err, t_mu, t_soft, bits,
-                    (size_t)max_bits, nbits, h->d_ncons + c0, 1, d_status, s);
+    rc = launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, n2, 0, tags, h->max_tags, ntags,
+                    h->mp, h->d_state + c0, t_sym, t_err, t_mu, (size_t)max_bits, nbits,
+                    h->d_ncons + c0, 1, d_status, s);
     B200_MARK(B200AIS_STAGE_T_MSK);
+    if (!rc)
+        rc = launch_tail(t_sym, (size_t)max_bits, nbits, cn, max_bits, bits, (size_t)max_bits, t_soft, s);
+    B200_MARK(B200AIS_STAGE_T_TAIL);
 #undef B200_MARK
     return rc;
 }
@@ -999,10 +1002,15 @@ static int demod_prepare(b200ais_demod *h, int n, int max_bits)
         set_error("demod_work: max_bits must be positive");
         return B200AIS_E_INVALID;
     }
+    {
+        int rc = h->t_sym.reserve((size_t)h->channels * max_bits * sizeof(float2));
+        if (rc)
+            return rc;
+    }
     if (h->taps_enabled) {
         const size_t items = (size_t)h->channels * max_bits;
         int rc;
-        if ((rc = h->t_sym.reserve(items * sizeof(float2))) || (rc = h->t_err.reserve(items * sizeof(float))) ||
+        if ((rc = h->t_err.reserve(items * sizeof(float))) ||
             (rc = h->t_mu.reserve(items * sizeof(float))) || (rc = h->t_soft.reserve(items * sizeof(float))))
             return rc;
     }
@@ -1142,6 +1150,9 @@ extern "C" int b200ais_demod_tap(b200ais_demod *h, int which, void **dev_ptr, si
         *row_items = h->mask_stride;
         return B200AIS_OK;
     case B200AIS_TAP_SYM:
+        *dev_ptr = h->t_sym.p;
+        *row_items = (size_t)h->last_max_bits;
+        return B200AIS_OK;
     case B200AIS_TAP_ERR:
     case B200AIS_TAP_MU:
     case B200AIS_TAP_SOFT: {

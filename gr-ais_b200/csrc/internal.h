@@ -93,13 +93,15 @@ int launch_detect(const float2 *in, size_t in_stride, int channels, int n_total,
                   unsigned mark_delay, const uint8_t *mask, size_t mask_stride, uint64_t base_offset,
                   int two_ports, b200ais_tag *tags, int max_tags, int *ntags, int *n2_out,
                   int *status, cudaStream_t s);
-// A7 (+ G4-G6, A9 when bits != nullptr): timing loop, one thread per channel.
+// A7: the timing-loop recurrence, one lane per channel (symbols out).
 int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
-               const int *ninput_items_dev, int ninput_items_const, uint64_t nitems_read,
-               const b200ais_tag *tags, int max_tags, const int *ntags, MskParams p, MskState *state,
-               float2 *out, float *out_err, float *out_mu, float *out_soft, uint8_t *bits,
-               size_t out_stride, int *nproduced, int *nconsumed, int require_unbounded,
-               int *status, cudaStream_t s);
+               int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
+               const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
+               float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
+               int require_unbounded, int *status, cudaStream_t s);
+// G4-G6 + A9: quadrature demod -> slicer -> diff decoder -> invert on the symbol stream.
+int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int channels, int max_sym,
+                uint8_t *bits, size_t bits_stride, float *soft, cudaStream_t s);
 int launch_msk_reset(MskState *state, int channels, float sps_half, cudaStream_t s);
 int launch_msk_set_omega(MskState *state, int channels, float omega, cudaStream_t s);
 int launch_invert(const uint8_t *in, uint8_t *out, size_t n, cudaStream_t s);

@@ -38,16 +38,14 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
     return true;
 }
 
-constexpr int kMskChunk = 64;             // samples per prefetch chunk
-constexpr int kMskRing = 2 * kMskChunk;     // ring of two chunks per channel
-constexpr int kMskPitch = kMskRing + 2;     // float2 per ring row (keeps rows 16-byte aligned)
-constexpr int kMskLookahead = 40;           // issue the next chunk this many samples early
+constexpr int kMskChunk = 32;              // samples per prefetch chunk
+constexpr int kMskRing = 128;               // ring slots per channel (4 chunks)
+constexpr int kMskMirror = 8;               // slots 0..7 repeated after the ring: 8-sample reads never wrap
+constexpr int kMskPitch = kMskRing + kMskMirror + 1; // 137: lane stride 274 words -> conflict-free 64-bit LDS
+constexpr int kMskInner = 4;                // half-symbol steps between two warp votes
+constexpr int kMskNeed = 3 * kMskInner + 2 * kMskInner + 8; // samples a lane may touch in one inner block
+constexpr int kMskAhead = kMskNeed + 32;    // issue a chunk once a lane is this close to it
 
-__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem, int src_bytes)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
-}
 __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem, int src_bytes)
 {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -56,45 +54,39 @@ __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
 
-// One warp = 32 channels.  Lane l runs channel (warp*32 + l)'s loop; the input samples of
-// all 32 channels are staged in a shared-memory ring (two 64-sample chunks per channel)
-// that the warp fills cooperatively with cp.async, one coalesced 512-byte chunk per channel,
-// issued kMskLookahead samples before the first lane needs it.
-template <bool kTail>
+// The serial core of msk_timing_recovery_cc.  One warp = 32 channels, lane l runs channel
+// (warp*32 + l).  A channel's loop is a recurrence on (mu, omega, iidx, div, previous
+// interpolant), so its run time is (#half-symbols) x (latency of one step); everything that
+// is not on that recurrence (the bit tail) lives in k_tail.  Input samples are staged in a
+// shared-memory ring per channel, filled with cp.async 32 samples at a time, one coalesced
+// 256-byte row segment per channel, kMskAhead samples before the first lane needs them.
+template <bool kDebug>
 __global__ void __launch_bounds__(32)
-k_msk(const float2 *__restrict__ in, size_t in_stride, int channels,
-      int noutput_items, const int *__restrict__ ninput_dev, int ninput_const,
-      uint64_t nitems_read, const b200ais_tag *__restrict__ tags, int max_tags,
+k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput_items,
+      int ninput_items, uint64_t nitems_read, const b200ais_tag *__restrict__ tags, int max_tags,
       const int *__restrict__ ntags, MskParams p, MskState *__restrict__ state,
-      const float *__restrict__ g_mmse, const float *__restrict__ g_atan,
-      float2 *__restrict__ out, float *__restrict__ out_err,
-      float *__restrict__ out_mu, float *__restrict__ out_soft,
-      uint8_t *__restrict__ bits, size_t out_stride, int *__restrict__ nproduced,
+      const float *__restrict__ g_mmse, float2 *__restrict__ out, float *__restrict__ out_err,
+      float *__restrict__ out_mu, size_t out_stride, int *__restrict__ nproduced,
       int *__restrict__ nconsumed, int require_unbounded, int *__restrict__ status)
 {
-    __shared__ float s_mmse[129 * 8];
-    __shared__ float s_atan[257];
+    __shared__ __align__(16) float s_mmse[129 * 8];
     __shared__ __align__(16) float2 ring[32 * kMskPitch];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
     for (int i = lane; i < 129 * 8; i += 32)
         s_mmse[i] = g_mmse[i];
-    for (int i = lane; i < 257; i += 32)
-        s_atan[i] = g_atan[i];
     const int c0 = blockIdx.x * 32;
     const int c = c0 + lane;
     const bool live = c < channels;
     const int cc = live ? c : channels - 1; // dead lanes shadow the last channel, never store
 
-    const float2 *xin = in + (size_t)cc * in_stride;
     MskState st = state[cc];
-    const int ninput_items = ninput_dev ? ninput_dev[0] : ninput_const;
     int oidx = 0, iidx = 0;
     const int ninp = (int)((double)ninput_items - 3.0 * (double)p.sps_half); // :119
 
-    // ring preset: slots of the (virtual) chunk -1 are zero, in[-1] is the carried sample
+    // ring preset: the slots of the (virtual) chunks before 0 are zero, in[-1] is the carried item
     float2 *my = ring + lane * kMskPitch;
-    for (int k = kMskChunk; k < kMskRing; k++)
+    for (int k = 0; k < kMskRing + kMskMirror; k++)
         my[k] = make_float2(0.0f, 0.0f);
     my[kMskRing - 1] = make_float2(st.prev_re, st.prev_im);
     __syncwarp();
@@ -102,170 +94,144 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels,
     // time_est tags inside [read, read+ninp), in offset order (:125-130)
     const b200ais_tag *tg = tags ? tags + (size_t)cc * max_tags : nullptr;
     const int nt = (tags && ntags && ninp > 0) ? min(ntags[cc], max_tags) : 0;
-    auto next_tag = [&](int from) {
+    int thead = 0;
+    int tag_off = 0x7fffffff; // pending tag, relative to the read pointer
+    float tag_val = 0.0f;
+    auto fetch_tag = [&](int from) {
         int k = from;
+        tag_off = 0x7fffffff;
         while (k < nt) {
             const b200ais_tag t = tg[k];
             if (t.key == B200AIS_TAG_TIME_EST && t.port == 0 && t.offset >= nitems_read &&
-                t.offset < nitems_read + (uint64_t)ninp)
+                t.offset < nitems_read + (uint64_t)ninp) {
+                tag_off = (int)(t.offset - nitems_read);
+                tag_val = (float)t.value;
                 break;
+            }
             k++;
         }
-        return k;
+        thead = k;
     };
-    int thead = next_tag(0);
-    int tag_off = 0x7fffffff; // offset of the pending tag relative to the read pointer
-    float tag_val = 0.0f;
-    auto fetch_tag = [&]() {
-        if (thead < nt) {
-            const b200ais_tag t = tg[thead];
-            tag_off = (int)(t.offset - nitems_read);
-            tag_val = (float)t.value;
-        } else {
-            tag_off = 0x7fffffff;
-        }
-    };
-    fetch_tag();
+    fetch_tag(0);
+    const int tag_span = (int)ceilf(p.sps_half) + 1; // integer pre-test before the float compare
 
-    // demod-tail state (fresh per call: the chain processes one record per call)
-    float2 qprev = make_float2(0.0f, 0.0f);
-    unsigned bprev = 0;
-    const float qgain = 1.57079632679489661923f; // (float)(pi/2), python/ais_demod.py:48
-    unsigned pack = 0;
-
-    float2 *oc = out ? out + (size_t)cc * out_stride : nullptr;
-    float *oe = out_err ? out_err + (size_t)cc * out_stride : nullptr;
-    float *om = out_mu ? out_mu + (size_t)cc * out_stride : nullptr;
-    float *os = out_soft ? out_soft + (size_t)cc * out_stride : nullptr;
-    uint8_t *ob = bits ? bits + (size_t)cc * out_stride : nullptr;
-    const bool word_ok = kTail && ((out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(bits) & 3) == 0);
-
-    // 16-byte cp.async needs the even samples of a row on 16-byte boundaries
-    const bool row16 = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((in_stride & 1) == 0);
+    float2 *oc = out + (size_t)cc * out_stride;
+    float *oe = kDebug && out_err ? out_err + (size_t)cc * out_stride : nullptr;
+    float *om = kDebug && out_mu ? out_mu + (size_t)cc * out_stride : nullptr;
     const float2 *row0 = in + (size_t)c0 * in_stride;
+    const int rows = min(32, channels - c0);
 
-    int next_chunk = 0;     // next chunk index to issue for this lane's channel
-    bool inflight = false;  // warp-uniform: a cp.async group may still be pending
+    // conj(dly2^2) of the reference equals conj(previous v^2): d_dly_conj_1 and _2 are always
+    // assigned together (:194-195), so only the squared previous interpolant is carried.
+    float psq_re = st.dly2_re * st.dly2_re - st.dly2_im * st.dly2_im;
+    float psq_im = st.dly2_re * st.dly2_im + st.dly2_im * st.dly2_re;
+    float2 vlast = make_float2(st.dly1_re, st.dly1_im);
+
+    int next_chunk = 0;    // next chunk to issue for this lane's channel
+    int ready_end = 0;     // samples [.., ready_end) of this lane's channel are known to have landed
+    bool inflight = false; // warp-uniform: a cp.async group may still be pending
     int err_code = 0;
     bool active = live && ninp > 0 && noutput_items > 0;
 
     while (__any_sync(FULL, active)) {
-        // (1) tag reset (:139-164)
-        if (active && tag_off != 0x7fffffff) {
-            if ((tag_off >= iidx) && ((float)tag_off < ((float)iidx + p.sps_half))) {
-                if (tag_val != tag_val) {
-                    thead = next_tag(thead + 1); // NaN: drop the tag, no reset (:144-147)
-                } else {
-                    st.mu = tag_val;
-                    iidx = tag_off;
-                    if (st.mu < 0) {
-                        st.mu = st.mu + 1.0f;
-                        iidx--;
-                    }
-                    st.div = 0;
-                    st.omega = p.sps_half;
-                    st.dly2_re = st.dly1_re;
-                    st.dly2_im = st.dly1_im;
-                    thead = next_tag(thead + 1);
-                }
-                fetch_tag();
-            }
-        }
-        // (2) keep the ring ahead of every lane
-        const int hi = iidx + 7;
+        // keep every lane's ring kMskAhead samples ahead of its read position
         for (;;) {
-            const bool want = active && ((hi + kMskLookahead) >> 6) >= next_chunk &&
-                              (next_chunk << 6) < ninput_items;
+            const bool want = active && (iidx + kMskAhead >= next_chunk * kMskChunk);
             const unsigned wm = __ballot_sync(FULL, want);
             if (!wm)
                 break;
-            for (int ch = 0; ch < 32; ch++) {
+            for (int ch = 0; ch < rows; ch++) {
                 if (!((wm >> ch) & 1u))
                     continue;
                 const int j = __shfl_sync(FULL, next_chunk, ch);
-                const int s0 = (j << 6) + 2 * lane; // first of this lane's two samples
-                const float2 *src = row0 + (size_t)ch * in_stride + s0;
-                float2 *dst = ring + ch * kMskPitch + ((j & 1) << 6) + 2 * lane;
-                int nb = (ninput_items - s0) * 8;
-                nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-                if (row16) {
-                    cp_async_16(dst, nb ? src : row0, nb);
-                } else {
-                    cp_async_8(dst, nb ? src : row0, nb >= 8 ? 8 : 0);
-                    cp_async_8(dst + 1, nb > 8 ? src + 1 : row0, nb > 8 ? 8 : 0);
-                }
+                const int sidx = j * kMskChunk + lane;
+                const float2 *src = row0 + (size_t)ch * in_stride + sidx;
+                const int nb = sidx < ninput_items ? 8 : 0;
+                const int slot = sidx & (kMskRing - 1);
+                float2 *dst = ring + ch * kMskPitch + slot;
+                cp_async_8(dst, nb ? src : row0, nb);
+                if (slot < kMskMirror)
+                    cp_async_8(dst + kMskRing, nb ? src : row0, nb);
             }
             cp_async_commit();
             inflight = true;
             if (want)
                 next_chunk++;
         }
-        if (inflight && __any_sync(FULL, active && (hi >> 6) >= next_chunk - 1)) {
+        if (inflight && __any_sync(FULL, active && (iidx + kMskNeed > ready_end))) {
             cp_async_wait_all();
             __syncwarp();
             inflight = false;
+            ready_end = next_chunk * kMskChunk;
         }
-        // (3) one half-symbol step
-        if (active) {
-            float2 s8[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                s8[k] = my[(iidx + k) & (kMskRing - 1)];
-            float2 v;
-            if (!interp8(s8, st.mu, s_mmse, &v)) {
+#pragma unroll 1
+        for (int it = 0; it < kMskInner; it++) {
+            if (!active)
+                break;
+            // tag reset (:139-164); rare, so an integer window test guards the float compare
+            if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
+                if ((float)tag_off < ((float)iidx + p.sps_half)) {
+                    if (tag_val == tag_val) { // NaN: drop the tag, no reset (:144-147)
+                        st.mu = tag_val;
+                        iidx = tag_off;
+                        if (st.mu < 0) {
+                            st.mu = st.mu + 1.0f;
+                            iidx--;
+                        }
+                        st.div = 0;
+                        st.omega = p.sps_half;
+                    }
+                    fetch_tag(thead + 1);
+                }
+            }
+            // mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), in[0..7] . reversed row
+            const int imu = __float2int_rn(st.mu * 128.0f);
+            if ((unsigned)imu > 128u) {
                 err_code = B200AIS_E_INTERP;
                 active = false;
-                continue;
+                break;
             }
+            const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu * 8);
+            const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu * 8 + 4);
+            const float2 *sp = my + (iidx & (kMskRing - 1));
+            const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+            const float2 s4 = sp[4], s5 = sp[5], s6 = sp[6], s7 = sp[7];
+            // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
+            const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
+            const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
+            const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
+            const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
+            float2 v;
+            v.x = (p0r + p1r) + (p2r + p3r);
+            v.y = (p0i + p1i) + (p2i + p3i);
             // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
-            const float sq_re = v.x * v.x - v.y * v.y, sq_im = v.x * v.y + v.y * v.x;
-            const float d_re = st.dly2_re * st.dly2_re - st.dly2_im * st.dly2_im;
-            const float d_im = -(st.dly2_re * st.dly2_im + st.dly2_im * st.dly2_re);
+            const float vxy = v.x * v.y;
+            const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
+            const float d_re = psq_re, d_im = -psq_im;
             const float nl_re = sq_re * d_re - sq_im * d_im;
             const float nl_im = sq_re * d_im + sq_im * d_re;
             float err_out = nl_re - st.diff1_re;
-            if (st.div & 1) {
+            const bool odd = st.div & 1;
+            if (odd) {
                 err_out = branchless_clip(err_out, 3.0f);
                 st.omega = st.omega + p.gain_omega * err_out;
                 st.omega = p.sps_half + branchless_clip(st.omega - p.sps_half, p.limit);
                 st.mu = st.mu + p.gain * err_out;
             }
-            if (!(st.div & 1) || p.osps == 2) {
-                if (oc)
-                    oc[oidx] = v;
-                if (oe)
-                    oe[oidx] = err_out;
-                if (om)
-                    om[oidx] = st.mu;
-                if (kTail) {
-                    // quadrature_demod_cf: x[n]*conj(x[n-1]), VOLK multiply-conjugate FMA form
-                    const float re = __fmaf_rn(v.x, qprev.x, v.y * qprev.y);
-                    const float im = __fmaf_rn(v.y, qprev.x, -(v.x * qprev.y));
-                    const float soft = qgain * fast_atan2f_tab(im, re, s_atan);
-                    qprev = v;
-                    const unsigned b = soft >= 0 ? 1u : 0u;   // binary_slicer_fb
-                    const unsigned d = (b - bprev) % 2u;      // diff_decoder_bb(2)
-                    bprev = b;
-                    if (os)
-                        os[oidx] = soft;
-                    const unsigned bit = (d ^ 0x01u) & 0x01u; // lib/invert_impl.cc:63
-                    if (word_ok) {
-                        pack |= bit << (8 * (oidx & 3));
-                        if ((oidx & 3) == 3) {
-                            *reinterpret_cast<unsigned *>(ob + (oidx & ~3)) = pack;
-                            pack = 0;
-                        }
-                    } else {
-                        ob[oidx] = (uint8_t)bit;
-                    }
+            if (!odd || p.osps == 2) {
+                oc[oidx] = v;
+                if (kDebug) {
+                    if (oe)
+                        oe[oidx] = err_out;
+                    if (om)
+                        om[oidx] = st.mu;
                 }
                 oidx++;
             }
             st.div++;
-            st.dly1_re = v.x;
-            st.dly1_im = v.y;
-            st.dly2_re = v.x;
-            st.dly2_im = v.y;
+            vlast = v;
+            psq_re = sq_re;
+            psq_im = sq_im;
             st.diff1_re = nl_re;
             st.diff1_im = nl_im;
             st.mu = st.mu + st.omega;
@@ -278,23 +244,76 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels,
     cp_async_wait_all();
     if (!live)
         return;
-    if (kTail && word_ok && (oidx & 3)) { // flush the partial word byte by byte
-        for (int k = oidx & ~3; k < oidx; k++)
-            ob[k] = (uint8_t)((pack >> (8 * (k & 3))) & 0xffu);
-    }
-    if (ninp > 0 && iidx > 0) {
-        const float2 pv = xin[iidx - 1];
-        st.prev_re = pv.x;
-        st.prev_im = pv.y;
+    if (ninp > 0) {
+        st.dly1_re = st.dly2_re = vlast.x;
+        st.dly1_im = st.dly2_im = vlast.y;
+        if (iidx > 0) {
+            const float2 pv = in[(size_t)c * in_stride + (iidx - 1)];
+            st.prev_re = pv.x;
+            st.prev_im = pv.y;
+        }
+        state[c] = st;
     }
     if (!err_code && require_unbounded && ninp > 0 && oidx >= noutput_items && iidx < ninp)
         err_code = B200AIS_E_OUT_OVERFLOW;
     if (err_code)
         atomicMin(status, err_code);
-    if (ninp > 0)
-        state[c] = st;
-    nproduced[c] = oidx;
+    nproduced[c] = ninp > 0 ? oidx : 0;
     nconsumed[c] = ninp > 0 ? iidx : 0;
+}
+
+// G4-G6 + A9 on the symbol stream: quadrature_demod_cf(pi/2) -> binary_slicer_fb ->
+// diff_decoder_bb(2) -> invert.  bit[k] depends on sym[k], sym[k-1], sym[k-2] only, so every
+// thread produces four consecutive bits (one 32-bit store) from six symbols.
+__global__ void __launch_bounds__(128)
+k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict__ nsym,
+       int channels, const float *__restrict__ g_atan, uint8_t *__restrict__ bits,
+       size_t bits_stride, float *__restrict__ soft_out)
+{
+    __shared__ float s_atan[257];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x)
+        s_atan[i] = g_atan[i];
+    __syncthreads();
+    const int c = blockIdx.y;
+    const int n = nsym[c];
+    const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (k0 >= n)
+        return;
+    const float2 *sc = sym + (size_t)c * sym_stride;
+    const float qgain = 1.57079632679489661923f; // (float)(pi/2), python/ais_demod.py:48
+    const float2 zero = make_float2(0.0f, 0.0f);
+    float2 prev = k0 >= 2 ? sc[k0 - 2] : zero;
+    float2 cur = k0 >= 1 ? sc[k0 - 1] : zero;
+    // slicer decision of symbol k0-1 (0 before the first symbol: diff_decoder history)
+    unsigned bprev = 0;
+    if (k0 >= 1) {
+        const float re = __fmaf_rn(cur.x, prev.x, cur.y * prev.y);
+        const float im = __fmaf_rn(cur.y, prev.x, -(cur.x * prev.y));
+        bprev = (qgain * fast_atan2f_tab(im, re, s_atan)) >= 0 ? 1u : 0u;
+    }
+    unsigned pack = 0;
+    const int kend = min(4, n - k0);
+    for (int q = 0; q < kend; q++) {
+        const float2 v = sc[k0 + q];
+        // quadrature_demod_cf: x[n]*conj(x[n-1]), VOLK multiply-conjugate FMA form
+        const float re = __fmaf_rn(v.x, cur.x, v.y * cur.y);
+        const float im = __fmaf_rn(v.y, cur.x, -(v.x * cur.y));
+        const float soft = qgain * fast_atan2f_tab(im, re, s_atan);
+        cur = v;
+        const unsigned b = soft >= 0 ? 1u : 0u;     // binary_slicer_fb
+        const unsigned d = (b - bprev) % 2u;        // diff_decoder_bb(2)
+        bprev = b;
+        if (soft_out)
+            soft_out[(size_t)c * sym_stride + k0 + q] = soft;
+        pack |= ((d ^ 0x01u) & 0x01u) << (8 * q);   // lib/invert_impl.cc:63
+    }
+    uint8_t *ob = bits + (size_t)c * bits_stride + k0;
+    if (kend == 4 && ((reinterpret_cast<uintptr_t>(ob) & 3) == 0)) {
+        *reinterpret_cast<unsigned *>(ob) = pack;
+    } else {
+        for (int q = 0; q < kend; q++)
+            ob[q] = (uint8_t)((pack >> (8 * q)) & 0xffu);
+    }
 }
 
 __global__ void k_msk_reset(MskState *state, int channels, float sps_half)
@@ -348,11 +367,10 @@ __global__ void k_invert(const uint8_t *__restrict__ in, uint8_t *__restrict__ o
 } // namespace
 
 int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
-               const int *ninput_items_dev, int ninput_items_const, uint64_t nitems_read,
-               const b200ais_tag *tags, int max_tags, const int *ntags, MskParams p, MskState *state,
-               float2 *out, float *out_err, float *out_mu, float *out_soft, uint8_t *bits,
-               size_t out_stride, int *nproduced, int *nconsumed, int require_unbounded,
-               int *status, cudaStream_t s)
+               int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
+               const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
+               float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
+               int require_unbounded, int *status, cudaStream_t s)
 {
     if (channels <= 0)
         return B200AIS_OK;
@@ -360,22 +378,33 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
     int rc = get_tables(&tb);
     if (rc)
         return rc;
-    // serial per channel: one warp (32 channels) per block spreads the channels over the SMs
-    const int threads = 32;
-    const int blocks = (channels + threads - 1) / threads;
-    if (bits)
-        k_msk<true><<<blocks, threads, 0, s>>>(in, in_stride, channels, noutput_items,
-                                               ninput_items_dev, ninput_items_const, nitems_read,
-                                               tags, max_tags, ntags, p, state, tb.mmse, tb.atan,
-                                               out, out_err, out_mu, out_soft, bits, out_stride,
-                                               nproduced, nconsumed, require_unbounded, status);
+    const int blocks = (channels + 31) / 32; // one warp (32 channels) per block
+    if (out_err || out_mu)
+        k_msk<true><<<blocks, 32, 0, s>>>(in, in_stride, channels, noutput_items, ninput_items,
+                                          nitems_read, tags, max_tags, ntags, p, state, tb.mmse, out,
+                                          out_err, out_mu, out_stride, nproduced, nconsumed,
+                                          require_unbounded, status);
     else
-        k_msk<false><<<blocks, threads, 0, s>>>(in, in_stride, channels, noutput_items,
-                                                ninput_items_dev, ninput_items_const, nitems_read,
-                                                tags, max_tags, ntags, p, state, tb.mmse, tb.atan,
-                                                out, out_err, out_mu, out_soft, bits, out_stride,
-                                                nproduced, nconsumed, require_unbounded, status);
+        k_msk<false><<<blocks, 32, 0, s>>>(in, in_stride, channels, noutput_items, ninput_items,
+                                           nitems_read, tags, max_tags, ntags, p, state, tb.mmse, out,
+                                           out_err, out_mu, out_stride, nproduced, nconsumed,
+                                           require_unbounded, status);
     B200_LAUNCH_CHECK("k_msk");
+    return B200AIS_OK;
+}
+
+int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int channels, int max_sym,
+                uint8_t *bits, size_t bits_stride, float *soft, cudaStream_t s)
+{
+    if (channels <= 0 || max_sym <= 0)
+        return B200AIS_OK;
+    Tables tb;
+    int rc = get_tables(&tb);
+    if (rc)
+        return rc;
+    dim3 grid((max_sym + 4 * 128 - 1) / (4 * 128), channels);
+    k_tail<<<grid, 128, 0, s>>>(sym, sym_stride, nsym, channels, tb.atan, bits, bits_stride, soft);
+    B200_LAUNCH_CHECK("k_tail");
     return B200AIS_OK;
 }
 

@@ -213,8 +213,9 @@ enum {
     B200AIS_STAGE_T_MIXAGC = 2, /* NCO mix + feedforward AGC */
     B200AIS_STAGE_T_CORR = 3,   /* corr_est correlator (the dominant kernel) */
     B200AIS_STAGE_T_DETECT = 4, /* corr_est detector */
-    B200AIS_STAGE_T_MSK = 5,    /* msk_timing_recovery + bit tail */
-    B200AIS_STAGE_T_COUNT = 6
+    B200AIS_STAGE_T_MSK = 5,    /* msk_timing_recovery recurrence */
+    B200AIS_STAGE_T_TAIL = 6,   /* quadrature demod -> slicer -> diff decoder -> invert */
+    B200AIS_STAGE_T_COUNT = 7
 };
 B200AIS_API int b200ais_demod_profile(b200ais_demod *h, int enable);
 B200AIS_API int b200ais_demod_stage_ms(b200ais_demod *h, double *stage_ms, int *calls);
