@@ -41,25 +41,28 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
 constexpr int kMskChunk = 32;              // samples per prefetch chunk
 constexpr int kMskRing = 128;               // ring slots per channel (4 chunks)
 constexpr int kMskMirror = 8;               // slots 0..7 repeated after the ring: 8-sample reads never wrap
-constexpr int kMskPitch = kMskRing + kMskMirror + 1; // 137: lane stride 274 words -> conflict-free 64-bit LDS
-constexpr int kMskInner = 4;                // half-symbol steps between two warp votes
-constexpr int kMskNeed = 3 * kMskInner + 2 * kMskInner + 8; // samples a lane may touch in one inner block
-constexpr int kMskAhead = kMskNeed + 32;    // issue a chunk once a lane is this close to it
+constexpr int kMskPitch = kMskRing + kMskMirror + 2; // 138 float2: rows stay 16-byte aligned
+constexpr int kMskNeed = 16;                // samples past iidx one step may touch (tag jump + 8 taps)
+constexpr int kMskAhead = 64;               // issue a chunk once the lane is this close to it
 
-__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem, int src_bytes)
+__device__ __forceinline__ void cp_async_8(unsigned smem, const void *gmem, int src_bytes)
 {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_16(unsigned smem, const void *gmem, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// The serial core of msk_timing_recovery_cc.  One warp = 32 channels, lane l runs channel
-// (warp*32 + l).  A channel's loop is a recurrence on (mu, omega, iidx, div, previous
-// interpolant), so its run time is (#half-symbols) x (latency of one step); everything that
-// is not on that recurrence (the bit tail) lives in k_tail.  Input samples are staged in a
-// shared-memory ring per channel, filled with cp.async 32 samples at a time, one coalesced
-// 256-byte row segment per channel, kMskAhead samples before the first lane needs them.
+// The serial core of msk_timing_recovery_cc: one lane per channel.  A channel's loop is a
+// recurrence on (mu, omega, iidx, div, previous interpolant), so the kernel's run time is
+// (#half-symbols) x (latency of one step) however many channels run: the step is kept as
+// short as possible and everything off the recurrence (the bit tail) lives in k_tail.
+// Each lane streams its own channel through a private shared-memory ring (4 chunks of 32
+// samples) with cp.async, issuing a 256-byte chunk kMskAhead samples before it is needed,
+// so no step waits on HBM.
 template <bool kDebug>
 __global__ void __launch_bounds__(32)
 k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput_items,
@@ -71,29 +74,35 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
 {
     __shared__ __align__(16) float s_mmse[129 * 8];
     __shared__ __align__(16) float2 ring[32 * kMskPitch];
-    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
     for (int i = lane; i < 129 * 8; i += 32)
         s_mmse[i] = g_mmse[i];
-    const int c0 = blockIdx.x * 32;
-    const int c = c0 + lane;
-    const bool live = c < channels;
-    const int cc = live ? c : channels - 1; // dead lanes shadow the last channel, never store
+    __syncwarp();
+    const int c = blockIdx.x * 32 + lane;
+    if (c >= channels)
+        return;
 
-    MskState st = state[cc];
+    MskState st = state[c];
     int oidx = 0, iidx = 0;
     const int ninp = (int)((double)ninput_items - 3.0 * (double)p.sps_half); // :119
+    if (ninp <= 0 || noutput_items <= 0) {
+        nproduced[c] = 0;
+        nconsumed[c] = 0;
+        return;
+    }
 
-    // ring preset: the slots of the (virtual) chunks before 0 are zero, in[-1] is the carried item
+    // ring preset: slots before sample 0 are zero, in[-1] is the item carried from the last call
     float2 *my = ring + lane * kMskPitch;
     for (int k = 0; k < kMskRing + kMskMirror; k++)
         my[k] = make_float2(0.0f, 0.0f);
     my[kMskRing - 1] = make_float2(st.prev_re, st.prev_im);
-    __syncwarp();
+    const unsigned my_s = (unsigned)__cvta_generic_to_shared(my);
+    const float2 *row = in + (size_t)c * in_stride;
+    const bool row16 = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 
     // time_est tags inside [read, read+ninp), in offset order (:125-130)
-    const b200ais_tag *tg = tags ? tags + (size_t)cc * max_tags : nullptr;
-    const int nt = (tags && ntags && ninp > 0) ? min(ntags[cc], max_tags) : 0;
+    const b200ais_tag *tg = tags ? tags + (size_t)c * max_tags : nullptr;
+    const int nt = (tags && ntags) ? min(ntags[c], max_tags) : 0;
     int thead = 0;
     int tag_off = 0x7fffffff; // pending tag, relative to the read pointer
     float tag_val = 0.0f;
@@ -115,151 +124,145 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     fetch_tag(0);
     const int tag_span = (int)ceilf(p.sps_half) + 1; // integer pre-test before the float compare
 
-    float2 *oc = out + (size_t)cc * out_stride;
-    float *oe = kDebug && out_err ? out_err + (size_t)cc * out_stride : nullptr;
-    float *om = kDebug && out_mu ? out_mu + (size_t)cc * out_stride : nullptr;
-    const float2 *row0 = in + (size_t)c0 * in_stride;
-    const int rows = min(32, channels - c0);
+    float2 *oc = out + (size_t)c * out_stride;
+    float *oe = kDebug && out_err ? out_err + (size_t)c * out_stride : nullptr;
+    float *om = kDebug && out_mu ? out_mu + (size_t)c * out_stride : nullptr;
 
     // conj(dly2^2) of the reference equals conj(previous v^2): d_dly_conj_1 and _2 are always
     // assigned together (:194-195), so only the squared previous interpolant is carried.
     float psq_re = st.dly2_re * st.dly2_re - st.dly2_im * st.dly2_im;
     float psq_im = st.dly2_re * st.dly2_im + st.dly2_im * st.dly2_re;
     float2 vlast = make_float2(st.dly1_re, st.dly1_im);
+    float mu = st.mu, omega = st.omega, diff1_re = st.diff1_re, diff1_im = st.diff1_im;
+    int div = st.div;
 
-    int next_chunk = 0;    // next chunk to issue for this lane's channel
-    int ready_end = 0;     // samples [.., ready_end) of this lane's channel are known to have landed
-    bool inflight = false; // warp-uniform: a cp.async group may still be pending
+    int issue_end = 0; // samples [0, issue_end) have been requested
+    int ready_end = 0; // samples [0, ready_end) are known to have landed
     int err_code = 0;
-    bool active = live && ninp > 0 && noutput_items > 0;
 
-    while (__any_sync(FULL, active)) {
-        // keep every lane's ring kMskAhead samples ahead of its read position
-        for (;;) {
-            const bool want = active && (iidx + kMskAhead >= next_chunk * kMskChunk);
-            const unsigned wm = __ballot_sync(FULL, want);
-            if (!wm)
-                break;
-            for (int ch = 0; ch < rows; ch++) {
-                if (!((wm >> ch) & 1u))
-                    continue;
-                const int j = __shfl_sync(FULL, next_chunk, ch);
-                const int sidx = j * kMskChunk + lane;
-                const float2 *src = row0 + (size_t)ch * in_stride + sidx;
-                const int nb = sidx < ninput_items ? 8 : 0;
-                const int slot = sidx & (kMskRing - 1);
-                float2 *dst = ring + ch * kMskPitch + slot;
-                cp_async_8(dst, nb ? src : row0, nb);
-                if (slot < kMskMirror)
-                    cp_async_8(dst + kMskRing, nb ? src : row0, nb);
+    for (;;) {
+        // keep the ring kMskAhead samples ahead of the read position
+        if (iidx + kMskAhead >= issue_end) {
+            const int slot = issue_end & (kMskRing - 1);
+            const float2 *src = row + issue_end;
+            const unsigned dst = my_s + slot * 8;
+            if (row16 && issue_end + kMskChunk <= ninput_items) {
+#pragma unroll
+                for (int k = 0; k < kMskChunk / 2; k++)
+                    cp_async_16(dst + 16 * k, src + 2 * k, 16);
+                if (slot == 0) {
+#pragma unroll
+                    for (int k = 0; k < kMskMirror / 2; k++)
+                        cp_async_16(dst + kMskRing * 8 + 16 * k, src + 2 * k, 16);
+                }
+            } else {
+                for (int k = 0; k < kMskChunk; k++) {
+                    const int nb = issue_end + k < ninput_items ? 8 : 0;
+                    cp_async_8(dst + 8 * k, nb ? src + k : row, nb);
+                    if (slot == 0 && k < kMskMirror)
+                        cp_async_8(dst + kMskRing * 8 + 8 * k, nb ? src + k : row, nb);
+                }
             }
             cp_async_commit();
-            inflight = true;
-            if (want)
-                next_chunk++;
+            issue_end += kMskChunk;
+            continue; // (at start-up two chunks are issued back to back)
         }
-        if (inflight && __any_sync(FULL, active && (iidx + kMskNeed > ready_end))) {
+        if (iidx + kMskNeed > ready_end) {
             cp_async_wait_all();
-            __syncwarp();
-            inflight = false;
-            ready_end = next_chunk * kMskChunk;
+            ready_end = issue_end;
         }
-#pragma unroll 1
-        for (int it = 0; it < kMskInner; it++) {
-            if (!active)
-                break;
-            // tag reset (:139-164); rare, so an integer window test guards the float compare
-            if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
-                if ((float)tag_off < ((float)iidx + p.sps_half)) {
-                    if (tag_val == tag_val) { // NaN: drop the tag, no reset (:144-147)
-                        st.mu = tag_val;
-                        iidx = tag_off;
-                        if (st.mu < 0) {
-                            st.mu = st.mu + 1.0f;
-                            iidx--;
-                        }
-                        st.div = 0;
-                        st.omega = p.sps_half;
+        // tag reset (:139-164); rare, so an integer window test guards the float compare
+        if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
+            if ((float)tag_off < ((float)iidx + p.sps_half)) {
+                if (tag_val == tag_val) { // NaN: drop the tag, no reset (:144-147)
+                    mu = tag_val;
+                    iidx = tag_off;
+                    if (mu < 0) {
+                        mu = mu + 1.0f;
+                        iidx--;
                     }
-                    fetch_tag(thead + 1);
+                    div = 0;
+                    omega = p.sps_half;
                 }
+                fetch_tag(thead + 1);
             }
-            // mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), in[0..7] . reversed row
-            const int imu = __float2int_rn(st.mu * 128.0f);
-            if ((unsigned)imu > 128u) {
-                err_code = B200AIS_E_INTERP;
-                active = false;
-                break;
-            }
-            const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu * 8);
-            const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu * 8 + 4);
-            const float2 *sp = my + (iidx & (kMskRing - 1));
-            const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
-            const float2 s4 = sp[4], s5 = sp[5], s6 = sp[6], s7 = sp[7];
-            // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
-            const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
-            const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
-            const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
-            const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
-            float2 v;
-            v.x = (p0r + p1r) + (p2r + p3r);
-            v.y = (p0i + p1i) + (p2i + p3i);
-            // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
-            const float vxy = v.x * v.y;
-            const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
-            const float d_re = psq_re, d_im = -psq_im;
-            const float nl_re = sq_re * d_re - sq_im * d_im;
-            const float nl_im = sq_re * d_im + sq_im * d_re;
-            float err_out = nl_re - st.diff1_re;
-            const bool odd = st.div & 1;
-            if (odd) {
-                err_out = branchless_clip(err_out, 3.0f);
-                st.omega = st.omega + p.gain_omega * err_out;
-                st.omega = p.sps_half + branchless_clip(st.omega - p.sps_half, p.limit);
-                st.mu = st.mu + p.gain * err_out;
-            }
-            if (!odd || p.osps == 2) {
-                oc[oidx] = v;
-                if (kDebug) {
-                    if (oe)
-                        oe[oidx] = err_out;
-                    if (om)
-                        om[oidx] = st.mu;
-                }
-                oidx++;
-            }
-            st.div++;
-            vlast = v;
-            psq_re = sq_re;
-            psq_im = sq_im;
-            st.diff1_re = nl_re;
-            st.diff1_im = nl_im;
-            st.mu = st.mu + st.omega;
-            const float fl = floorf(st.mu);
-            iidx += (int)fl;
-            st.mu = st.mu - fl;
-            active = (oidx < noutput_items) && (iidx < ninp);
         }
+        // mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), in[0..7] . reversed row
+        const int imu = __float2int_rn(mu * 128.0f);
+        if ((unsigned)imu > 128u) {
+            err_code = B200AIS_E_INTERP;
+            break;
+        }
+        const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu * 8);
+        const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu * 8 + 4);
+        const float2 *sp = my + (iidx & (kMskRing - 1));
+        const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+        const float2 s4 = sp[4], s5 = sp[5], s6 = sp[6], s7 = sp[7];
+        // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
+        const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
+        const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
+        const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
+        const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
+        float2 v;
+        v.x = (p0r + p1r) + (p2r + p3r);
+        v.y = (p0i + p1i) + (p2i + p3i);
+        // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
+        const float vxy = v.x * v.y;
+        const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
+        const float d_re = psq_re, d_im = -psq_im;
+        const float nl_re = sq_re * d_re - sq_im * d_im;
+        const float nl_im = sq_re * d_im + sq_im * d_re;
+        float err_out = nl_re - diff1_re;
+        const bool odd = div & 1;
+        if (odd) {
+            err_out = branchless_clip(err_out, 3.0f);
+            omega = omega + p.gain_omega * err_out;
+            omega = p.sps_half + branchless_clip(omega - p.sps_half, p.limit);
+            mu = mu + p.gain * err_out;
+        }
+        if (!odd || p.osps == 2) {
+            oc[oidx] = v;
+            if (kDebug) {
+                if (oe)
+                    oe[oidx] = err_out;
+                if (om)
+                    om[oidx] = mu;
+            }
+            oidx++;
+        }
+        div++;
+        vlast = v;
+        psq_re = sq_re;
+        psq_im = sq_im;
+        diff1_re = nl_re;
+        diff1_im = nl_im;
+        mu = mu + omega;
+        const float fl = floorf(mu);
+        iidx += (int)fl;
+        mu = mu - fl;
+        if (!((oidx < noutput_items) && (iidx < ninp)))
+            break;
     }
     cp_async_wait_all();
-    if (!live)
-        return;
-    if (ninp > 0) {
-        st.dly1_re = st.dly2_re = vlast.x;
-        st.dly1_im = st.dly2_im = vlast.y;
-        if (iidx > 0) {
-            const float2 pv = in[(size_t)c * in_stride + (iidx - 1)];
-            st.prev_re = pv.x;
-            st.prev_im = pv.y;
-        }
-        state[c] = st;
+    st.mu = mu;
+    st.omega = omega;
+    st.div = div;
+    st.diff1_re = diff1_re;
+    st.diff1_im = diff1_im;
+    st.dly1_re = st.dly2_re = vlast.x;
+    st.dly1_im = st.dly2_im = vlast.y;
+    if (iidx > 0) {
+        const float2 pv = row[iidx - 1];
+        st.prev_re = pv.x;
+        st.prev_im = pv.y;
     }
-    if (!err_code && require_unbounded && ninp > 0 && oidx >= noutput_items && iidx < ninp)
+    state[c] = st;
+    if (!err_code && require_unbounded && oidx >= noutput_items && iidx < ninp)
         err_code = B200AIS_E_OUT_OVERFLOW;
     if (err_code)
         atomicMin(status, err_code);
-    nproduced[c] = ninp > 0 ? oidx : 0;
-    nconsumed[c] = ninp > 0 ? iidx : 0;
+    nproduced[c] = oidx;
+    nconsumed[c] = iidx;
 }
 
 // G4-G6 + A9 on the symbol stream: quadrature_demod_cf(pi/2) -> binary_slicer_fb ->
