@@ -136,41 +136,52 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     float mu = st.mu, omega = st.omega, diff1_re = st.diff1_re, diff1_im = st.diff1_im;
     int div = st.div;
 
-    int issue_end = 0; // samples [0, issue_end) have been requested
+    int issue_end = 0; // samples [0, issue_end) of this lane's channel have been requested
     int ready_end = 0; // samples [0, ready_end) are known to have landed
     int err_code = 0;
+    bool active = true;
+    const unsigned FULL = __activemask(); // the lanes that own a channel (a prefix of the warp)
 
-    for (;;) {
-        // keep the ring kMskAhead samples ahead of the read position
-        if (iidx + kMskAhead >= issue_end) {
-            const int slot = issue_end & (kMskRing - 1);
-            const float2 *src = row + issue_end;
-            const unsigned dst = my_s + slot * 8;
-            if (row16 && issue_end + kMskChunk <= ninput_items) {
+    // cp.async groups are tracked per warp, not per lane, so issuing and waiting happen in
+    // warp-wide rounds: when any lane gets within kMskAhead samples of the end of what it
+    // has requested, every lane that has room in its ring requests its next chunk, and the
+    // (rare) wait is a wait for rounds issued ~20 steps earlier.
+    while (__any_sync(FULL, active)) {
+        const bool want = active && (iidx + kMskAhead >= issue_end);
+        if (__any_sync(FULL, want)) {
+            // room: the chunk being replaced (4 back) must be behind this lane's read position
+            if (active && (iidx + kMskRing - kMskChunk - 1 >= issue_end)) {
+                const int slot = issue_end & (kMskRing - 1);
+                const float2 *src = row + issue_end;
+                const unsigned dst = my_s + slot * 8;
+                if (row16 && issue_end + kMskChunk <= ninput_items) {
 #pragma unroll
-                for (int k = 0; k < kMskChunk / 2; k++)
-                    cp_async_16(dst + 16 * k, src + 2 * k, 16);
-                if (slot == 0) {
+                    for (int k = 0; k < kMskChunk / 2; k++)
+                        cp_async_16(dst + 16 * k, src + 2 * k, 16);
+                    if (slot == 0) {
 #pragma unroll
-                    for (int k = 0; k < kMskMirror / 2; k++)
-                        cp_async_16(dst + kMskRing * 8 + 16 * k, src + 2 * k, 16);
+                        for (int k = 0; k < kMskMirror / 2; k++)
+                            cp_async_16(dst + kMskRing * 8 + 16 * k, src + 2 * k, 16);
+                    }
+                } else {
+                    for (int k = 0; k < kMskChunk; k++) {
+                        const int nb = issue_end + k < ninput_items ? 8 : 0;
+                        cp_async_8(dst + 8 * k, nb ? src + k : row, nb);
+                        if (slot == 0 && k < kMskMirror)
+                            cp_async_8(dst + kMskRing * 8 + 8 * k, nb ? src + k : row, nb);
+                    }
                 }
-            } else {
-                for (int k = 0; k < kMskChunk; k++) {
-                    const int nb = issue_end + k < ninput_items ? 8 : 0;
-                    cp_async_8(dst + 8 * k, nb ? src + k : row, nb);
-                    if (slot == 0 && k < kMskMirror)
-                        cp_async_8(dst + kMskRing * 8 + 8 * k, nb ? src + k : row, nb);
-                }
+                issue_end += kMskChunk;
             }
             cp_async_commit();
-            issue_end += kMskChunk;
-            continue; // (at start-up two chunks are issued back to back)
+            continue; // (at start-up several chunks are requested back to back)
         }
-        if (iidx + kMskNeed > ready_end) {
+        if (__any_sync(FULL, active && (iidx + kMskNeed > ready_end))) {
             cp_async_wait_all();
             ready_end = issue_end;
         }
+        if (!active)
+            continue;
         // tag reset (:139-164); rare, so an integer window test guards the float compare
         if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
             if ((float)tag_off < ((float)iidx + p.sps_half)) {
@@ -191,7 +202,8 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         const int imu = __float2int_rn(mu * 128.0f);
         if ((unsigned)imu > 128u) {
             err_code = B200AIS_E_INTERP;
-            break;
+            active = false;
+            continue;
         }
         const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu * 8);
         const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu * 8 + 4);
@@ -240,8 +252,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         const float fl = floorf(mu);
         iidx += (int)fl;
         mu = mu - fl;
-        if (!((oidx < noutput_items) && (iidx < ninp)))
-            break;
+        active = (oidx < noutput_items) && (iidx < ninp);
     }
     cp_async_wait_all();
     st.mu = mu;
