@@ -193,19 +193,9 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
 
     # rank 0 owns the preamble template; the other ranks receive it over NCCL (the only collective)
-    if rank == 0:
-        tmpl = preamble_template(args.template)
-        t_len = torch.tensor([len(tmpl)], dtype=torch.int32, device=dev)
-    else:
-        t_len = torch.zeros(1, dtype=torch.int32, device=dev)
-    if world > 1:
-        dist.broadcast(t_len, src=0)
-    t_dev = torch.zeros((int(t_len.item()), 2), dtype=torch.float32, device=dev)
-    if rank == 0:
-        t_dev.copy_(torch.from_numpy(tmpl.view(np.float32).reshape(-1, 2)))
-    if world > 1:
-        dist.broadcast(t_dev, src=0)
-    tmpl = t_dev.cpu().numpy().reshape(-1).view(np.complex64).copy()
+    from gr_ais_b200 import sharding
+    tmpl = sharding.broadcast_template(preamble_template(args.template) if rank == 0 else None,
+                                       src=0, device=dev)
 
     pin_in, n = make_host_batch(args, B.PinnedArray)
     C = args.channels
@@ -251,10 +241,7 @@ def run_b200(args):
     d.profile(False)
     d.status()
     clocks = sampler.stop()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = sharding.max_over_ranks(ms_total, dev) / args.steps
     value = world * C * (n / FS) / (ms_step * 1e-3)
     nbits_host = nbits_dev.cpu().numpy()
 
@@ -277,10 +264,7 @@ def run_b200(args):
             step_host()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_step = float(t.item()) / args.steps
+        dt_step = sharding.max_over_ranks(dt, dev) / args.steps
         if not np.array_equal(pin_nbits.array, nbits_host):
             raise RuntimeError("host-buffer and device-resident runs disagree on symbol counts")
         e2e = {"value": world * C * (n / FS) / dt_step, "unit": "channels/s",
