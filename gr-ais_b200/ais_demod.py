@@ -223,6 +223,9 @@ class ais_demod:
                                                int(max_bits), B.ptr(nbits_ptr), B.ptr(tags_ptr),
                                                B.ptr(ntags_ptr), stream))
 
+    def set_overlap(self, groups):
+        B.check(B.lib().b200ais_demod_set_overlap(self._h, int(groups)))
+
     def profile(self, on=True):
         B.check(B.lib().b200ais_demod_profile(self._h, 1 if on else 0))
 

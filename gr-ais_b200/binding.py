@@ -40,6 +40,7 @@ EXPORTS = [
     "b200ais_demod_max_bits", "b200ais_demod_work", "b200ais_demod_work_dev",
     "b200ais_demod_status", "b200ais_demod_enable_taps", "b200ais_demod_tap",
     "b200ais_demod_read_tap", "b200ais_demod_profile", "b200ais_demod_stage_ms",
+    "b200ais_demod_set_overlap",
 ]
 STAGE_NAMES = ["sqfft_freqest", "nco_phase", "mix_agc", "corr", "detect", "msk", "tail"]
 
@@ -130,6 +131,7 @@ def lib():
     L.b200ais_demod_tap.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz)]
     L.b200ais_demod_read_tap.argtypes = [vp, i, vp, sz]
     L.b200ais_demod_profile.argtypes = [vp, i]
+    L.b200ais_demod_set_overlap.argtypes = [vp, i]
     L.b200ais_demod_stage_ms.argtypes = [vp, vp, vp]
     _lib = L
     return L

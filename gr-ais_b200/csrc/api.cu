@@ -654,7 +654,7 @@ extern "C" int b200ais_invert_work(const uint8_t *in, uint8_t *out, size_t nitem
 
 namespace {
 constexpr int kSeg = 16;      // NCO phase checkpoint spacing (samples)
-constexpr int kMaxGroups = 4; // channel groups pipelined over streams in the host variant
+constexpr int kMaxGroups = 8; // channel groups pipelined over internal streams
 } // namespace
 
 struct b200ais_demod {
@@ -682,8 +682,10 @@ struct b200ais_demod {
     uint8_t *d_bits = nullptr;
     size_t bits_cap = 0;
     int *d_status = nullptr; // [kMaxGroups + 1]
-    cudaStream_t streams[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t done[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t streams[kMaxGroups] = {};
+    cudaEvent_t done[kMaxGroups] = {};
+    cudaEvent_t ev_fork = nullptr;
+    int overlap_groups = 4; // channel groups a *_dev call forks over internal streams (1 = none)
     bool taps_enabled = false;
     DevBuf t_sym, t_err, t_mu, t_soft;
     bool profiling = false;
@@ -820,6 +822,8 @@ extern "C" int b200ais_demod_create(b200ais_demod **out, const b200ais_demod_con
         e = cudaMemset(h->d_a, 0, sizeof(float2) * h->a_stride * C); // the zero history pads
     if (e == cudaSuccess)
         e = cudaMemset(h->d_status, 0, sizeof(int) * (kMaxGroups + 1));
+    if (e == cudaSuccess)
+        e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (int g2 = 0; g2 < kMaxGroups && e == cudaSuccess; g2++) {
         e = cudaStreamCreateWithFlags(&h->streams[g2], cudaStreamNonBlocking);
         if (e == cudaSuccess)
@@ -844,6 +848,8 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
     for (void *p : ptrs)
         if (p)
             cudaFree(p);
+    if (h->ev_fork)
+        cudaEventDestroy(h->ev_fork);
     for (int g = 0; g < kMaxGroups; g++) {
         if (h->streams[g])
             cudaStreamDestroy(h->streams[g]);
@@ -957,6 +963,16 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     return rc;
 }
 
+extern "C" int b200ais_demod_set_overlap(b200ais_demod *h, int groups)
+{
+    if (!h || groups < 1) {
+        set_error("demod_set_overlap: groups must be >= 1");
+        return B200AIS_E_INVALID;
+    }
+    h->overlap_groups = std::min(groups, kMaxGroups);
+    return B200AIS_OK;
+}
+
 extern "C" int b200ais_demod_profile(b200ais_demod *h, int enable)
 {
     if (!h)
@@ -1032,11 +1048,34 @@ extern "C" int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsa
     if (rc)
         return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), s));
-    rc = demod_launch_group(h, 0, h->channels, reinterpret_cast<const float2 *>(iq), (size_t)nsamples,
-                            nsamples, 0, bits, max_bits, nbits, h->d_tags, h->d_ntags, h->d_status, s);
-    if (rc)
-        return rc;
+    const float2 *iq2 = reinterpret_cast<const float2 *>(iq);
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
+    int groups = h->profiling ? 1 : std::min(std::min(h->overlap_groups, kMaxGroups), h->channels / 64);
+    if (groups <= 1) {
+        rc = demod_launch_group(h, 0, h->channels, iq2, (size_t)nsamples, nsamples, 0, bits, max_bits,
+                                nbits, h->d_tags, h->d_ntags, h->d_status, s);
+        if (rc)
+            return rc;
+    } else {
+        // The NCO-phase and timing-loop kernels are per-channel recurrences whose run time does
+        // not depend on the channel count; forking channel groups over internal streams lets one
+        // group's recurrences run under the other groups' throughput-bound kernels.
+        B200_CU(cudaEventRecord(h->ev_fork, s));
+        for (int g = 0; g < groups; g++) {
+            const int c0 = (int)((long long)h->channels * g / groups);
+            const int c1 = (int)((long long)h->channels * (g + 1) / groups);
+            cudaStream_t gs = h->streams[g];
+            B200_CU(cudaStreamWaitEvent(gs, h->ev_fork, 0));
+            rc = demod_launch_group(h, c0, c1 - c0, iq2 + (size_t)c0 * nsamples, (size_t)nsamples,
+                                    nsamples, 0, bits + (size_t)c0 * max_bits, max_bits, nbits + c0,
+                                    h->d_tags + (size_t)c0 * h->max_tags, h->d_ntags + c0,
+                                    h->d_status + 1 + g, gs);
+            if (rc)
+                return rc;
+            B200_CU(cudaEventRecord(h->done[g], gs));
+            B200_CU(cudaStreamWaitEvent(s, h->done[g], 0));
+        }
+    }
     if (tags)
         B200_CU(cudaMemcpyAsync(tags, h->d_tags, sizeof(b200ais_tag) * (size_t)h->max_tags * h->channels,
                                 cudaMemcpyDeviceToDevice, s));
@@ -1084,7 +1123,7 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
     }
     B200_CU(cudaMemset(h->d_status, 0, sizeof(int) * (kMaxGroups + 1)));
     // channel groups pipelined over streams: copy-in of group g+1 overlaps compute of group g
-    const int ngroups = C >= 64 ? kMaxGroups : 1;
+    const int ngroups = std::max(1, std::min(std::min(2 * h->overlap_groups, kMaxGroups), C / 64));
     for (int g = 0; g < ngroups; g++) {
         const int c0 = (int)((long long)C * g / ngroups), c1 = (int)((long long)C * (g + 1) / ngroups);
         const int cn = c1 - c0;

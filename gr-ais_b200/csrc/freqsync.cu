@@ -177,8 +177,14 @@ __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec,
         const float inc = sens * f;
         for (int sgi = 0; sgi < segs_per_vec; sgi++) {
             ckpt[((size_t)b * segs_per_vec + sgi) * channels + c] = ph;
-            for (int i = 0; i < seg; i++)
-                ph = nco_step(ph, inc);
+            if (seg == 16) {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    ph = nco_step(ph, inc);
+            } else {
+                for (int i = 0; i < seg; i++)
+                    ph = nco_step(ph, inc);
+            }
         }
     }
 }

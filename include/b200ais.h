@@ -218,6 +218,9 @@ enum {
     B200AIS_STAGE_T_COUNT = 7
 };
 B200AIS_API int b200ais_demod_profile(b200ais_demod *h, int enable);
+/* Number of channel groups a work call forks over internal CUDA streams (default 4; 1 = run
+ * every kernel on the caller's stream).  The caller's stream still orders the whole call. */
+B200AIS_API int b200ais_demod_set_overlap(b200ais_demod *h, int groups);
 B200AIS_API int b200ais_demod_stage_ms(b200ais_demod *h, double *stage_ms, int *calls);
 
 /* Device pointers to the chain's intermediate streams of the last work call (parity

@@ -79,3 +79,19 @@ def test_ragged_and_silent_inputs(oracle, templates):
     x[1] = 0  # all-zero channel: freqest maxpos carry-over quirk, AGC floor 1e-4
     x[2, 1024:3072] = 0
     _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC)
+
+
+def test_overlap_groups_do_not_change_results(oracle, templates):
+    """forking channel groups over internal streams is a scheduling choice only"""
+    x, _ = _records(8, 4096, nbursts=1, snr_db=20)
+    x = np.tile(x, (32, 1))  # 256 channels
+    outs = []
+    for groups in (1, 4):
+        d = ais_demod(channels=256, max_samples=4096, template=templates[120])
+        d.set_overlap(groups)
+        outs.append(d.work(x))
+        d.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    r = oracle.demod_chain(x[5], templates[120])
+    assert np.array_equal(outs[1][0][5, :outs[1][1][5]], r["bits"])
