@@ -74,6 +74,63 @@ k_mix_agc(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, i
     for (int i = threadIdx.x; i < span; i += blockDim.x)
         env[i] = agc_envelope(ys[i].x, ys[i].y);
     __syncthreads();
+    if (W == 512) {
+        // van Herk / Gil-Werman: per aligned block of W, prefix maxima P and suffix maxima S;
+        // max over [i, i+W-1] = max(S[i], P[i+W-1]).  One warp per block, 16 elements per lane,
+        // lane carries combined with shuffles.  max() is exact, so any evaluation order is.
+        float *sfx = env + (kAgcTile + halo);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int nblocks = (span + 511) >> 9;
+        for (int blk = warp; blk < nblocks; blk += kAgcThreads / 32) {
+            const int base = blk * 512 + lane * 16;
+            float v[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                v[k] = (base + k < span) ? env[base + k] : 0.0f;
+            float pre[16], suf[16];
+            pre[0] = v[0];
+#pragma unroll
+            for (int k = 1; k < 16; k++)
+                pre[k] = fmaxf(pre[k - 1], v[k]);
+            suf[15] = v[15];
+#pragma unroll
+            for (int k = 14; k >= 0; k--)
+                suf[k] = fmaxf(suf[k + 1], v[k]);
+            // exclusive scans of the lane totals (envelopes are >= 0, so 0 is the identity)
+            float up = pre[15], dn = suf[0];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float a = __shfl_up_sync(0xffffffffu, up, o);
+                const float b = __shfl_down_sync(0xffffffffu, dn, o);
+                if (lane >= o)
+                    up = fmaxf(up, a);
+                if (lane + o < 32)
+                    dn = fmaxf(dn, b);
+            }
+            float cup = __shfl_up_sync(0xffffffffu, up, 1);
+            float cdn = __shfl_down_sync(0xffffffffu, dn, 1);
+            if (lane == 0)
+                cup = 0.0f;
+            if (lane == 31)
+                cdn = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (base + k < span) {
+                    env[base + k] = fmaxf(cup, pre[k]);
+                    sfx[base + k] = fmaxf(cdn, suf[k]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tile; i += blockDim.x) {
+            const float m = fmaxf(sfx[i], env[i + W - 1]);
+            const float max_env = fmaxf(1e-4f, m);
+            const float gain = reference / max_env;
+            const float2 y = ys[i];
+            oc[t0 + i] = make_float2(gain * y.x, gain * y.y);
+        }
+        return;
+    }
     // sparse-table doubling: after the pass for width k, env[i] = max(env0[i .. i+k-1]) (clipped)
     int p = 1;
     constexpr int kMaxPer = (kAgcTile + 2047 + kAgcThreads - 1) / kAgcThreads;
@@ -127,9 +184,9 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
     if (rc)
         return rc;
     int halo = (stages & B200AIS_STAGE_AGC) ? agc_nsamples - 1 : 0;
-    size_t smem = (size_t)(kAgcTile + halo) * (sizeof(float2) + sizeof(float));
+    size_t smem = (size_t)(kAgcTile + halo) * (sizeof(float2) + 2 * sizeof(float));
     B200_CU(cudaFuncSetAttribute(k_mix_agc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((kAgcTile + 2047) * (sizeof(float2) + sizeof(float)))));
+                                 (int)((kAgcTile + 2047) * (sizeof(float2) + 2 * sizeof(float)))));
     dim3 grid((n1 + kAgcTile - 1) / kAgcTile, channels);
     k_mix_agc<<<grid, kAgcThreads, smem, s>>>(x, x_stride, channels, n1, fftlen, fhat, vstride, ckpt, seg,
                                               sens, stages, agc_nsamples, agc_reference,

@@ -109,6 +109,178 @@ k_sqfft_freqest(const float2 *__restrict__ x, size_t x_stride, int vstride, int 
         raw[(size_t)c * vstride + b] = (best.j == 0x7fffffff) ? -1 : best.j + offset / 2;
 }
 
+// ---- 1024-point fast path: 64 threads, 16 values per thread, three register passes ----
+//
+// Same radix-2 decimation-in-time graph as the generic kernel (and the oracle): stage s
+// combines X[e] and X[e + 2^(s-1)] with W[(e mod 2^(s-1)) * 1024/2^s].  Stages 1-4 touch
+// index bits 0-3, stages 5-7 bits 4-6, stages 8-10 bits 7-9, so a thread can hold all the
+// elements that differ only in those bits and run the stages in registers; shared memory
+// is crossed twice instead of ten times.  W = 1 and W = -i (exact table entries) skip the
+// multiply: fma(1,b,-0) = b and fma(0,x,y) = y are exact.
+constexpr int kFast = 64;
+
+__device__ __forceinline__ int fphys(int e) { return e + (e >> 4); } // 1-in-16 padding
+
+__device__ __forceinline__ void bf(float2 &a, float2 &b, const float2 w)
+{
+    const float2 t = cmul_fma(w, b), a0 = a;
+    a = make_float2(a0.x + t.x, a0.y + t.y);
+    b = make_float2(a0.x - t.x, a0.y - t.y);
+}
+__device__ __forceinline__ void bf_one(float2 &a, float2 &b) // W = (1, 0)
+{
+    const float2 t = b, a0 = a;
+    a = make_float2(a0.x + t.x, a0.y + t.y);
+    b = make_float2(a0.x - t.x, a0.y - t.y);
+}
+__device__ __forceinline__ void bf_mi(float2 &a, float2 &b) // W = (0, -1): t = (b.y, -b.x)
+{
+    const float2 a0 = a, b0 = b;
+    a = make_float2(a0.x + b0.y, a0.y - b0.x);
+    b = make_float2(a0.x - b0.y, a0.y + b0.x);
+}
+
+// three radix-2 stages on 8 register values whose pair distances are 1, 2, 4
+__device__ __forceinline__ void pass8(float2 (&u)[8], const float2 w1, const float2 (&w2)[2],
+                                      const float2 (&w3)[4])
+{
+#pragma unroll
+    for (int q = 0; q < 8; q += 2)
+        bf(u[q], u[q + 1], w1);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        if (!(q & 2))
+            bf(u[q], u[q + 2], w2[q & 1]);
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        bf(u[q], u[q + 4], w3[q]);
+}
+
+__global__ void __launch_bounds__(kFast)
+k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
+                     const float2 *__restrict__ tw, int offset, int *__restrict__ raw)
+{
+    constexpr int N = 1024;
+    __shared__ float2 cx[N + N / 16];
+    __shared__ float hs[N];
+    __shared__ Best sh[kFast / 32];
+    __shared__ float s_max[kFast / 32];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x, c = blockIdx.y;
+    const float2 *src = x + (size_t)c * x_stride + (size_t)b * N;
+
+    // ---- pass A: stages 1-4 on elements e = 16*tid + q, loaded from x[bitrev10(e)] ----
+    {
+        float2 v[16];
+        const int r6 = (int)(__brev((unsigned)tid) >> 26); // bitrev6(tid)
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int r4 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
+            const float2 in = src[r4 * 64 + r6];
+            v[q] = cmul_fma(in, in); // blocks.multiply_cc(x, x)
+        }
+        const float2 w128 = tw[128], w384 = tw[384];
+        const float2 w64 = tw[64], w192 = tw[192], w320 = tw[320], w448 = tw[448];
+#pragma unroll
+        for (int q = 0; q < 16; q += 2)
+            bf_one(v[q], v[q + 1]);
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+            bf_one(v[q], v[q + 2]);
+            bf_mi(v[q + 1], v[q + 3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q += 8) {
+            bf_one(v[q], v[q + 4]);
+            bf(v[q + 1], v[q + 5], w128);
+            bf_mi(v[q + 2], v[q + 6]);
+            bf(v[q + 3], v[q + 7], w384);
+        }
+        bf_one(v[0], v[8]);
+        bf(v[1], v[9], w64);
+        bf(v[2], v[10], w128);
+        bf(v[3], v[11], w192);
+        bf_mi(v[4], v[12]);
+        bf(v[5], v[13], w320);
+        bf(v[6], v[14], w384);
+        bf(v[7], v[15], w448);
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+            cx[17 * tid + q] = v[q]; // fphys(16*tid + q)
+    }
+    __syncthreads();
+    // ---- pass B: stages 5-7 on e = hi*128 + q*16 + lo ----
+#pragma unroll 1
+    for (int g = tid; g < 128; g += kFast) {
+        const int hi = g >> 4, lo = g & 15;
+        float2 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            u[q] = cx[fphys(hi * 128 + q * 16 + lo)];
+        const float2 w1 = tw[lo << 5];
+        const float2 w2[2] = { tw[lo << 4], tw[(lo + 16) << 4] };
+        const float2 w3[4] = { tw[lo << 3], tw[(lo + 16) << 3], tw[(lo + 32) << 3], tw[(lo + 48) << 3] };
+        pass8(u, w1, w2, w3);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            cx[fphys(hi * 128 + q * 16 + lo)] = u[q];
+    }
+    __syncthreads();
+    // ---- pass C: stages 8-10 on e = q*128 + lo; output bin k = e (natural order) ----
+#pragma unroll 1
+    for (int lo = tid; lo < 128; lo += kFast) {
+        float2 u[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            u[q] = cx[fphys(q * 128 + lo)];
+        const float2 w1 = tw[lo << 2];
+        const float2 w2[2] = { tw[lo << 1], tw[(lo + 128) << 1] };
+        const float2 w3[4] = { tw[lo], tw[lo + 128], tw[lo + 256], tw[lo + 384] };
+        pass8(u, w1, w2, w3);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = q * 128 + lo;
+            cx[fphys(k)] = u[q];
+            // float estimate of |X[k]| for the pre-filter, stored in fft-shifted order
+            hs[(k + N / 2) & (N - 1)] = sqrtf(__fmaf_rn(u[q].x, u[q].x, u[q].y * u[q].y));
+        }
+    }
+    __syncthreads();
+    // ---- freqest: argmax_j |S[j]| + |S[j+offset]| with strict '>' in ascending j ----
+    // The float estimates are within 3e-7 relative of the canonical (double-evaluated) sums,
+    // so only bins within 2e-6 of the estimated maximum can be the canonical argmax; those
+    // few are re-evaluated canonically.  Degenerate spectra take the exact path for every bin.
+    float m_est = 0.0f;
+    for (int j = tid; j < N - offset; j += kFast)
+        m_est = fmaxf(m_est, hs[j] + hs[j + offset]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m_est = fmaxf(m_est, __shfl_xor_sync(0xffffffffu, m_est, o));
+    if ((tid & 31) == 0)
+        s_max[tid >> 5] = m_est;
+    __syncthreads();
+    m_est = fmaxf(s_max[0], s_max[1]);
+    const bool exact_all = !(m_est > 1e-12f && m_est < 1e30f);
+    const float cut = m_est * (1.0f - 2e-6f);
+    Best best;
+    best.e = 0.0f;
+    best.j = 0x7fffffff;
+    for (int j = tid; j < N - offset; j += kFast) {
+        if (exact_all || hs[j] + hs[j + offset] >= cut) {
+            const float2 p = cx[fphys((j + N / 2) & (N - 1))];
+            const float2 q2 = cx[fphys((j + offset + N / 2) & (N - 1))];
+            const float e = hypot_canon(p.x, p.y) + hypot_canon(q2.x, q2.y);
+            if (e > best.e) {
+                best.e = e;
+                best.j = j;
+            }
+        }
+    }
+    best = block_argmax(best, sh);
+    if (tid == 0)
+        raw[(size_t)c * vstride + b] = (best.j == 0x7fffffff) ? -1 : best.j + offset / 2;
+}
+
 // Stand-alone freqest on caller-supplied spectra (any fftlen).
 __global__ void __launch_bounds__(kFftThreads)
 k_freqest_spec(const float2 *__restrict__ spec, int nvec, int n, int offset, int *__restrict__ raw)
@@ -215,7 +387,10 @@ int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nve
         return rc;
     size_t smem = (size_t)fftlen * (sizeof(float2) + sizeof(float));
     dim3 grid(nvec, channels);
-    k_sqfft_freqest<<<grid, kFftThreads, smem, s>>>(x, x_stride, vstride, fftlen, lg, tw, offset, raw);
+    if (fftlen == 1024)
+        k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw);
+    else
+        k_sqfft_freqest<<<grid, kFftThreads, smem, s>>>(x, x_stride, vstride, fftlen, lg, tw, offset, raw);
     B200_LAUNCH_CHECK("k_sqfft_freqest");
     return B200AIS_OK;
 }
