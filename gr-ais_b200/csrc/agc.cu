@@ -166,6 +166,106 @@ k_mix_agc(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, i
     }
 }
 
+// ---- fast path for the reference's constants: feedforward_agc_cc(512, 2), 16-sample
+// phase checkpoints.  One block = 4096 consecutive samples (512 of history + 3584 outputs);
+// thread t owns samples [16t, 16t+16): it re-runs the NCO from its checkpoint, mixes, takes
+// the envelopes and -- because a warp's 32 x 16 samples are exactly one aligned 512 block --
+// finishes the van Herk prefix/suffix maxima with warp shuffles without leaving registers.
+constexpr int kFSpan = 4096;
+constexpr int kFHalo = 512;
+constexpr int kFOut = kFSpan - kFHalo;
+constexpr int kFPad = kFSpan + kFSpan / 16; // 1-in-16 padding: a thread's 16 items hit 16 banks
+
+__global__ void __launch_bounds__(256)
+k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
+             const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
+             int do_mix, float reference, const float2 *__restrict__ sine,
+             float2 *__restrict__ out, size_t out_stride)
+{
+    extern __shared__ float2 ys[];               // [kFPad]
+    float *P = reinterpret_cast<float *>(ys + kFPad); // prefix maxima  [kFPad]
+    float *S = P + kFPad;                             // suffix maxima  [kFPad]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int c = blockIdx.y;
+    const int t0 = blockIdx.x * kFOut;
+    const int n0 = t0 - kFHalo + 16 * tid; // absolute index of this thread's first sample
+    const float2 *xc = x + (size_t)c * x_stride;
+
+    float2 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        v[k] = make_float2(0.0f, 0.0f);
+    if (n0 >= 0 && n0 < n1) {
+        if (do_mix) { // n1 is a multiple of fftlen, itself a multiple of 16: whole segments only
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                v[k] = xc[n0 + k];
+            float ph = ckpt[(size_t)(n0 >> 4) * channels + c];
+            const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                ph = nco_step(ph, inc);
+                float sn, cs;
+                fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
+                v[k] = cmul_fma(v[k], make_float2(cs, sn));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (n0 + k < n1)
+                    v[k] = xc[n0 + k];
+        }
+    }
+    float pre[16], suf[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        ys[17 * tid + k] = v[k];
+        pre[k] = agc_envelope(v[k].x, v[k].y);
+        suf[k] = pre[k];
+    }
+#pragma unroll
+    for (int k = 1; k < 16; k++)
+        pre[k] = fmaxf(pre[k - 1], pre[k]);
+#pragma unroll
+    for (int k = 14; k >= 0; k--)
+        suf[k] = fmaxf(suf[k + 1], suf[k]);
+    // exclusive scans of the lane totals across the warp's 512-sample block (max is exact and
+    // envelopes are >= 0, so 0 is the identity)
+    float up = pre[15], dn = suf[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float a = __shfl_up_sync(0xffffffffu, up, o);
+        const float b = __shfl_down_sync(0xffffffffu, dn, o);
+        if (lane >= o)
+            up = fmaxf(up, a);
+        if (lane + o < 32)
+            dn = fmaxf(dn, b);
+    }
+    float cup = __shfl_up_sync(0xffffffffu, up, 1);
+    float cdn = __shfl_down_sync(0xffffffffu, dn, 1);
+    if (lane == 0)
+        cup = 0.0f;
+    if (lane == 31)
+        cdn = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        P[17 * tid + k] = fmaxf(cup, pre[k]);
+        S[17 * tid + k] = fmaxf(cdn, suf[k]);
+    }
+    __syncthreads();
+    // out[t] = y[t-511] * (reference / max(1e-4, max env(y[t-511 .. t]))); local index of
+    // y[t-511] is i+1, of y[t] is i+512
+    float2 *oc = out + (size_t)c * out_stride;
+    const int nout = min(kFOut, n1 - t0);
+    for (int i = tid; i < nout; i += 256) {
+        const int a = i + 1, b = i + kFHalo;
+        const float m = fmaxf(S[a + (a >> 4)], P[b + (b >> 4)]);
+        const float gain = reference / fmaxf(1e-4f, m);
+        const float2 y = ys[a + (a >> 4)];
+        oc[t0 + i] = make_float2(gain * y.x, gain * y.y);
+    }
+}
+
 } // namespace
 
 int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int fftlen,
@@ -183,6 +283,20 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
     int rc = get_tables(&tb);
     if (rc)
         return rc;
+    if ((stages & B200AIS_STAGE_AGC) && agc_nsamples == 512 && seg == 16 &&
+        (!(stages & B200AIS_STAGE_FREQSYNC) || (fftlen % 16 == 0 && n1 % fftlen == 0))) {
+        const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float));
+        B200_CU(cudaFuncSetAttribute(k_mix_agc512, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem512));
+        dim3 grid512((n1 + kFOut - 1) / kFOut, channels);
+        k_mix_agc512<<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat, vstride,
+                                                   ckpt, sens, (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0,
+                                                   agc_reference,
+                                                   reinterpret_cast<const float2 *>(tb.sine), out,
+                                                   out_stride);
+        B200_LAUNCH_CHECK("k_mix_agc512");
+        return B200AIS_OK;
+    }
     int halo = (stages & B200AIS_STAGE_AGC) ? agc_nsamples - 1 : 0;
     size_t smem = (size_t)(kAgcTile + halo) * (sizeof(float2) + 2 * sizeof(float));
     B200_CU(cudaFuncSetAttribute(k_mix_agc, cudaFuncAttributeMaxDynamicSharedMemorySize,

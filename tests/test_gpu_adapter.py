@@ -20,7 +20,7 @@ def test_cpp_adapter_chain_matches_oracle(oracle, templates, tmp_path):
     exe = os.path.join(ADAPTER, "qa_adapter")
     assert os.path.exists(exe), "build gr_adapter first (__graft_entry__.build())"
     t = templates[120]
-    L, n, ncalls = 120, 137 * 6, 5
+    L, n, ncalls = 120, 137 * 12, 8
     x, _ = synth.make_record(1, n=ncalls * n + L, nbursts=2, snr_db=25)
     x = (x * 1.8).astype(np.complex64)
     fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"

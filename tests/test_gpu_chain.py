@@ -14,13 +14,14 @@ def _records(channels, n, **kw):
     return np.stack([r[0] for r in recs]), [r[1] for r in recs]
 
 
-def _compare_chain(oracle, x, tmpl, stages, corr_chunk=0, threshold=0.9, check_payload=None):
+def _compare_chain(oracle, x, tmpl, stages, corr_chunk=0, threshold=0.9, agc=(512, 2.0)):
     C, n = x.shape
     d = ais_demod(channels=C, max_samples=n, template=tmpl, stages=stages, corr_chunk=corr_chunk,
-                  threshold=threshold, max_tags=1024)
+                  threshold=threshold, max_tags=1024, agc=agc)
     d.enable_taps(True)
     bits, nbits, tags, ntags = d.work(x)
-    cfg = oracle.chain_cfg(stages=stages, corr_chunk=corr_chunk, threshold=threshold)
+    cfg = oracle.chain_cfg(stages=stages, corr_chunk=corr_chunk, threshold=threshold,
+                           agc_nsamples=agc[0], agc_reference=agc[1])
     fh = d.read_tap(B.TAP_FHAT) if stages & B.STAGE_FREQSYNC else None
     agc = d.read_tap(B.TAP_AGC)
     sym, err, mu, soft = (d.read_tap(t) for t in (B.TAP_SYM, B.TAP_ERR, B.TAP_MU, B.TAP_SOFT))
@@ -95,3 +96,15 @@ def test_overlap_groups_do_not_change_results(oracle, templates):
         assert np.array_equal(a, b)
     r = oracle.demod_chain(x[5], templates[120])
     assert np.array_equal(outs[1][0][5, :outs[1][1][5]], r["bits"])
+
+
+@pytest.mark.parametrize("agc", [(100, 1.0), (513, 2.0), (1, 0.5), (2048, 3.0)])
+def test_other_agc_windows_take_the_generic_kernel(oracle, templates, agc):
+    x, _ = _records(3, 8192, nbursts=2, snr_db=20)
+    _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC, threshold=0.5, agc=agc)
+
+
+def test_long_record_many_tiles(oracle, templates):
+    """several AGC tiles (3584 outputs each), corr tiles and two corr_est work chunks"""
+    x, _ = _records(2, 48000, nbursts=4, snr_db=22)
+    _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC)
