@@ -330,6 +330,7 @@ __global__ void k_freqest_resolve(const int *__restrict__ raw, int channels, int
 // float recurrence (one rounding per sample) and cannot be evaluated out of order.  Only
 // the recurrence runs here; phases are checkpointed every `seg` samples so the mixing can
 // be done by many threads in k_mix_agc.
+template <int kSeg>
 __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec, int vstride, int n,
                             float binsize, float sens, float *__restrict__ fhat,
                             float *__restrict__ ckpt, int seg)
@@ -340,6 +341,7 @@ __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec,
     float ph = 0.0f;
     int maxpos = 0;
     const int segs_per_vec = n / seg;
+    float *cp = ckpt + c; // ckpt[segment * channels + c], walked with a running pointer
     for (int b = 0; b < nvec; b++) {
         int r = raw[(size_t)c * vstride + b];
         if (r >= 0)
@@ -348,11 +350,19 @@ __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec,
         fhat[(size_t)c * vstride + b] = f;
         const float inc = sens * f;
         for (int sgi = 0; sgi < segs_per_vec; sgi++) {
-            ckpt[((size_t)b * segs_per_vec + sgi) * channels + c] = ph;
-            if (seg == 16) {
+            *cp = ph;
+            cp += channels;
+            if (kSeg == 16) {
+                const float ph0 = ph;
+                bool bad = false;
 #pragma unroll
                 for (int i = 0; i < 16; i++)
-                    ph = nco_step(ph, inc);
+                    ph = nco_step_nobranch(ph, inc, bad);
+                if (bad) { // |phase| ran past 4 pi: take the general fmod path for this segment
+                    ph = ph0;
+                    for (int i = 0; i < 16; i++)
+                        ph = nco_step(ph, inc);
+                }
             } else {
                 for (int i = 0; i < seg; i++)
                     ph = nco_step(ph, inc);
@@ -424,9 +434,13 @@ int launch_nco_phase(const int *raw, int channels, int nvec, int vstride, int ff
     if (nvec <= 0 || channels <= 0)
         return B200AIS_OK;
     int threads = 32; // latency-bound serial walk: spread the channels over as many SMs as possible
-    k_nco_phase<<<(channels + threads - 1) / threads, threads, 0, s>>>(raw, channels, nvec, vstride,
-                                                                        fftlen, binsize, sens, fhat,
-                                                                        ckpt, seg);
+    const int blocks = (channels + threads - 1) / threads;
+    if (seg == 16)
+        k_nco_phase<16><<<blocks, threads, 0, s>>>(raw, channels, nvec, vstride, fftlen, binsize, sens,
+                                                   fhat, ckpt, seg);
+    else
+        k_nco_phase<0><<<blocks, threads, 0, s>>>(raw, channels, nvec, vstride, fftlen, binsize, sens,
+                                                  fhat, ckpt, seg);
     B200_LAUNCH_CHECK("k_nco_phase");
     return B200AIS_OK;
 }

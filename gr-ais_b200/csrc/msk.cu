@@ -42,7 +42,8 @@ constexpr int kMskChunk = 32;              // samples per prefetch chunk
 constexpr int kMskRing = 128;               // ring slots per channel (4 chunks)
 constexpr int kMskMirror = 8;               // slots 0..7 repeated after the ring: 8-sample reads never wrap
 constexpr int kMskPitch = kMskRing + kMskMirror + 2; // 138 float2: rows stay 16-byte aligned
-constexpr int kMskNeed = 16;                // samples past iidx one step may touch (tag jump + 8 taps)
+constexpr int kMskInner = 4;                // half-symbol steps per round of warp votes
+constexpr int kMskNeed = 5 * kMskInner + 10; // samples past iidx kMskInner steps may touch (advance <= 3, tag jump <= 2, 8 taps)
 constexpr int kMskAhead = 64;               // issue a chunk once the lane is this close to it
 
 __device__ __forceinline__ void cp_async_8(unsigned smem, const void *gmem, int src_bytes)
@@ -139,7 +140,9 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     int issue_end = 0; // samples [0, issue_end) of this lane's channel have been requested
     int ready_end = 0; // samples [0, ready_end) are known to have landed
     int err_code = 0;
+    bool bad_imu = false;
     bool active = true;
+    float2 *op = oc; // next symbol slot
     const unsigned FULL = __activemask(); // the lanes that own a channel (a prefix of the warp)
 
     // cp.async groups are tracked per warp, not per lane, so issuing and waiting happen in
@@ -180,80 +183,86 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             cp_async_wait_all();
             ready_end = issue_end;
         }
-        if (!active)
-            continue;
-        // tag reset (:139-164); rare, so an integer window test guards the float compare
-        if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
-            if ((float)tag_off < ((float)iidx + p.sps_half)) {
-                if (tag_val == tag_val) { // NaN: drop the tag, no reset (:144-147)
-                    mu = tag_val;
-                    iidx = tag_off;
-                    if (mu < 0) {
-                        mu = mu + 1.0f;
-                        iidx--;
+        // kMskInner half-symbol steps between two rounds of votes; the steps are written
+        // without data-dependent branches (a lone warp pays ~20 cycles per taken branch)
+#pragma unroll
+        for (int it = 0; it < kMskInner; it++) {
+            if (active) {
+                // tag reset (:139-164); rare: an integer window test guards the float compare
+                if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
+                    if ((float)tag_off < ((float)iidx + p.sps_half)) {
+                        if (tag_val == tag_val) { // NaN: drop the tag, no reset (:144-147)
+                            mu = tag_val;
+                            iidx = tag_off;
+                            if (mu < 0) {
+                                mu = mu + 1.0f;
+                                iidx--;
+                            }
+                            div = 0;
+                            omega = p.sps_half;
+                        }
+                        fetch_tag(thead + 1);
                     }
-                    div = 0;
-                    omega = p.sps_half;
                 }
-                fetch_tag(thead + 1);
+                // mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), in[0..7] . reversed row
+                const int imu = __float2int_rn(mu * 128.0f);
+                const int imu_c = min(max(imu, 0), 128);
+                bad_imu |= (imu != imu_c); // the reference's interpolator throws here
+                const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8);
+                const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8 + 4);
+                const float2 *sp = my + (iidx & (kMskRing - 1));
+                const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+                const float2 s4 = sp[4], s5 = sp[5], s6 = sp[6], s7 = sp[7];
+                // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
+                const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
+                const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
+                const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
+                const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
+                float2 v;
+                v.x = (p0r + p1r) + (p2r + p3r);
+                v.y = (p0i + p1i) + (p2i + p3i);
+                // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
+                const float vxy = v.x * v.y;
+                const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
+                const float d_re = psq_re, d_im = -psq_im;
+                const float nl_re = sq_re * d_re - sq_im * d_im;
+                const float nl_im = sq_re * d_im + sq_im * d_re;
+                const float err_raw = nl_re - diff1_re;
+                // odd half-steps run the loop filter (:179-184); evaluated always, selected by parity
+                const bool odd = div & 1;
+                const float err_c = branchless_clip(err_raw, 3.0f);
+                const float om_t = omega + p.gain_omega * err_c;
+                const float om_n = p.sps_half + branchless_clip(om_t - p.sps_half, p.limit);
+                const float mu_n = mu + p.gain * err_c;
+                omega = odd ? om_n : omega;
+                mu = odd ? mu_n : mu;
+                if (!odd || p.osps == 2) {
+                    *op = v;
+                    op++;
+                    if (kDebug) {
+                        if (oe)
+                            oe[oidx] = odd ? err_c : err_raw;
+                        if (om)
+                            om[oidx] = mu;
+                    }
+                    oidx++;
+                }
+                div++;
+                vlast = v;
+                psq_re = sq_re;
+                psq_im = sq_im;
+                diff1_re = nl_re;
+                diff1_im = nl_im;
+                mu = mu + omega;
+                const float fl = floorf(mu);
+                iidx += (int)fl;
+                mu = mu - fl;
+                active = (oidx < noutput_items) && (iidx < ninp);
             }
         }
-        // mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), in[0..7] . reversed row
-        const int imu = __float2int_rn(mu * 128.0f);
-        if ((unsigned)imu > 128u) {
-            err_code = B200AIS_E_INTERP;
-            active = false;
-            continue;
-        }
-        const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu * 8);
-        const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu * 8 + 4);
-        const float2 *sp = my + (iidx & (kMskRing - 1));
-        const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
-        const float2 s4 = sp[4], s5 = sp[5], s6 = sp[6], s7 = sp[7];
-        // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
-        const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
-        const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
-        const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
-        const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
-        float2 v;
-        v.x = (p0r + p1r) + (p2r + p3r);
-        v.y = (p0i + p1i) + (p2i + p3i);
-        // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
-        const float vxy = v.x * v.y;
-        const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
-        const float d_re = psq_re, d_im = -psq_im;
-        const float nl_re = sq_re * d_re - sq_im * d_im;
-        const float nl_im = sq_re * d_im + sq_im * d_re;
-        float err_out = nl_re - diff1_re;
-        const bool odd = div & 1;
-        if (odd) {
-            err_out = branchless_clip(err_out, 3.0f);
-            omega = omega + p.gain_omega * err_out;
-            omega = p.sps_half + branchless_clip(omega - p.sps_half, p.limit);
-            mu = mu + p.gain * err_out;
-        }
-        if (!odd || p.osps == 2) {
-            oc[oidx] = v;
-            if (kDebug) {
-                if (oe)
-                    oe[oidx] = err_out;
-                if (om)
-                    om[oidx] = mu;
-            }
-            oidx++;
-        }
-        div++;
-        vlast = v;
-        psq_re = sq_re;
-        psq_im = sq_im;
-        diff1_re = nl_re;
-        diff1_im = nl_im;
-        mu = mu + omega;
-        const float fl = floorf(mu);
-        iidx += (int)fl;
-        mu = mu - fl;
-        active = (oidx < noutput_items) && (iidx < ninp);
     }
+    if (bad_imu)
+        err_code = B200AIS_E_INTERP;
     cp_async_wait_all();
     st.mu = mu;
     st.omega = omega;
