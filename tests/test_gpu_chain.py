@@ -108,3 +108,18 @@ def test_long_record_many_tiles(oracle, templates):
     """several AGC tiles (3584 outputs each), corr tiles and two corr_est work chunks"""
     x, _ = _records(2, 48000, nbursts=4, snr_db=22)
     _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC)
+
+
+def test_snr_sweep_gpu_equals_oracle():
+    """BASELINE configs[4] in miniature: impaired bursts at three SNRs, GPU == oracle, and the
+    packet-detect rate rises with SNR"""
+    import subprocess, sys, os, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "snr_sweep.py"), "--channels", "48",
+                        "--oracle-channels", "48", "--seconds", "0.5", "--snrs", "0", "10", "20"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [json.loads(l) for l in r.stdout.strip().splitlines()]
+    assert all(row["gpu_equals_oracle_on_subset"] for row in rows)
+    assert all(row["gpu_detect"] == row["oracle_detect"] and row["gpu_crc"] == row["oracle_crc"] for row in rows)
+    assert rows[-1]["gpu_detect"] >= rows[0]["gpu_detect"] and rows[-1]["gpu_crc"] >= 0.5
