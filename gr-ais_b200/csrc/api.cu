@@ -85,26 +85,47 @@ struct b200ais_corr_est {
     float thresh = 0;
     int nsamples = 0;
     std::vector<float> taps; // stored FIR taps, interleaved (what symbols() returns)
-    float2 *d_taps_time = nullptr;
+    float2 *d_hbr = nullptr;  // transformed taps, bit-reversed order [fftsize]
+    float2 *d_tail[2] = { nullptr, nullptr }; // fft_filter tail [channels][L-1], ping-pong
+    int tail_cur = 0, tail_L = 0;
     int *d_status = nullptr;
     cudaStream_t stream = nullptr;
-    DevBuf mask, in, out0, out1, tags, ntags;
+    DevBuf mask, corr, in, out0, out1, tags, ntags;
     std::mutex lock; // d_setlock (lib/corr_est_cc_impl.cc:135,169)
 };
 
+// kernel::fft_filter_ccc::set_taps: new transformed taps; the tail keeps its contents and is
+// resized to ntaps - 1 (std::vector::resize)
 static int corr_upload_taps(b200ais_corr_est *h)
 {
-    // time order g[m] pairs with sample t-L+1+m: g[m] = stored[L-1-m]
-    std::vector<float2> g((size_t)h->L);
-    for (int m = 0; m < h->L; m++) {
-        g[m].x = h->taps[2 * (h->L - 1 - m)];
-        g[m].y = h->taps[2 * (h->L - 1 - m) + 1];
+    const int F = corr_fft_size(h->L);
+    std::vector<float2> hbr((size_t)F);
+    make_corr_spectrum(h->taps.data(), h->L, hbr.data());
+    if (h->d_hbr)
+        cudaFree(h->d_hbr);
+    h->d_hbr = nullptr;
+    B200_CU(cudaMalloc(&h->d_hbr, sizeof(float2) * hbr.size()));
+    B200_CU(cudaMemcpy(h->d_hbr, hbr.data(), sizeof(float2) * hbr.size(), cudaMemcpyHostToDevice));
+    const size_t tl = (size_t)std::max(h->L - 1, 1), C = (size_t)h->channels;
+    float2 *nt[2] = { nullptr, nullptr };
+    for (int k = 0; k < 2; k++) {
+        B200_CU(cudaMalloc(&nt[k], sizeof(float2) * tl * C));
+        B200_CU(cudaMemset(nt[k], 0, sizeof(float2) * tl * C));
     }
-    if (h->d_taps_time)
-        cudaFree(h->d_taps_time);
-    h->d_taps_time = nullptr;
-    B200_CU(cudaMalloc(&h->d_taps_time, sizeof(float2) * g.size()));
-    B200_CU(cudaMemcpy(h->d_taps_time, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice));
+    if (h->d_tail[h->tail_cur] && h->tail_L > 1) {
+        const size_t keep = (size_t)std::min(h->tail_L, h->L) - 1;
+        if (keep)
+            B200_CU(cudaMemcpy2D(nt[0], tl * sizeof(float2), h->d_tail[h->tail_cur],
+                                 (size_t)(h->tail_L - 1) * sizeof(float2), keep * sizeof(float2), C,
+                                 cudaMemcpyDeviceToDevice));
+    }
+    for (int k = 0; k < 2; k++) {
+        if (h->d_tail[k])
+            cudaFree(h->d_tail[k]);
+        h->d_tail[k] = nt[k];
+    }
+    h->tail_cur = 0;
+    h->tail_L = h->L;
     return B200AIS_OK;
 }
 
@@ -112,8 +133,8 @@ extern "C" int b200ais_corr_est_create(b200ais_corr_est **out, const float *symb
                                        int nsymbols, float sps, unsigned mark_delay,
                                        float threshold, int channels)
 {
-    if (!out || !symbols_iq || nsymbols < 1 || nsymbols > 4096 || channels < 1) {
-        set_error("corr_est_create: need 1..4096 symbols and channels >= 1");
+    if (!out || !symbols_iq || nsymbols < 5 || nsymbols > 2048 || channels < 1) {
+        set_error("corr_est_create: need 5..2048 symbols and channels >= 1");
         return B200AIS_E_INVALID;
     }
     b200ais_corr_est *h = new (std::nothrow) b200ais_corr_est;
@@ -159,13 +180,17 @@ extern "C" int b200ais_corr_est_destroy(b200ais_corr_est *h)
 {
     if (!h)
         return B200AIS_OK;
-    if (h->d_taps_time)
-        cudaFree(h->d_taps_time);
+    if (h->d_hbr)
+        cudaFree(h->d_hbr);
+    for (int k = 0; k < 2; k++)
+        if (h->d_tail[k])
+            cudaFree(h->d_tail[k]);
     if (h->d_status)
         cudaFree(h->d_status);
     if (h->stream)
         cudaStreamDestroy(h->stream);
     h->mask.release();
+    h->corr.release();
     h->in.release();
     h->out0.release();
     h->out1.release();
@@ -178,8 +203,8 @@ extern "C" int b200ais_corr_est_destroy(b200ais_corr_est *h)
 extern "C" int b200ais_corr_est_set_symbols(b200ais_corr_est *h, const float *symbols_iq,
                                             int nsymbols)
 {
-    if (!h || !symbols_iq || nsymbols < 1 || nsymbols > 4096) {
-        set_error("set_symbols: need 1..4096 symbols");
+    if (!h || !symbols_iq || nsymbols < 5 || nsymbols > 2048) {
+        set_error("set_symbols: need 5..2048 symbols");
         return B200AIS_E_INVALID;
     }
     std::lock_guard<std::mutex> lk(h->lock);
@@ -214,8 +239,6 @@ extern "C" int b200ais_corr_est_history(const b200ais_corr_est *h) { return h ? 
 extern "C" unsigned b200ais_corr_est_mark_delay(const b200ais_corr_est *h) { return h ? h->mark_delay : 0; }
 extern "C" float b200ais_corr_est_threshold(const b200ais_corr_est *h) { return h ? h->thresh : 0.0f; }
 
-static size_t mask_stride_for(int n) { return (size_t)((n + 1023) / 1024) * 128; }
-
 extern "C" int b200ais_corr_est_work_dev(b200ais_corr_est *h, int noutput_items, const float *in,
                                          size_t in_stride, uint64_t nitems_written, float *out0,
                                          float *out1, size_t out_stride, b200ais_tag *tags,
@@ -229,21 +252,40 @@ extern "C" int b200ais_corr_est_work_dev(b200ais_corr_est *h, int noutput_items,
     std::lock_guard<std::mutex> lk(h->lock);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int n = noutput_items;
-    const size_t ms = mask_stride_for(n);
+    if (n % h->nsamples) { // set_output_multiple(nsamples): the scheduler never does this
+        set_error("corr_est_work: noutput_items (%d) is not a multiple of the output multiple (%d)", n,
+                  h->nsamples);
+        return B200AIS_E_INVALID;
+    }
+    const size_t ms = corr_mask_stride_bytes(h->L, n);
     int rc = h->mask.reserve(ms * (size_t)h->channels);
     if (rc)
+        return rc;
+    float2 *corr = reinterpret_cast<float2 *>(out1);
+    size_t corr_stride = out_stride;
+    if (!corr) { // the detector still needs the correlator stream
+        corr_stride = round_up((size_t)std::max(n, 1), 2);
+        if ((rc = h->corr.reserve(corr_stride * h->channels * sizeof(float2))))
+            return rc;
+        corr = h->corr.as<float2>();
+    }
+    const float2 *tw = nullptr;
+    if ((rc = get_twiddles(corr_fft_size(h->L), &tw)))
         return rc;
     B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int), s));
     const float2 *in2 = reinterpret_cast<const float2 *>(in);
     const float2 *in_eff = in2 + h->L; // &in[hist_len] (lib/corr_est_cc_impl.cc:188)
-    rc = launch_corr(in_eff, in_stride, h->channels, n, n, h->d_taps_time, h->L, h->thresh,
-                     h->mask.as<uint8_t>(), ms, reinterpret_cast<float2 *>(out1), out_stride, s);
+    rc = launch_corr_fft(in_eff, in_stride, h->channels, n, h->L, tw, h->d_hbr, h->thresh,
+                         h->d_tail[h->tail_cur], h->d_tail[h->tail_cur ^ 1], h->mask.as<uint8_t>(), ms,
+                         corr, corr_stride, s);
     if (rc)
         return rc;
+    if (n > 0)
+        h->tail_cur ^= 1;
     const int isps = (int)(h->sps + 0.5f); // :193
-    rc = launch_detect(in_eff, in_stride, h->channels, n, n > 0 ? n : 1, 1, h->d_taps_time, h->L,
-                       h->thresh, isps, h->mark_delay, h->mask.as<uint8_t>(), ms, nitems_written,
-                       out1 != nullptr, tags, max_tags, ntags, nullptr, h->d_status, s);
+    rc = launch_detect(corr, corr_stride, h->channels, n, n > 0 ? n : 1, 1, isps, h->mark_delay,
+                       h->mask.as<uint8_t>(), ms, nitems_written, out1 != nullptr, tags, max_tags,
+                       ntags, h->d_status, s);
     if (rc)
         return rc;
     if (out0)
@@ -670,7 +712,9 @@ struct b200ais_demod {
     size_t a_stride = 0; // items per row of the corr_est input stream
     size_t mask_stride = 0;
     int nvec_max = 0;
-    float2 *d_taps_time = nullptr;
+    float2 *d_taps_time = nullptr; // transformed taps (bit-reversed order) [fftsize]
+    float2 *d_corr = nullptr;      // correlator stream [channels][corr_stride]
+    size_t corr_stride = 0;
     float2 *d_x = nullptr; // staging for the host variant [channels][max_samples]
     float2 *d_a = nullptr;
     uint8_t *d_mask = nullptr;
@@ -729,7 +773,7 @@ extern "C" int b200ais_demod_create(b200ais_demod **out, const b200ais_demod_con
                                     const float *symbols_iq, int nsymbols, int channels,
                                     int max_samples, int max_tags)
 {
-    if (!out || !cfg || !symbols_iq || nsymbols < 1 || nsymbols > 4096 || channels < 1 ||
+    if (!out || !cfg || !symbols_iq || nsymbols < 5 || nsymbols > 2048 || channels < 1 ||
         max_samples < 1 || max_tags < 4) {
         set_error("demod_create: bad arguments");
         return B200AIS_E_INVALID;
@@ -790,15 +834,19 @@ extern "C" int b200ais_demod_create(b200ais_demod **out, const b200ais_demod_con
     h->mp.osps = cfg->osps;
     h->HP = (int)round_up((size_t)nsymbols + 2, 4);
     h->a_stride = round_up((size_t)h->HP + (size_t)max_samples + 16, 4);
-    h->mask_stride = (size_t)((max_samples + 1023) / 1024) * 128;
+    h->mask_stride = corr_mask_stride_bytes(nsymbols, max_samples);
+    h->corr_stride = round_up((size_t)max_samples, 2);
     h->nvec_max = (cfg->stages & B200AIS_STAGE_FREQSYNC) ? max_samples / cfg->fftlen : 0;
 
     const size_t C = (size_t)channels;
-    std::vector<float2> g((size_t)nsymbols);
-    for (int m = 0; m < nsymbols; m++) { // time order: conj(symbols[m])
-        g[m].x = symbols_iq[2 * m];
-        g[m].y = -symbols_iq[2 * m + 1];
+    // corr_est ctor: taps = reverse(conj(symbols)); fft_filter::set_taps transforms them once
+    std::vector<float> fir(2 * (size_t)nsymbols);
+    for (int i = 0; i < nsymbols; i++) {
+        fir[2 * (size_t)(nsymbols - 1 - i)] = symbols_iq[2 * i];
+        fir[2 * (size_t)(nsymbols - 1 - i) + 1] = -symbols_iq[2 * i + 1];
     }
+    std::vector<float2> g((size_t)corr_fft_size(nsymbols));
+    make_corr_spectrum(fir.data(), nsymbols, g.data());
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) {
         if (e == cudaSuccess)
@@ -806,6 +854,7 @@ extern "C" int b200ais_demod_create(b200ais_demod **out, const b200ais_demod_con
     };
     alloc((void **)&h->d_taps_time, sizeof(float2) * g.size());
     alloc((void **)&h->d_a, sizeof(float2) * h->a_stride * C);
+    alloc((void **)&h->d_corr, sizeof(float2) * h->corr_stride * C);
     alloc((void **)&h->d_mask, h->mask_stride * C);
     alloc((void **)&h->d_raw, sizeof(int) * (size_t)std::max(h->nvec_max, 1) * C);
     alloc((void **)&h->d_fhat, sizeof(float) * (size_t)std::max(h->nvec_max, 1) * C);
@@ -842,7 +891,7 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
 {
     if (!h)
         return B200AIS_OK;
-    void *ptrs[] = { h->d_taps_time, h->d_x, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
+    void *ptrs[] = { h->d_taps_time, h->d_corr, h->d_x, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
                      h->d_tags, h->d_ntags, h->d_nbits, h->d_ncons, h->d_state, h->d_bits,
                      h->d_status };
     for (void *p : ptrs)
@@ -929,22 +978,22 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
             return rc;
     }
     B200_MARK(B200AIS_STAGE_T_MIXAGC);
-    if ((rc = launch_corr(a_rows, h->a_stride, cn, n1, n1, h->d_taps_time, h->L, h->thresh, mask,
-                          h->mask_stride, nullptr, 0, s)))
+    // corr_est covers n2 = whole blocks of its output multiple (the scheduler's view); the filter
+    // starts from a zero tail (freshly constructed block)
+    const int n2 = (n1 / h->nsamples) * h->nsamples;
+    float2 *corr = h->d_corr + (size_t)c0 * h->corr_stride;
+    const float2 *tw = nullptr;
+    if ((rc = get_twiddles(corr_fft_size(h->L), &tw)))
+        return rc;
+    if ((rc = launch_corr_fft(a_rows, h->a_stride, cn, n2, h->L, tw, h->d_taps_time, h->thresh,
+                              nullptr, nullptr, mask, h->mask_stride, corr, h->corr_stride, s)))
         return rc;
     B200_MARK(B200AIS_STAGE_T_CORR);
-    if ((rc = launch_detect(a_rows, h->a_stride, cn, n1, h->chunk, h->nsamples, h->d_taps_time,
-                            h->L, h->thresh, h->isps, h->mark_delay, mask, h->mask_stride, 0, 0,
-                            tags, h->max_tags, ntags, nullptr, d_status, s)))
+    if ((rc = launch_detect(corr, h->corr_stride, cn, n2, h->chunk, h->nsamples, h->isps,
+                            h->mark_delay, mask, h->mask_stride, 0, 0, tags, h->max_tags, ntags,
+                            d_status, s)))
         return rc;
     B200_MARK(B200AIS_STAGE_T_DETECT);
-    // corr_est covers n2 = whole chunks of its output multiple (the scheduler's view)
-    int n2 = 0;
-    while (n1 - n2 >= h->nsamples) {
-        int nn = n1 - n2;
-        nn = nn > h->chunk ? h->chunk : (nn / h->nsamples) * h->nsamples;
-        n2 += nn;
-    }
     if ((rc = launch_msk_reset(h->d_state + c0, cn, h->mp.sps_half, s)))
         return rc;
     float2 *t_sym = h->t_sym.as<float2>() + (size_t)c0 * max_bits;

@@ -1,0 +1,373 @@
+// corr_fft.cu -- corr_est_cc's correlation filter as GNU Radio runs it: kernel::fft_filter_ccc,
+// an FFT overlap-add filter (reference lib/corr_est_cc_impl.cc:77,84,188), followed by
+// volk_32fc_magnitude_squared_32f and the threshold compare (:191,197).
+//
+// Canonical arithmetic (the oracle does the same):
+//   fftsize F = 2 * 2^ceil(log2 L), block ns = F - L + 1 items;
+//   per block: zero-pad to F -> radix-2 DIF forward (natural in, bit-reversed out) ->
+//   multiply by the transformed taps (volk product order) -> radix-2 DIT inverse with
+//   conjugated twiddles (bit-reversed in, natural out, unnormalised; the taps carry 1/F) ->
+//   the first L-1 outputs get the previous block's tail added, the last L-1 become the tail.
+//
+// Mapping: F/16 threads own one block transform, 16 values per thread.  A pass runs up to four
+// consecutive radix-2 stages in registers on the values that differ only in those index bits;
+// between passes the values cross a padded shared-memory buffer.  DIF leaves the spectrum in
+// bit-reversed positions, which is exactly what the DIT inverse wants, so the taps spectrum is
+// stored bit-reversed and nothing is permuted.  A CTA walks NB consecutive blocks of one channel
+// (NB * ns is a multiple of 32, so it owns whole words of the detector bitmask), GROUPS blocks at
+// a time, handing each block's tail to the next through shared memory; it recomputes the block
+// before its range only for that tail.
+#include "device_math.cuh"
+#include "internal.h"
+
+namespace b200ais {
+
+namespace {
+
+__device__ __forceinline__ int xphys(int e) { return e + (e >> 4); }
+
+template <int LOGF> struct Plan {
+    static constexpr int F = 1 << LOGF;
+    static constexpr int NT = F / 16;                       // threads per transform
+    static constexpr int THREADS = NT > 128 ? NT : 128;     // CTA size
+    static constexpr int GROUPS = THREADS / NT;             // transforms in flight per CTA
+    static constexpr int NPASS = (LOGF + 3) / 4;
+    static constexpr int REM = LOGF % 4;                    // width of the lowest pass (0 = full)
+};
+
+// element index of slot (g, q) of thread t for a pass over index bits [S0, S0+R)
+template <int S0, int R> __device__ __forceinline__ int elem(int t, int g, int q)
+{
+    const int u = t * (16 >> R) + g;
+    const int lo = u & ((1 << S0) - 1), hi = u >> S0;
+    return (hi << (S0 + R)) | (q << S0) | lo;
+}
+
+// one pass: R radix-2 stages on index bits [S0, S0+R), forward DIF or inverse DIT
+template <int LOGF, int S0, int R, bool INV>
+__device__ __forceinline__ void run_pass(float2 (&v)[16], int t, const float2 *__restrict__ tw)
+{
+    constexpr int G = 16 >> R, Q = 1 << R, F = 1 << LOGF;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int lo = (t * G + g) & ((1 << S0) - 1);
+#pragma unroll
+        for (int st = 0; st < R; st++) {
+            const int bq = INV ? st : (R - 1 - st);  // bit of q this stage pairs on
+            const int beta = S0 + bq;                // index bit
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                if (q & (1 << bq))
+                    continue;
+                const int q1 = q | (1 << bq);
+                const int jq = (q & ((1 << bq) - 1)) << S0;
+                float2 &a = v[g * Q + q], &b = v[g * Q + q1];
+                const float2 a0 = a, b0 = b;
+                if (S0 == 0 && (jq << (LOGF - beta - 1)) == 0) { // W = 1
+                    a = make_float2(a0.x + b0.x, a0.y + b0.y);
+                    b = make_float2(a0.x - b0.x, a0.y - b0.y);
+                } else if (S0 == 0 && (jq << (LOGF - beta - 1)) == F / 4) { // W = -i (conj: +i)
+                    if (INV) { // t = i*b = (-b.y, b.x)
+                        a = make_float2(a0.x - b0.y, a0.y + b0.x);
+                        b = make_float2(a0.x + b0.y, a0.y - b0.x);
+                    } else { // (a-b) * (-i) = (d.y, -d.x)
+                        const float dx = a0.x - b0.x, dy = a0.y - b0.y;
+                        a = make_float2(a0.x + b0.x, a0.y + b0.y);
+                        b = make_float2(dy, -dx);
+                    }
+                } else {
+                    float2 w = tw[(jq | lo) << (LOGF - beta - 1)];
+                    if (INV) {
+                        w.y = -w.y;
+                        const float2 tt = cmul_fma(w, b0);
+                        a = make_float2(a0.x + tt.x, a0.y + tt.y);
+                        b = make_float2(a0.x - tt.x, a0.y - tt.y);
+                    } else {
+                        a = make_float2(a0.x + b0.x, a0.y + b0.y);
+                        b = cmul_fma(w, make_float2(a0.x - b0.x, a0.y - b0.y));
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int S0, int R>
+__device__ __forceinline__ void to_smem(const float2 (&v)[16], int t, float2 *xb)
+{
+#pragma unroll
+    for (int s = 0; s < 16; s++)
+        xb[xphys(elem<S0, R>(t, s >> R, s & ((1 << R) - 1)))] = v[s];
+}
+template <int S0, int R>
+__device__ __forceinline__ void from_smem(float2 (&v)[16], int t, const float2 *xb)
+{
+#pragma unroll
+    for (int s = 0; s < 16; s++)
+        v[s] = xb[xphys(elem<S0, R>(t, s >> R, s & ((1 << R) - 1)))];
+}
+
+// forward transform, multiply by the taps spectrum, inverse transform; v enters and leaves in
+// the top-pass mapping (element t + NT*q in slot q)
+template <int LOGF>
+__device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float2 *__restrict__ tw,
+                                             const float2 *__restrict__ hbr, float2 *xb)
+{
+    constexpr int NP = Plan<LOGF>::NPASS, REM = Plan<LOGF>::REM;
+    constexpr int TOP = LOGF - 4;
+    // ---- forward, top bits first ----
+    run_pass<LOGF, TOP, 4, false>(v, t, tw);
+    if constexpr (NP >= 2) {
+        to_smem<TOP, 4>(v, t, xb);
+        __syncthreads();
+        constexpr int S1 = (NP == 2) ? 0 : TOP - 4;
+        constexpr int R1 = (NP == 2 && REM) ? REM : 4;
+        from_smem<S1, R1>(v, t, xb);
+        __syncthreads();
+        run_pass<LOGF, S1, R1, false>(v, t, tw);
+        if constexpr (NP >= 3) {
+            to_smem<S1, R1>(v, t, xb);
+            __syncthreads();
+            constexpr int R2 = REM ? REM : 4;
+            from_smem<0, R2>(v, t, xb);
+            __syncthreads();
+            run_pass<LOGF, 0, R2, false>(v, t, tw);
+        }
+    }
+    // ---- pointwise product with the (bit-reversed) transformed taps: volk multiply(X, H) ----
+    {
+        constexpr int SL = 0;
+        constexpr int RL = (NP == 1) ? 4 : (REM ? REM : 4);
+#pragma unroll
+        for (int s = 0; s < 16; s++)
+            v[s] = cmul_fma(v[s], hbr[elem<SL, RL>(t, s >> RL, s & ((1 << RL) - 1))]);
+        // ---- inverse, low bits first ----
+        run_pass<LOGF, SL, RL, true>(v, t, tw);
+    }
+    if constexpr (NP >= 3) {
+        constexpr int R2 = REM ? REM : 4;
+        constexpr int S1 = TOP - 4;
+        to_smem<0, R2>(v, t, xb);
+        __syncthreads();
+        from_smem<S1, 4>(v, t, xb);
+        __syncthreads();
+        run_pass<LOGF, S1, 4, true>(v, t, tw);
+        to_smem<S1, 4>(v, t, xb);
+        __syncthreads();
+        from_smem<TOP, 4>(v, t, xb);
+        __syncthreads();
+        run_pass<LOGF, TOP, 4, true>(v, t, tw);
+    } else if constexpr (NP == 2) {
+        constexpr int R1 = REM ? REM : 4;
+        to_smem<0, R1>(v, t, xb);
+        __syncthreads();
+        from_smem<TOP, 4>(v, t, xb);
+        __syncthreads();
+        run_pass<LOGF, TOP, 4, true>(v, t, tw);
+    }
+}
+
+template <int LOGF>
+__global__ void __launch_bounds__(Plan<LOGF>::THREADS)
+k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, int nb_per_cta,
+           const float2 *__restrict__ tw, const float2 *__restrict__ hbr, float thresh,
+           const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
+           uint32_t *__restrict__ mask, size_t mask_stride_words, float2 *__restrict__ corr_out,
+           size_t corr_stride)
+{
+    using P = Plan<LOGF>;
+    constexpr int F = P::F, NT = P::NT, GROUPS = P::GROUPS;
+    extern __shared__ float4 smem_raw[];
+    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);     // [F/2]
+    float2 *s_h = s_tw + F / 2;                              // [F]
+    float2 *s_x = s_h + F;                                   // [GROUPS][F + F/16]
+    float2 *s_tail = s_x + GROUPS * (F + F / 16);            // [2][GROUPS][L-1]
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_tail + 2 * GROUPS * (L > 1 ? L - 1 : 1));
+
+    const int ns = F - L + 1, tl = L - 1;
+    const int c = blockIdx.y;
+    const int b0 = blockIdx.x * nb_per_cta;
+    const int g = threadIdx.x / NT, t = threadIdx.x % NT;
+    const int nwords = (nb_per_cta * ns) >> 5;
+    for (int i = threadIdx.x; i < F / 2; i += blockDim.x)
+        s_tw[i] = tw[i];
+    for (int i = threadIdx.x; i < F; i += blockDim.x)
+        s_h[i] = hbr[i];
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x)
+        s_mask[i] = 0u;
+    __syncthreads();
+
+    const float2 *xc = in + (size_t)c * in_stride;
+    float2 *xb = s_x + g * (F + F / 16);
+    const int first = b0 > 0 ? b0 - 1 : 0;                   // lead block: only its tail is used
+    const int last = min(b0 + nb_per_cta, nblocks);          // exclusive
+    const int rounds = (last - first + GROUPS - 1) / GROUPS;
+    for (int r = 0; r < rounds; r++) {
+        const int b = first + r * GROUPS + g;
+        const bool valid = b < last;
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int e = t + NT * q;
+            v[q] = (valid && e < ns) ? xc[(size_t)b * ns + e] : make_float2(0.0f, 0.0f);
+        }
+        block_filter<LOGF>(v, t, s_tw, s_h, xb);
+        // stash this block's tail (outputs ns .. F-1) for the next block
+        float2 *my_tail = s_tail + ((r & 1) * GROUPS + g) * tl;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int e = t + NT * q;
+            if (valid && e >= ns)
+                my_tail[e - ns] = v[q];
+        }
+        if (valid && b == nblocks - 1 && tail_out) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int e = t + NT * q;
+                if (e >= ns)
+                    tail_out[(size_t)c * tl + (e - ns)] = v[q];
+            }
+        }
+        __syncthreads();
+        if (valid && b >= b0) {
+            const float2 *prev = nullptr; // tail of block b-1
+            if (g > 0)
+                prev = s_tail + ((r & 1) * GROUPS + g - 1) * tl;
+            else if (r > 0)
+                prev = s_tail + (((r - 1) & 1) * GROUPS + GROUPS - 1) * tl;
+            else if (b == 0 && tail_in)
+                prev = tail_in + (size_t)c * tl; // state carried from the previous work() call
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int e = t + NT * q;
+                if (e < ns) {
+                    float2 y = v[q];
+                    if (e < tl && prev) {
+                        const float2 pt = prev[e];
+                        y.x += pt.x;
+                        y.y += pt.y;
+                    }
+                    const size_t idx = (size_t)b * ns + e;
+                    if (corr_out)
+                        corr_out[(size_t)c * corr_stride + idx] = y;
+                    // volk_32fc_magnitude_squared_32f, then `mag <= thresh` skips (:191,197)
+                    const float mag = y.x * y.x + y.y * y.y;
+                    if (!(mag <= thresh)) {
+                        const int bit = (b - b0) * ns + e;
+                        atomicOr(&s_mask[bit >> 5], 1u << (bit & 31));
+                    }
+                }
+            }
+        }
+        // the tail slots read here are rewritten next round (other parity: two rounds later);
+        // single-pass transforms have no barrier inside block_filter, so order it explicitly
+        if (Plan<LOGF>::NPASS == 1)
+            __syncthreads();
+    }
+    __syncthreads();
+    uint32_t *mrow = mask + (size_t)c * mask_stride_words + (((size_t)b0 * ns) >> 5);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x)
+        mrow[i] = s_mask[i];
+}
+
+template <int LOGF>
+int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, int L, int nb,
+               const float2 *tw, const float2 *hbr, float thresh, const float2 *tail_in,
+               float2 *tail_out, uint32_t *mask, size_t msw, float2 *corr_out, size_t corr_stride,
+               cudaStream_t s)
+{
+    using P = Plan<LOGF>;
+    const int ns = P::F - L + 1;
+    size_t smem = sizeof(float2) * (size_t)(P::F / 2 + P::F + P::GROUPS * (P::F + P::F / 16) +
+                                            2 * P::GROUPS * (L > 1 ? L - 1 : 1)) +
+                  sizeof(uint32_t) * (size_t)((nb * ns) >> 5) + 16;
+    if (smem > 200 * 1024) {
+        set_error("corr_est: %d taps need %zu bytes of shared memory", L, smem);
+        return B200AIS_E_INVALID;
+    }
+    B200_CU(cudaFuncSetAttribute(k_corr_fft<LOGF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    dim3 grid((nblocks + nb - 1) / nb, channels);
+    k_corr_fft<LOGF><<<grid, P::THREADS, smem, s>>>(in, in_stride, nblocks, L, nb, tw, hbr, thresh,
+                                                    tail_in, tail_out, mask, msw, corr_out,
+                                                    corr_stride);
+    B200_LAUNCH_CHECK("k_corr_fft");
+    return B200AIS_OK;
+}
+
+} // namespace
+
+int corr_fft_size(int L)
+{
+    int p = 1;
+    while (p < L)
+        p <<= 1;
+    return 2 * p;
+}
+
+// blocks per CTA: a multiple of 32/gcd(ns, 32) so the CTA's outputs cover whole bitmask words
+int corr_blocks_per_cta(int L)
+{
+    const int F = corr_fft_size(L), ns = F - L + 1;
+    int g = 32, a = ns;
+    while (a) {
+        int tmp = g % a;
+        g = a;
+        a = tmp;
+    }
+    int nb0 = 32 / g;
+    int nb = nb0;
+    while (nb < 32 && nb * ns < 8192)
+        nb += nb0;
+    return nb;
+}
+
+size_t corr_mask_stride_bytes(int L, int n)
+{
+    const int F = corr_fft_size(L), ns = F - L + 1, nb = corr_blocks_per_cta(L);
+    const int nblocks = n / ns;
+    const size_t ctas = (size_t)(nblocks + nb - 1) / nb;
+    size_t words = (ctas ? ctas : 1) * (((size_t)nb * ns) >> 5);
+    return words * 4;
+}
+
+int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int L,
+                    const float2 *tw, const float2 *hbr, float thresh, const float2 *tail_in,
+                    float2 *tail_out, uint8_t *mask, size_t mask_stride, float2 *corr_out,
+                    size_t corr_stride, cudaStream_t s)
+{
+    if (n <= 0 || channels <= 0)
+        return B200AIS_OK;
+    const int F = corr_fft_size(L), ns = F - L + 1;
+    if (n % ns) {
+        set_error("corr_est: noutput_items (%d) must be a multiple of the output multiple (%d)", n, ns);
+        return B200AIS_E_INVALID;
+    }
+    int lg = 0;
+    while ((1 << lg) < F)
+        lg++;
+    const int nblocks = n / ns, nb = corr_blocks_per_cta(L);
+    uint32_t *m32 = reinterpret_cast<uint32_t *>(mask);
+    const size_t msw = mask_stride / 4;
+#define B200_CASE(LG)                                                                             \
+    case LG:                                                                                      \
+        return launch_one<LG>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh, tail_in,  \
+                              tail_out, m32, msw, corr_out, corr_stride, s);
+    switch (lg) {
+        B200_CASE(4)
+        B200_CASE(5)
+        B200_CASE(6)
+        B200_CASE(7)
+        B200_CASE(8)
+        B200_CASE(9)
+        B200_CASE(10)
+        B200_CASE(11)
+        B200_CASE(12)
+    default:
+        set_error("corr_est supports 5..2048 taps (fft size 16..4096), got %d taps", L);
+        return B200AIS_E_INVALID;
+    }
+#undef B200_CASE
+}
+
+} // namespace b200ais

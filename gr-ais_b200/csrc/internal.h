@@ -81,18 +81,24 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
                    const float *fhat, int vstride, const float *ckpt, int seg, float sens, int stages,
                    int agc_nsamples, float agc_reference, float2 *out, size_t out_stride,
                    cudaStream_t s);
-// A3: sliding correlation, |.|^2 > thresh bitmask (+ optional correlator stream).
-// in rows: in[c*in_stride + t], t in [-(L), n) readable (zeros for history).
-// taps_time: [L] in time order g[m] (pairs with sample t-L+1+m).
-int launch_corr(const float2 *in, size_t in_stride, int channels, int n, int n_valid,
-                const float2 *taps_time, int L, float thresh, uint8_t *mask, size_t mask_stride,
-                float2 *corr_out, size_t corr_stride, cudaStream_t s);
-// A4: the serial detector, one warp per channel.
-int launch_detect(const float2 *in, size_t in_stride, int channels, int n_total, int chunk,
-                  int nsamples_mult, const float2 *taps_time, int L, float thresh, int isps,
-                  unsigned mark_delay, const uint8_t *mask, size_t mask_stride, uint64_t base_offset,
-                  int two_ports, b200ais_tag *tags, int max_tags, int *ntags, int *n2_out,
-                  int *status, cudaStream_t s);
+// A3: the correlation filter (GNU Radio's fft_filter_ccc: FFT overlap-add), |.|^2 > thresh
+// bitmask and the correlator stream.  in rows: in[c*in_stride + t], t in [0, n), n a multiple
+// of the block size fftsize - L + 1.  tw: fftsize/2 twiddles, hbr: fftsize transformed taps in
+// bit-reversed order (make_corr_spectrum).  tail_in/tail_out: [channels][L-1] filter state
+// (nullptr = zero / discard); they must not alias.
+int corr_fft_size(int L);
+int corr_blocks_per_cta(int L);
+size_t corr_mask_stride_bytes(int L, int n);
+int make_corr_spectrum(const float *taps_iq, int L, float2 *hbr_host /* [fftsize] */);
+int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int L,
+                    const float2 *tw, const float2 *hbr, float thresh, const float2 *tail_in,
+                    float2 *tail_out, uint8_t *mask, size_t mask_stride, float2 *corr_out,
+                    size_t corr_stride, cudaStream_t s);
+// A4: the serial detector, one warp per channel, on the correlator stream.
+int launch_detect(const float2 *corr, size_t corr_stride, int channels, int n_total, int chunk,
+                  int nsamples_mult, int isps, unsigned mark_delay, const uint8_t *mask,
+                  size_t mask_stride, uint64_t base_offset, int two_ports, b200ais_tag *tags,
+                  int max_tags, int *ntags, int *status, cudaStream_t s);
 // A7: the timing-loop recurrence, one lane per channel (symbols out).
 int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,

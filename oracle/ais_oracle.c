@@ -358,20 +358,124 @@ void ao_agc_work(const float *in, int n, int nsamples, float reference, float *o
 
 /* ----------------------------------------------------- A1-A4: corr_est_cc */
 
-static int fft_filter_nsamples(int ntaps)
+static int fft_filter_fftsize(int ntaps)
 {
     /* kernel::fft_filter_ccc::compute_sizes [G]: fftsize = 2 * 2^ceil(log2 ntaps) */
     int p = 1;
     while (p < ntaps)
         p <<= 1;
-    int fftsize = 2 * p;
-    return fftsize - ntaps + 1;
+    return 2 * p;
+}
+
+static int fft_filter_nsamples(int ntaps) { return fft_filter_fftsize(ntaps) - ntaps + 1; }
+
+static void make_twiddles(int n, float *w)
+{
+    for (int k = 0; k < n / 2; k++) {
+        double ang = 2.0 * M_PI * (double)k / (double)n;
+        w[2 * k] = (float)cos(ang);
+        w[2 * k + 1] = (float)(-sin(ang));
+    }
+    w[0] = 1.0f;
+    w[1] = 0.0f;
+    if (n >= 4) {
+        w[2 * (n / 4)] = 0.0f;
+        w[2 * (n / 4) + 1] = -1.0f;
+    }
+}
+
+/* Forward DFT, radix-2 decimation in frequency: natural-order input, bit-reversed output.
+ * Stage m: a' = a + b, b' = W_m^j * (a - b) (cmul order), m = n, n/2, ..., 2. */
+static void fft_dif(float *x, int n, const float *w)
+{
+    for (int m = n; m >= 2; m >>= 1) {
+        int half = m / 2, step = n / m;
+        for (int k = 0; k < n; k += m)
+            for (int j = 0; j < half; j++) {
+                float *a = &x[2 * (k + j)], *b = &x[2 * (k + j + half)];
+                float ar = a[0], ai = a[1], br = b[0], bi = b[1];
+                a[0] = ar + br;
+                a[1] = ai + bi;
+                cmul(w[2 * (j * step)], w[2 * (j * step) + 1], ar - br, ai - bi, &b[0], &b[1]);
+            }
+    }
+}
+
+/* Inverse DFT (unnormalised), radix-2 decimation in time with conjugated twiddles:
+ * bit-reversed input, natural-order output.  Stage m: t = conj(W_m^j) * b, a' = a + t, b' = a - t. */
+static void ifft_dit(float *x, int n, const float *w)
+{
+    for (int m = 2; m <= n; m <<= 1) {
+        int half = m / 2, step = n / m;
+        for (int k = 0; k < n; k += m)
+            for (int j = 0; j < half; j++) {
+                float *a = &x[2 * (k + j)], *b = &x[2 * (k + j + half)];
+                float tr, ti;
+                cmul(w[2 * (j * step)], -w[2 * (j * step) + 1], b[0], b[1], &tr, &ti);
+                float ar = a[0], ai = a[1];
+                a[0] = ar + tr;
+                a[1] = ai + ti;
+                b[0] = ar - tr;
+                b[1] = ai - ti;
+            }
+    }
+}
+
+int ao_fft_dif_inplace(float *x, int n)
+{
+    if (n < 2 || (n & (n - 1)))
+        return -1;
+    float *w = (float *)malloc(sizeof(float) * n);
+    make_twiddles(n, w);
+    fft_dif(x, n, w);
+    free(w);
+    return 0;
+}
+
+int ao_ifft_dit_inplace(float *x, int n)
+{
+    if (n < 2 || (n & (n - 1)))
+        return -1;
+    float *w = (float *)malloc(sizeof(float) * n);
+    make_twiddles(n, w);
+    ifft_dit(x, n, w);
+    free(w);
+    return 0;
+}
+
+/* fft_filter_ccc::set_taps [G]: taps scaled by 1/fftsize, zero padded, transformed once.
+ * The tail keeps its contents and is resized to ntaps-1 (std::vector::resize). */
+static void corr_set_taps(ao_corr_est *c, int old_L)
+{
+    int F = fft_filter_fftsize(c->L);
+    c->fftsize = F;
+    c->nsamples = F - c->L + 1;
+    free(c->H);
+    free(c->tw);
+    c->H = (float *)calloc((size_t)F * 2, sizeof(float));
+    c->tw = (float *)malloc(sizeof(float) * F);
+    make_twiddles(F, c->tw);
+    float scale = 1.0f / (float)F;
+    for (int k = 0; k < c->L; k++) {
+        c->H[2 * k] = c->taps[2 * k] * scale;
+        c->H[2 * k + 1] = c->taps[2 * k + 1] * scale;
+    }
+    fft_dif(c->H, F, c->tw);
+    float *nt = (float *)calloc((size_t)(c->L > 1 ? c->L - 1 : 1) * 2, sizeof(float));
+    if (c->tail) {
+        int keep = (old_L < c->L ? old_L : c->L) - 1;
+        if (keep > 0)
+            memcpy(nt, c->tail, sizeof(float) * 2 * (size_t)keep);
+        free(c->tail);
+    }
+    c->tail = nt;
 }
 
 /* lib/corr_est_cc_impl.cc:48-117 */
 int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, unsigned mark_delay,
                      float threshold)
 {
+    memset(c, 0, sizeof(*c));
     c->taps = (float *)malloc(sizeof(float) * 2 * (size_t)L);
     if (!c->taps)
         return -1;
@@ -388,7 +492,7 @@ int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, uns
         corr += re * re + im * im;
     }
     c->thresh = threshold * corr * corr;
-    c->nsamples = fft_filter_nsamples(L);
+    corr_set_taps(c, L);
     return 0;
 }
 
@@ -396,18 +500,43 @@ int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, uns
  * reverse) and d_thresh is NOT recomputed. */
 void ao_corr_est_set_symbols(ao_corr_est *c, const float *symbols, int L)
 {
+    int old_L = c->L;
     free(c->taps);
     c->taps = (float *)malloc(sizeof(float) * 2 * (size_t)L);
     memcpy(c->taps, symbols, sizeof(float) * 2 * (size_t)L);
     c->L = L;
-    c->nsamples = fft_filter_nsamples(L);
+    corr_set_taps(c, old_L);
     c->mark_delay = c->mark_delay >= (unsigned)L ? (unsigned)L - 1 : c->mark_delay;
 }
 
 void ao_corr_est_free(ao_corr_est *c)
 {
     free(c->taps);
-    c->taps = 0;
+    free(c->H);
+    free(c->tail);
+    free(c->tw);
+    c->taps = c->H = c->tail = c->tw = 0;
+}
+
+/* float64 direct-form truth of the same filter on a fresh block: like fft_filter_ccc, it is
+ * fed &in[hist_len] only, so the items before it (the block's tagging history) do not enter
+ * the correlation of the first call; the filter's own tail, zero at construction, does. */
+void ao_corr_direct_f64(const ao_corr_est *c, int n, const float *in, double *corr_out)
+{
+    const float *x = in + 2 * (size_t)c->L;
+    for (int i = 0; i < n; i++) {
+        double re = 0, im = 0;
+        for (int k = 0; k < c->L; k++) {
+            if (i - k < 0)
+                break;
+            double tr = c->taps[2 * k], ti = c->taps[2 * k + 1];
+            double xr = x[2 * (i - k)], xi = x[2 * (i - k) + 1];
+            re += tr * xr - ti * xi;
+            im += tr * xi + ti * xr;
+        }
+        corr_out[2 * i] = re;
+        corr_out[2 * i + 1] = im;
+    }
 }
 
 static void push_tag(ao_tag *tags, int max_tags, int *ntags, uint64_t off, int key, int port,
@@ -422,33 +551,42 @@ static void push_tag(ao_tag *tags, int max_tags, int *ntags, uint64_t off, int k
     (*ntags)++;
 }
 
-/* lib/corr_est_cc_impl.cc:164-279.  The FFT overlap-add filter (:188) is a causal
- * FIR y[i] = sum_k taps[k] * x[i-k]; canonical evaluation: k descending, i.e. in
- * template order m = L-1-k ascending, one fmaf chain per component:
- *   re = fma(tr, xr, re); re = fma(-ti, xi, re); im = fma(tr, xi, im); im = fma(ti, xr, im) */
-int ao_corr_est_work(const ao_corr_est *c, int n, const float *in, uint64_t nitems_written,
+/* lib/corr_est_cc_impl.cc:164-279.  The correlation filter (:188) is GNU Radio's
+ * kernel::fft_filter_ccc [G]: blocks of nsamples items, zero padded to fftsize, forward FFT,
+ * multiplied by the transformed taps (volk multiply order), inverse FFT, the first ntaps-1
+ * outputs get the previous block's tail added, the last ntaps-1 become the new tail.
+ * Canonical transforms: the radix-2 DIF / DIT pair above. */
+int ao_corr_est_work(ao_corr_est *c, int n, const float *in, uint64_t nitems_written,
                      float *out0, float *corr, float *mag, int two_ports, ao_tag *tags,
                      int max_tags, int *ntags)
 {
-    int L = c->L;
+    int L = c->L, F = c->fftsize, ns = c->nsamples;
+    *ntags = 0;
+    if (n % ns)
+        return -1; /* set_output_multiple(nsamples) */
     float *corr_buf = corr ? corr : (float *)malloc(sizeof(float) * 2 * (size_t)(n > 0 ? n : 1));
     float *mag_buf = mag ? mag : (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
-    *ntags = 0;
     if (out0)
         memcpy(out0, in, sizeof(float) * 2 * (size_t)n); /* :184 */
     const float *x = in + 2 * (size_t)L;                 /* &in[hist_len] (:188) */
-    for (int i = 0; i < n; i++) {
-        float re = 0.0f, im = 0.0f;
-        for (int k = L - 1; k >= 0; k--) {
-            float tr = c->taps[2 * k], ti = c->taps[2 * k + 1];
-            float xr = x[2 * (i - k)], xi = x[2 * (i - k) + 1];
-            re = fmaf(tr, xr, re);
-            re = fmaf(-ti, xi, re);
-            im = fmaf(tr, xi, im);
-            im = fmaf(ti, xr, im);
+    float *buf = (float *)malloc(sizeof(float) * 2 * (size_t)F);
+    for (int i0 = 0; i0 < n; i0 += ns) {
+        memcpy(buf, x + 2 * (size_t)i0, sizeof(float) * 2 * (size_t)ns);
+        memset(buf + 2 * (size_t)ns, 0, sizeof(float) * 2 * (size_t)(F - ns));
+        fft_dif(buf, F, c->tw);
+        for (int p = 0; p < F; p++)
+            cmul(buf[2 * p], buf[2 * p + 1], c->H[2 * p], c->H[2 * p + 1], &buf[2 * p], &buf[2 * p + 1]);
+        ifft_dit(buf, F, c->tw);
+        for (int j = 0; j < L - 1; j++) {
+            buf[2 * j] += c->tail[2 * j];
+            buf[2 * j + 1] += c->tail[2 * j + 1];
         }
-        corr_buf[2 * i] = re;
-        corr_buf[2 * i + 1] = im;
+        memcpy(corr_buf + 2 * (size_t)i0, buf, sizeof(float) * 2 * (size_t)ns);
+        memcpy(c->tail, buf + 2 * (size_t)ns, sizeof(float) * 2 * (size_t)(L - 1));
+    }
+    free(buf);
+    for (int i = 0; i < n; i++) {
+        float re = corr_buf[2 * i], im = corr_buf[2 * i + 1];
         mag_buf[i] = re * re + im * im; /* volk_32fc_magnitude_squared_32f (:191) */
     }
     int isps = (int)(c->sps + 0.5f);

@@ -94,15 +94,26 @@ typedef struct ao_corr_est {
     unsigned mark_delay;
     float thresh;
     int nsamples; /* fft_filter block size = output multiple */
+    /* kernel::fft_filter_ccc state [G]: fftsize, transformed taps (bit-reversed order), tail */
+    int fftsize;
+    float *H;    /* [fftsize] complex */
+    float *tail; /* [L-1] complex, zero at construction */
+    float *tw;   /* [fftsize/2] complex twiddles */
 } ao_corr_est;
 int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, unsigned mark_delay,
                      float threshold);
 void ao_corr_est_set_symbols(ao_corr_est *c, const float *symbols, int L);
 void ao_corr_est_free(ao_corr_est *c);
+/* the correlation of the whole call by a float64 direct sum (test truth, not the canonical path) */
+void ao_corr_direct_f64(const ao_corr_est *c, int n, const float *in, double *corr_out);
+/* forward DIF (natural in, bit-reversed out) / inverse DIT (bit-reversed in, natural out,
+ * unnormalised) of the correlator, in place on n complex values */
+int ao_fft_dif_inplace(float *x, int n);
+int ao_ifft_dit_inplace(float *x, int n);
 /* One work() call.  in holds n+L items (history first).  corr/mag may be NULL.
  * two_ports != 0 also emits the port-1 debug tags.  Returns n; *ntags = tags written
  * (tags beyond max_tags are counted but dropped). */
-int ao_corr_est_work(const ao_corr_est *c, int n, const float *in, uint64_t nitems_written,
+int ao_corr_est_work(ao_corr_est *c, int n, const float *in, uint64_t nitems_written,
                      float *out0, float *corr, float *mag, int two_ports, ao_tag *tags,
                      int max_tags, int *ntags);
 

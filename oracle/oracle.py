@@ -26,7 +26,9 @@ class Tag(C.Structure):
 
 class CorrEst(C.Structure):
     _fields_ = [("taps", C.POINTER(C.c_float)), ("L", C.c_int), ("sps", C.c_float),
-                ("mark_delay", C.c_uint), ("thresh", C.c_float), ("nsamples", C.c_int)]
+                ("mark_delay", C.c_uint), ("thresh", C.c_float), ("nsamples", C.c_int),
+                ("fftsize", C.c_int), ("H", C.POINTER(C.c_float)), ("tail", C.POINTER(C.c_float)),
+                ("tw", C.POINTER(C.c_float))]
 
 
 class Msk(C.Structure):
@@ -188,6 +190,22 @@ def fft_forward(x):
     return out
 
 
+def fft_dif(x):
+    """correlator forward transform: natural-order in, bit-reversed out"""
+    x = _c64(x).copy()
+    if lib().ao_fft_dif_inplace(_fp(x), len(x)):
+        raise ValueError("fft length must be a power of two >= 2")
+    return x
+
+
+def ifft_dit(x):
+    """correlator inverse transform (unnormalised): bit-reversed in, natural-order out"""
+    x = _c64(x).copy()
+    if lib().ao_ifft_dit_inplace(_fp(x), len(x)):
+        raise ValueError("fft length must be a power of two >= 2")
+    return x
+
+
 def fft_shift(x):
     x = _c64(x)
     out = np.empty_like(x)
@@ -277,12 +295,29 @@ class CorrEstBlock:
         mag = np.empty(n, dtype=np.float32)
         tags = np.zeros(max_tags, dtype=TAG_DTYPE)
         nt = C.c_int(0)
-        lib().ao_corr_est_work(C.byref(self._c), int(n), _fp(inbuf), C.c_uint64(nitems_written),
-                               _fp(out0), _fp(corr), _fp(mag), int(bool(two_ports)), _fp(tags),
-                               int(max_tags), C.byref(nt))
+        rc = lib().ao_corr_est_work(C.byref(self._c), int(n), _fp(inbuf), C.c_uint64(nitems_written),
+                                    _fp(out0), _fp(corr), _fp(mag), int(bool(two_ports)), _fp(tags),
+                                    int(max_tags), C.byref(nt))
+        if rc < 0:
+            raise ValueError("noutput_items must be a multiple of the output multiple (%d)" % self.nsamples)
         if nt.value > max_tags:
             raise RuntimeError("tag buffer overflow")
         return out0, corr, mag, tags[:nt.value].copy()
+
+    @property
+    def fftsize(self):
+        return self._c.fftsize
+
+    def tail(self):
+        n = max(self._c.L - 1, 0)
+        return np.ctypeslib.as_array(self._c.tail, shape=(2 * max(n, 1),)).copy().view(np.complex64)[:n]
+
+    def direct_f64(self, n, inbuf):
+        """float64 direct-form correlation of the same call (truth for tests; ignores the tail)"""
+        inbuf = _c64(inbuf)
+        out = np.zeros(n, dtype=np.complex128)
+        lib().ao_corr_direct_f64(C.byref(self._c), int(n), _fp(inbuf), _fp(out))
+        return out
 
 
 # ------------------------------------------------------------------ msk

@@ -167,9 +167,13 @@ def test_corr_est_detects_template(oracle, templates):
     b = oracle.CorrEstBlock(t, 5.0, 1, 0.9)
     out0, corr, mag, tags = b.work(n, stream, nitems_written=1000)
     assert np.array_equal(out0, stream[:n])                      # :184 delay by the history
-    truth = np.array([np.vdot(t, stream[i + 1:i + 1 + L]) for i in range(n)])   # float64-ish
+    # the filter is fed &in[L] and starts from a zero tail: the tagging history does not enter
+    # the first call's correlation (fft_filter_ccc keeps its own state)
+    fed = np.concatenate([np.zeros(L, np.complex128), stream[L:].astype(np.complex128)])
+    truth = np.array([np.vdot(t.astype(np.complex128), fed[i + 1:i + 1 + L]) for i in range(n)])
     assert np.max(np.abs(corr - truth)) < 1e-5 * L
-    assert np.allclose(mag, np.abs(truth) ** 2, rtol=1e-4, atol=1e-3)
+    assert np.max(np.abs(corr - oracle.CorrEstBlock(t, 5.0, 1, 0.9).direct_f64(n, stream))) < 1e-5 * L
+    assert np.allclose(mag, np.abs(truth) ** 2, rtol=1e-4, atol=1e-2)
     i_peak = p - 1   # out0[i+1] is the first template sample
     cs = tags[tags["key"] == TAG["corr_start"]]
     assert 1000 + i_peak in cs["offset"]
@@ -192,16 +196,48 @@ def test_corr_est_chunk_edges(oracle, templates):
     t = templates[120]
     L = len(t)
     n = 274
-    for pos in (L + 0, L + n - 1):     # peak lands on item 0 / item n-1 of the chunk
-        stream = np.zeros(n + L, np.complex64)
-        lo = pos - L + 1
-        seg = t[max(0, -lo):][:n + L - max(lo, 0)]
-        stream[max(lo, 0):max(lo, 0) + len(seg)] = seg
+    for item in (0, n - 1):     # the peak lands on item 0 / item n-1 of the second work() chunk
+        stream = np.zeros(2 * n + L, np.complex64)
+        end = L + n + item      # stream index of the template's last sample <=> the peak item
+        stream[end - L + 1:end + 1] = t
         b = oracle.CorrEstBlock(t, 5.0, 1, 0.5)
-        _, _, mag, tags = b.work(n, stream)
-        i = pos - L
-        te = tags[(tags["key"] == TAG["time_est"]) & (tags["offset"] == i + 1)]
+        b.work(n, stream[:n + L])
+        _, _, mag, tags = b.work(n, stream[n:], nitems_written=n)
+        assert int(np.argmax(mag)) == item
+        te = tags[(tags["key"] == TAG["time_est"]) & (tags["offset"] == n + item + 1)]
         assert len(te) == 1 and te["value"][0] == 0.0
+        # the same peak in the middle of a chunk gets a non-zero centre of mass
+        c = oracle.CorrEstBlock(t, 5.0, 1, 0.5)
+        _, _, _, tags2 = c.work(3 * n, np.concatenate([stream, np.zeros(n, np.complex64)]))
+        te2 = tags2[(tags2["key"] == TAG["time_est"]) & (tags2["offset"] == n + item + 1)]
+        assert len(te2) == 1 and te2["value"][0] != 0.0
+
+
+def test_corr_est_is_gnuradio_fft_filter(oracle, templates):
+    """kernel::fft_filter_ccc structure: fftsize = 2*2^ceil(log2 L), blocks of nsamples, a tail of
+    L-1 items carried from call to call; splitting the stream into calls changes nothing"""
+    rng = np.random.default_rng(12)
+    for L, fft in ((120, 256), (140, 512), (1120, 4096)):
+        t = templates[L]
+        a = oracle.CorrEstBlock(t, 5.0, 1, 0.9)
+        assert a.fftsize == fft and a.nsamples == fft - L + 1
+        ns = a.nsamples
+        x = (rng.standard_normal(6 * ns + L) + 1j * rng.standard_normal(6 * ns + L)).astype(np.complex64)
+        x[:L] = 0
+        _, whole, _, _ = a.work(6 * ns, x)
+        b = oracle.CorrEstBlock(t, 5.0, 1, 0.9)
+        parts = [b.work(k * ns, x[o * ns:o * ns + k * ns + L])[1] for o, k in ((0, 1), (1, 3), (4, 2))]
+        assert np.array_equal(np.concatenate(parts), whole)
+        assert np.array_equal(a.tail(), b.tail()) and len(a.tail()) == L - 1
+        assert np.max(np.abs(whole - a.direct_f64(6 * ns, x))) < 1e-5 * L
+        with pytest.raises(ValueError):
+            a.work(ns + 1, x)
+    # the transform pair: DIF forward leaves bit-reversed order, DIT inverse undoes it
+    x = (rng.standard_normal(512) + 1j * rng.standard_normal(512)).astype(np.complex64)
+    br = np.array([int(format(i, "09b")[::-1], 2) for i in range(512)])
+    X = oracle.fft_dif(x)
+    assert np.max(np.abs(X - np.fft.fft(x.astype(np.complex128))[br])) < 2e-5 * np.abs(X).max()
+    assert np.max(np.abs(oracle.ifft_dit(X) / 512 - x)) < 2e-6
 
 
 def test_corr_est_two_port_tags(oracle, templates):
