@@ -186,3 +186,40 @@ def test_square_and_fft_sync_stage(oracle):
         r = oracle.demod_chain(x[c], np.ones(8, np.complex64), oracle.chain_cfg(stages=oracle.STAGE_FREQSYNC),
                                debug=True)
         assert np.array_equal(fhat[c], r["fhat"]) and np.array_equal(y[c], r["mixed"])
+
+
+@pytest.mark.parametrize("L", [5, 8, 9, 16, 17, 33, 64, 65, 100, 128, 129, 256, 300, 513, 1024, 1025, 2048])
+def test_corr_est_every_fft_size(oracle, L):
+    """fft sizes 16 .. 4096 (every template instantiation of the overlap-add filter), random
+    taps, three work() calls so the filter tail crosses calls and CTA boundaries"""
+    rng = np.random.default_rng(100 + L)
+    t = np.exp(2j * np.pi * rng.uniform(0, 1, L)).astype(np.complex64)
+    blk = blocks.corr_est_cc.make(t, 5.0, 2, 0.5)
+    ref = oracle.CorrEstBlock(t, 5.0, 2, 0.5)
+    ns = ref.nsamples
+    assert blk.output_multiple() == ns
+    calls = [max(1, 600 // ns), max(2, 40000 // ns), 1]
+    total = sum(calls) * ns
+    stream = (0.3 * (rng.standard_normal(total + L) + 1j * rng.standard_normal(total + L))).astype(np.complex64)
+    for p in (L + 40, L + total // 2, L + total - L - 3):
+        stream[p:p + L] += t
+    written = 0
+    for k in calls:
+        n = k * ns
+        inbuf = stream[written:written + n + L]
+        out0 = np.zeros((1, n), np.complex64)
+        out1 = np.zeros((1, n), np.complex64)
+        blk.work(n, [inbuf], [out0, out1], max_tags=8192)
+        r0, rc, _, rtags = ref.work(n, inbuf, nitems_written=written, two_ports=True, max_tags=8192)
+        assert np.array_equal(out1[0], rc), "correlator stream differs (L=%d)" % L
+        assert np.array_equal(out0[0], r0)
+        _same_tags(blk.tags[0], rtags)
+        written += n
+    with pytest.raises(B.B200AisError):
+        blk.work(ns + 1, [stream[:ns + 1 + L]], [np.zeros((1, ns + 1), np.complex64)])
+
+
+def test_corr_est_rejects_unsupported_tap_counts():
+    for L in (1, 4, 2049):
+        with pytest.raises(B.B200AisError):
+            blocks.corr_est_cc.make(np.ones(L, np.complex64), 5.0, 1, 0.9)
