@@ -191,29 +191,30 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     const int n0 = t0 - kFHalo + 16 * tid; // absolute index of this thread's first sample
     const float2 *xc = x + (size_t)c * x_stride;
 
+    // stage the block's 4096 input samples through shared memory with coalesced loads (lane i
+    // reads sample i of each 256-sample row), then every thread picks up its own 16
+    {
+        const int base = t0 - kFHalo;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int li = k * 256 + tid, n = base + li;
+            ys[li + (li >> 4)] = (n >= 0 && n < n1) ? xc[n] : make_float2(0.0f, 0.0f);
+        }
+    }
+    __syncthreads();
     float2 v[16];
 #pragma unroll
     for (int k = 0; k < 16; k++)
-        v[k] = make_float2(0.0f, 0.0f);
-    if (n0 >= 0 && n0 < n1) {
-        if (do_mix) { // n1 is a multiple of fftlen, itself a multiple of 16: whole segments only
+        v[k] = ys[17 * tid + k];
+    if (do_mix && n0 >= 0 && n0 < n1) { // n1 is a multiple of fftlen (a multiple of 16): whole segments
+        float ph = ckpt[(size_t)(n0 >> 4) * channels + c];
+        const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                v[k] = xc[n0 + k];
-            float ph = ckpt[(size_t)(n0 >> 4) * channels + c];
-            const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                ph = nco_step(ph, inc);
-                float sn, cs;
-                fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
-                v[k] = cmul_fma(v[k], make_float2(cs, sn));
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                if (n0 + k < n1)
-                    v[k] = xc[n0 + k];
+        for (int k = 0; k < 16; k++) {
+            ph = nco_step(ph, inc);
+            float sn, cs;
+            fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
+            v[k] = cmul_fma(v[k], make_float2(cs, sn));
         }
     }
     float pre[16], suf[16];

@@ -168,7 +168,7 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
 }
 
 template <int LOGF>
-__global__ void __launch_bounds__(Plan<LOGF>::THREADS)
+__global__ void __launch_bounds__(Plan<LOGF>::THREADS, (LOGF <= 8 ? 5 : (LOGF <= 10 ? 3 : 1)))
 k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, int nb_per_cta,
            const float2 *__restrict__ tw, const float2 *__restrict__ hbr, float thresh,
            const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
