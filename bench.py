@@ -2,8 +2,11 @@
 """bench.py -- AIS channels demodulated per second on N B200s (BASELINE.json metric).
 
 A "step" is one pass of the demod hot path over one batch of synthetic IQ:
-`--channels` independent 48 ksps channels per GPU (default 4096, BASELINE.json configs[1]
-scale), each `--seconds` long (default 1 s = 48 000 complex samples), through
+`--channels` independent 48 ksps channels per GPU (default 16384: between BASELINE.json
+configs[1]'s 4096 and configs[3]'s 32768 per GPU; the two per-channel recurrences cost the
+same ~6 ms for any batch up to ~19k channels, so small batches under-use the GPU;
+`--channels 4096` runs configs[1]'s size), each `--seconds` long (default 1 s = 48 000
+complex samples), through
   workload "chain"    : freq sync -> AGC -> corr_est_cc -> msk_timing_recovery_cc -> bits
                         (every row of SURVEY.md section 8a; the default)
   workload "corr_msk" : corr_est_cc -> msk_timing_recovery_cc -> bits only
@@ -44,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="chain", choices=["chain", "corr_msk"])
-    ap.add_argument("--channels", type=int, default=4096, help="channels per GPU")
+    ap.add_argument("--channels", type=int, default=16384, help="channels per GPU")
     ap.add_argument("--seconds", type=float, default=1.0, help="record length per channel")
     ap.add_argument("--template", default="north_star", choices=["north_star", "intended", "reference"])
     ap.add_argument("--snr-db", type=float, default=20.0)
@@ -300,23 +303,34 @@ def run_b200(args):
     except Exception:
         pass
     corr_ms = stage_ms["corr"] / max(calls, 1)
+    taps = len(tmpl)
+    fft = 2
+    while fft < 2 * taps:
+        fft *= 2                      # kernel::fft_filter_ccc: 2 * 2^ceil(log2 taps)
+    ns = fft - taps + 1
     n1 = (n // 1024) * 1024 if args.workload == "chain" else n
-    alg_bytes = 8.0 * C * n1  # 8 B per complex sample read; the bitmask write is 1/64 of that
+    n2 = (n1 // ns) * ns              # corr_est processes whole filter blocks
+    alg_bytes = 8.0 * C * n2          # 8 B per complex sample read
     achieved = alg_bytes / (corr_ms * 1e-3) / 1e9 if corr_ms > 0 else None
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "corr_traffic.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            t = json.load(fh)
+            traffic = t["dram_bytes_per_launch"] * (C * n2) / float(t["samples_per_launch"])
     except Exception:
         pass
-    taps = len(tmpl)
-    roofline = {"bound": "hbm", "kernel": "k_corr", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    lg = fft.bit_length() - 1
+    flop_per_block = 2 * (fft // 2) * lg * 10 + 6 * fft + 2 * (taps - 1) + 3 * ns
+    roofline = {"bound": "hbm", "kernel": "k_corr_fft", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_moved_per_launch": 16.0 * C * n2 + C * n2 / 8.0,
                 "ms_per_launch": corr_ms,
-                "timing": "CUDA events around each k_corr launch, K steps re-run with all kernels serialised on the launching stream, right after the timed region",
-                "fp32_tflops": (8.0 * taps * C * n1 / (corr_ms * 1e-3) / 1e12) if corr_ms > 0 else None,
-                "note": "direct-form correlator is FP32-bound (8*L flop per 8-byte sample); both numbers reported"}
+                "timing": "CUDA events around each k_corr_fft launch, K steps re-run with all kernels serialised on the launching stream, right after the timed region",
+                "fp32_tflops": (flop_per_block * (C * n2 / ns) / (corr_ms * 1e-3) / 1e12) if corr_ms > 0 else None,
+                "note": "GNU Radio's fft_filter (FFT overlap-add, fftsize %d, %d items per block): ~%d flop per 8-byte sample, "
+                        "compute-bound; achieved counts the 8 B/sample read, bytes_moved adds the correlator stream "
+                        "(8 B/sample) and the bitmask it writes" % (fft, ns, flop_per_block // ns)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "channels/s", "n_gpus": world, "steps": args.steps,
