@@ -176,7 +176,7 @@ constexpr int kFHalo = 512;
 constexpr int kFOut = kFSpan - kFHalo;
 constexpr int kFPad = kFSpan + kFSpan / 16; // 1-in-16 padding: a thread's 16 items hit 16 banks
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
              int do_mix, float reference, const float2 *__restrict__ sine,
@@ -207,14 +207,29 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     for (int k = 0; k < 16; k++)
         v[k] = ys[17 * tid + k];
     if (do_mix && n0 >= 0 && n0 < n1) { // n1 is a multiple of fftlen (a multiple of 16): whole segments
-        float ph = ckpt[(size_t)(n0 >> 4) * channels + c];
+        const float ph0 = ckpt[(size_t)(n0 >> 4) * channels + c];
         const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
+        const float F_PI = 3.14159265358979323846f;
+        // straight-line fast path: every phase inside [-pi, pi) (always, for |inc| < 2 pi)
+        float ph = ph0;
+        bool bad = false;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            ph = nco_step(ph, inc);
+            ph = nco_step_nobranch(ph, inc, bad);
+            bad = bad || !(ph >= -F_PI && ph < F_PI);
             float sn, cs;
-            fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
+            fxpt_sincos(float_to_fixed_inrange(ph), sine, &sn, &cs);
             v[k] = cmul_fma(v[k], make_float2(cs, sn));
+        }
+        if (bad) { // general path (fmod, fold, true division) from the raw samples still in ys
+            ph = ph0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                ph = nco_step(ph, inc);
+                float sn, cs;
+                fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
+                v[k] = cmul_fma(ys[17 * tid + k], make_float2(cs, sn));
+            }
         }
     }
     float pre[16], suf[16];

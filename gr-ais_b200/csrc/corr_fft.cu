@@ -115,22 +115,32 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
 {
     constexpr int NP = Plan<LOGF>::NPASS, REM = Plan<LOGF>::REM;
     constexpr int TOP = LOGF - 4;
+    // the exchange buffer belongs to one transform: only its own threads have to meet
+    auto xsync = [&]() {
+        if constexpr (Plan<LOGF>::NT <= 32)
+            __syncwarp();
+        else if constexpr (Plan<LOGF>::GROUPS == 1)
+            __syncthreads();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / Plan<LOGF>::NT)),
+                         "r"(Plan<LOGF>::NT));
+    };
     // ---- forward, top bits first ----
     run_pass<LOGF, TOP, 4, false>(v, t, tw);
     if constexpr (NP >= 2) {
         to_smem<TOP, 4>(v, t, xb);
-        __syncthreads();
+        xsync();
         constexpr int S1 = (NP == 2) ? 0 : TOP - 4;
         constexpr int R1 = (NP == 2 && REM) ? REM : 4;
         from_smem<S1, R1>(v, t, xb);
-        __syncthreads();
+        xsync();
         run_pass<LOGF, S1, R1, false>(v, t, tw);
         if constexpr (NP >= 3) {
             to_smem<S1, R1>(v, t, xb);
-            __syncthreads();
+            xsync();
             constexpr int R2 = REM ? REM : 4;
             from_smem<0, R2>(v, t, xb);
-            __syncthreads();
+            xsync();
             run_pass<LOGF, 0, R2, false>(v, t, tw);
         }
     }
@@ -148,21 +158,21 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
         constexpr int R2 = REM ? REM : 4;
         constexpr int S1 = TOP - 4;
         to_smem<0, R2>(v, t, xb);
-        __syncthreads();
+        xsync();
         from_smem<S1, 4>(v, t, xb);
-        __syncthreads();
+        xsync();
         run_pass<LOGF, S1, 4, true>(v, t, tw);
         to_smem<S1, 4>(v, t, xb);
-        __syncthreads();
+        xsync();
         from_smem<TOP, 4>(v, t, xb);
-        __syncthreads();
+        xsync();
         run_pass<LOGF, TOP, 4, true>(v, t, tw);
     } else if constexpr (NP == 2) {
         constexpr int R1 = REM ? REM : 4;
         to_smem<0, R1>(v, t, xb);
-        __syncthreads();
+        xsync();
         from_smem<TOP, 4>(v, t, xb);
-        __syncthreads();
+        xsync();
         run_pass<LOGF, TOP, 4, true>(v, t, tw);
     }
 }
@@ -181,8 +191,8 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);     // [F/2]
     float2 *s_h = s_tw + F / 2;                              // [F]
     float2 *s_x = s_h + F;                                   // [GROUPS][F + F/16]
-    float2 *s_tail = s_x + GROUPS * (F + F / 16);            // [2][GROUPS][L-1]
-    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_tail + 2 * GROUPS * (L > 1 ? L - 1 : 1));
+    float2 *s_tail = s_x + GROUPS * (F + F / 16);            // [3][GROUPS][L-1], round r uses r % 3
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_tail + 3 * GROUPS * (L > 1 ? L - 1 : 1));
 
     const int ns = F - L + 1, tl = L - 1;
     const int c = blockIdx.y;
@@ -213,7 +223,7 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
         }
         block_filter<LOGF>(v, t, s_tw, s_h, xb);
         // stash this block's tail (outputs ns .. F-1) for the next block
-        float2 *my_tail = s_tail + ((r & 1) * GROUPS + g) * tl;
+        float2 *my_tail = s_tail + ((r % 3) * GROUPS + g) * tl;
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int e = t + NT * q;
@@ -232,9 +242,9 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
         if (valid && b >= b0) {
             const float2 *prev = nullptr; // tail of block b-1
             if (g > 0)
-                prev = s_tail + ((r & 1) * GROUPS + g - 1) * tl;
+                prev = s_tail + ((r % 3) * GROUPS + g - 1) * tl;
             else if (r > 0)
-                prev = s_tail + (((r - 1) & 1) * GROUPS + GROUPS - 1) * tl;
+                prev = s_tail + (((r - 1) % 3) * GROUPS + GROUPS - 1) * tl;
             else if (b == 0 && tail_in)
                 prev = tail_in + (size_t)c * tl; // state carried from the previous work() call
 #pragma unroll
@@ -259,10 +269,8 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
                 }
             }
         }
-        // the tail slots read here are rewritten next round (other parity: two rounds later);
-        // single-pass transforms have no barrier inside block_filter, so order it explicitly
-        if (Plan<LOGF>::NPASS == 1)
-            __syncthreads();
+        // three rotating tail buffers: the slots read above (rounds r and r-1) are next written
+        // in round r+2, after round r+1's barrier
     }
     __syncthreads();
     uint32_t *mrow = mask + (size_t)c * mask_stride_words + (((size_t)b0 * ns) >> 5);
@@ -279,7 +287,7 @@ int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, in
     using P = Plan<LOGF>;
     const int ns = P::F - L + 1;
     size_t smem = sizeof(float2) * (size_t)(P::F / 2 + P::F + P::GROUPS * (P::F + P::F / 16) +
-                                            2 * P::GROUPS * (L > 1 ? L - 1 : 1)) +
+                                            3 * P::GROUPS * (L > 1 ? L - 1 : 1)) +
                   sizeof(uint32_t) * (size_t)((nb * ns) >> 5) + 16;
     if (smem > 200 * 1024) {
         set_error("corr_est: %d taps need %zu bytes of shared memory", L, smem);
