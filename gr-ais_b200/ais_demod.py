@@ -145,7 +145,7 @@ class ais_demod:
 
     def __init__(self, options=None, channels=1, max_samples=48000, template="north_star",
                  max_tags=256, stages=B.STAGE_FREQSYNC | B.STAGE_AGC, corr_chunk=0,
-                 threshold=0.9, mark_delay=1, agc=(512, 2.0)):
+                 threshold=0.9, mark_delay=1, agc=(512, 2.0), osps=1):
         options = dict(default_options(), **(options or {}))
         self._samples_per_symbol = options["samples_per_symbol"]
         self._bits_per_sec = options["bits_per_sec"]
@@ -166,7 +166,7 @@ class ais_demod:
                                     limit=float(self._omega_relative_limit),
                                     threshold=float(threshold), mark_delay=int(mark_delay),
                                     corr_chunk=int(corr_chunk), stages=int(stages),
-                                    agc_nsamples=int(agc[0]), agc_reference=float(agc[1]))
+                                    agc_nsamples=int(agc[0]), agc_reference=float(agc[1]), osps=int(osps))
         self._h = C.c_void_p()
         rc = B.lib().b200ais_demod_create(C.byref(self._h), C.byref(self.cfg), B.ptr(self.mod_vector),
                                           len(self.mod_vector), self.channels, self.max_samples,

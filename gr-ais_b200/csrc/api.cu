@@ -761,7 +761,7 @@ extern "C" int b200ais_demod_default_config(b200ais_demod_config *cfg)
 
 static int demod_max_bits(const b200ais_demod *h, int nsamples)
 {
-    return (int)((double)nsamples / (double)h->cfg.sps * 1.05) + 64;
+    return (int)((double)nsamples / (double)h->cfg.sps * (double)h->cfg.osps * 1.05) + 64;
 }
 
 extern "C" int b200ais_demod_max_bits(const b200ais_demod *h, int nsamples)

@@ -403,8 +403,8 @@ def default_corr_chunk(L):
     return int(lib().ao_default_corr_chunk(int(L)))
 
 
-def max_bits_for(n, sps=5.0):
-    return int(n / sps * 1.05) + 64
+def max_bits_for(n, sps=5.0, osps=1):
+    return int(n / sps * osps * 1.05) + 64
 
 
 def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096):
@@ -413,7 +413,7 @@ def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096):
     x = _c64(x)
     symbols = _c64(symbols)
     n = len(x)
-    mb = max_bits_for(n, cfg.sps)
+    mb = max_bits_for(n, cfg.sps, cfg.osps)
     bits = np.zeros(mb, dtype=np.uint8)
     tags = np.zeros(max_tags, dtype=TAG_DTYPE)
     o = ChainOut()
@@ -446,7 +446,7 @@ def demod_chain_batch(x, symbols, cfg=None, max_tags=256, nthreads=0):
     x = np.ascontiguousarray(x, dtype=np.complex64)
     symbols = _c64(symbols)
     Cn, n = x.shape
-    mb = max_bits_for(n, cfg.sps)
+    mb = max_bits_for(n, cfg.sps, cfg.osps)
     bits = np.zeros((Cn, mb), dtype=np.uint8)
     nbits = np.zeros(Cn, dtype=np.int32)
     tags = np.zeros((Cn, max_tags), dtype=TAG_DTYPE)

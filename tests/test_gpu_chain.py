@@ -14,14 +14,17 @@ def _records(channels, n, **kw):
     return np.stack([r[0] for r in recs]), [r[1] for r in recs]
 
 
-def _compare_chain(oracle, x, tmpl, stages, corr_chunk=0, threshold=0.9, agc=(512, 2.0)):
+def _compare_chain(oracle, x, tmpl, stages, corr_chunk=0, threshold=0.9, agc=(512, 2.0), options=None,
+                   osps=1):
     C, n = x.shape
-    d = ais_demod(channels=C, max_samples=n, template=tmpl, stages=stages, corr_chunk=corr_chunk,
-                  threshold=threshold, max_tags=1024, agc=agc)
+    d = ais_demod(options, channels=C, max_samples=n, template=tmpl, stages=stages, corr_chunk=corr_chunk,
+                  threshold=threshold, max_tags=1024, agc=agc, osps=osps)
     d.enable_taps(True)
     bits, nbits, tags, ntags = d.work(x)
     cfg = oracle.chain_cfg(stages=stages, corr_chunk=corr_chunk, threshold=threshold,
-                           agc_nsamples=agc[0], agc_reference=agc[1])
+                           agc_nsamples=agc[0], agc_reference=agc[1], sample_rate=d.cfg.sample_rate,
+                           data_rate=d.cfg.data_rate, fftlen=d.cfg.fftlen, sps=d.cfg.sps, gain=d.cfg.gain,
+                           limit=d.cfg.limit, osps=osps)
     fh = d.read_tap(B.TAP_FHAT) if stages & B.STAGE_FREQSYNC else None
     agc = d.read_tap(B.TAP_AGC)
     sym, err, mu, soft = (d.read_tap(t) for t in (B.TAP_SYM, B.TAP_ERR, B.TAP_MU, B.TAP_SOFT))
@@ -123,3 +126,24 @@ def test_snr_sweep_gpu_equals_oracle():
     assert all(row["gpu_equals_oracle_on_subset"] for row in rows)
     assert all(row["gpu_detect"] == row["oracle_detect"] and row["gpu_crc"] == row["oracle_crc"] for row in rows)
     assert rows[-1]["gpu_detect"] >= rows[0]["gpu_detect"] and rows[-1]["gpu_crc"] >= 0.5
+
+
+@pytest.mark.parametrize("fftlen", [256, 512, 2048, 4096])
+def test_other_fft_lengths_take_the_generic_kernel(oracle, templates, fftlen):
+    """options["fftlen"] (python/radio.py:60) other than 1024: generic shared-memory FFT kernel"""
+    x, _ = _records(3, 3 * 4096, nbursts=2, snr_db=20)
+    _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC, options={"fftlen": fftlen})
+
+
+def test_non_integer_sps_and_loop_options(oracle, templates):
+    """the reference's default front end gives 250k/5/9600 = 5.2083 samples per symbol
+    (python/radio.py:50,56); gain / limit come from the options dict"""
+    x, _ = _records(3, 16384, nbursts=3, snr_db=20)
+    opts = {"samples_per_symbol": 250000.0 / 5 / 9600.0, "clockrec_gain": 0.07, "omega_relative_limit": 0.05}
+    _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC, options=opts)
+
+
+def test_two_outputs_per_symbol(oracle, templates):
+    """osps = 2: msk_timing_recovery emits every half-symbol step (:186)"""
+    x, _ = _records(2, 8192, nbursts=2, snr_db=20)
+    _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC, osps=2)
