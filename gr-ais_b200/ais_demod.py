@@ -224,6 +224,50 @@ class ais_demod:
                                                int(max_bits), B.ptr(nbits_ptr), B.ptr(tags_ptr),
                                                B.ptr(ntags_ptr), stream))
 
+    # ---- the chain as a stream: the blocks keep their state from call to call ----
+
+    def stream_reset(self, stream=None):
+        """Back to freshly constructed blocks (also implied by the first stream call)."""
+        B.check(B.lib().b200ais_demod_stream_reset(self._h, stream))
+
+    def stream_max_bits(self, nsamples):
+        return B.lib().b200ais_demod_stream_max_bits(self._h, int(nsamples))
+
+    def stream_work(self, iq):
+        """Feed the next piece of every channel's capture: iq [channels, n] complex64 host
+        array, any n in [0, max_samples].  Returns this call's (bits, nbits, tags, ntags);
+        tag offsets are absolute corr_est item offsets."""
+        iq = np.asarray(iq)
+        if iq.dtype != np.complex64 or not iq.flags.c_contiguous:
+            iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if iq.ndim == 1:
+            iq = iq.reshape(1, -1)
+        if iq.shape[0] != self.channels:
+            raise ValueError("expected %d channels" % self.channels)
+        n = iq.shape[1]
+        mb = self.stream_max_bits(n)
+        bits = np.zeros((self.channels, mb), dtype=np.uint8)
+        nbits = np.zeros(self.channels, dtype=np.int32)
+        tags = np.zeros((self.channels, self.max_tags), dtype=B.TAG_DTYPE)
+        ntags = np.zeros(self.channels, dtype=np.int32)
+        B.check(B.lib().b200ais_demod_stream_work(self._h, B.ptr(iq), n, B.ptr(bits), mb, B.ptr(nbits),
+                                                  B.ptr(tags), B.ptr(ntags)))
+        return bits, nbits, tags, ntags
+
+    def stream_work_dev(self, iq_ptr, nsamples, bits_ptr, max_bits, nbits_ptr, tags_ptr=None,
+                        ntags_ptr=None, stream=None):
+        """Device-resident variant of stream_work (raw device addresses, asynchronous)."""
+        B.check(B.lib().b200ais_demod_stream_work_dev(self._h, B.ptr(iq_ptr), int(nsamples),
+                                                      B.ptr(bits_ptr), int(max_bits), B.ptr(nbits_ptr),
+                                                      B.ptr(tags_ptr), B.ptr(ntags_ptr), stream))
+
+    def stream_pending(self):
+        """(input items short of an FFT vector, AGC outputs short of a corr_est output
+        multiple, corr_est nitems_written)."""
+        a, b, w = C.c_int(0), C.c_int(0), C.c_uint64(0)
+        B.check(B.lib().b200ais_demod_stream_pending(self._h, C.byref(a), C.byref(b), C.byref(w)))
+        return a.value, b.value, w.value
+
     def set_overlap(self, groups):
         B.check(B.lib().b200ais_demod_set_overlap(self._h, int(groups)))
 

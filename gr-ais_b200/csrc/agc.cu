@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256, 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
              int do_mix, float reference, const float2 *__restrict__ sine,
-             float2 *__restrict__ out, size_t out_stride)
+             float2 *__restrict__ out, size_t out_stride, const float2 *__restrict__ hist_in,
+             float2 *__restrict__ hist_out)
 {
     extern __shared__ float2 ys[];               // [kFPad]
     float *P = reinterpret_cast<float *>(ys + kFPad); // prefix maxima  [kFPad]
@@ -198,7 +199,12 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const int li = k * 256 + tid, n = base + li;
-            ys[li + (li >> 4)] = (n >= 0 && n < n1) ? xc[n] : make_float2(0.0f, 0.0f);
+            float2 v0 = make_float2(0.0f, 0.0f);
+            if (n >= 0 && n < n1)
+                v0 = xc[n];
+            else if (n < 0 && n >= -(kFHalo - 1) && hist_in) // already mixed: the stream's AGC history
+                v0 = hist_in[(size_t)c * (kFHalo - 1) + (kFHalo - 1 + n)];
+            ys[li + (li >> 4)] = v0;
         }
     }
     __syncthreads();
@@ -230,6 +236,14 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
                 fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
                 v[k] = cmul_fma(ys[17 * tid + k], make_float2(cs, sn));
             }
+        }
+    }
+    if (hist_out) { // the last 511 mixed items become the next call's AGC history
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int n = n0 + k;
+            if (n >= n1 - (kFHalo - 1) && n < n1 && n >= -(kFHalo - 1))
+                hist_out[(size_t)c * (kFHalo - 1) + (n - (n1 - (kFHalo - 1)))] = v[k];
         }
     }
     float pre[16], suf[16];
@@ -287,7 +301,7 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
 int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int fftlen,
                    const float *fhat, int vstride, const float *ckpt, int seg, float sens, int stages,
                    int agc_nsamples, float agc_reference, float2 *out, size_t out_stride,
-                   cudaStream_t s)
+                   const float2 *hist_in, float2 *hist_out, cudaStream_t s)
 {
     if (n1 <= 0 || channels <= 0)
         return B200AIS_OK;
@@ -309,9 +323,13 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
                                                    ckpt, sens, (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0,
                                                    agc_reference,
                                                    reinterpret_cast<const float2 *>(tb.sine), out,
-                                                   out_stride);
+                                                   out_stride, hist_in, hist_out);
         B200_LAUNCH_CHECK("k_mix_agc512");
         return B200AIS_OK;
+    }
+    if (hist_in || hist_out) {
+        set_error("streaming needs the feedforward_agc_cc(512, .) fast path (16-sample checkpoints)");
+        return B200AIS_E_INVALID;
     }
     int halo = (stages & B200AIS_STAGE_AGC) ? agc_nsamples - 1 : 0;
     size_t smem = (size_t)(kAgcTile + halo) * (sizeof(float2) + 2 * sizeof(float));

@@ -285,7 +285,7 @@ extern "C" int b200ais_corr_est_work_dev(b200ais_corr_est *h, int noutput_items,
     const int isps = (int)(h->sps + 0.5f); // :193
     rc = launch_detect(corr, corr_stride, h->channels, n, n > 0 ? n : 1, 1, isps, h->mark_delay,
                        h->mask.as<uint8_t>(), ms, nitems_written, out1 != nullptr, tags, max_tags,
-                       ntags, h->d_status, s);
+                       ntags, h->d_status, 0, s);
     if (rc)
         return rc;
     if (out0)
@@ -491,7 +491,7 @@ extern "C" int b200ais_msk_general_work_dev(b200ais_msk *h, int noutput_items, i
     return launch_msk(reinterpret_cast<const float2 *>(in), in_stride, h->channels, noutput_items,
                       ninput_items, nitems_read, tags, max_tags, ntags, h->p, h->d_state,
                       reinterpret_cast<float2 *>(out), out_err, out_mu, out_stride, nproduced,
-                      nconsumed, 0, h->d_status, s);
+                      nconsumed, 0, h->d_status, nullptr, s);
 }
 
 extern "C" int b200ais_msk_general_work(b200ais_msk *h, int noutput_items, int ninput_items,
@@ -695,6 +695,7 @@ extern "C" int b200ais_invert_work(const uint8_t *in, uint8_t *out, size_t nitem
 // =============================================== the fused ais_demod chain
 
 namespace {
+constexpr int kKeep = 32;     // stream mode: corr_est output-0 items kept for the timing loop
 constexpr int kSeg = 16;      // NCO phase checkpoint spacing (samples)
 constexpr int kMaxGroups = 8; // channel groups pipelined over internal streams
 } // namespace
@@ -731,12 +732,27 @@ struct b200ais_demod {
     cudaEvent_t ev_fork = nullptr;
     int overlap_groups = 4; // channel groups a *_dev call forks over internal streams (1 = none)
     bool taps_enabled = false;
-    DevBuf t_sym, t_err, t_mu, t_soft;
+    DevBuf t_sym, t_err, t_mu, t_soft, t_otags;
     bool profiling = false;
     std::vector<std::vector<cudaEvent_t>> ev_used, ev_free; // 7 events per profiled call
     double stage_ms[B200AIS_STAGE_T_COUNT] = { 0, 0, 0, 0, 0, 0, 0 };
     int prof_calls = 0;
     int last_n = 0, last_max_bits = 0, last_n1 = 0;
+    // ---- stream mode (b200ais_demod_stream_*): what every block keeps between calls ----
+    bool st_ready = false;     // state allocated and reset
+    bool pad_dirty = false;    // stream calls used the rows' history pads: batch calls re-zero them
+    int st_nx = 0;             // input items waiting for a whole FFT vector (same for all channels)
+    int st_na = 0;             // AGC outputs corr_est has not taken yet
+    uint64_t st_written = 0;   // corr_est nitems_written
+    float2 *d_xcarry = nullptr;            // [channels][fftlen]
+    DevBuf xs;                             // assembled input rows [channels][xs_stride]
+    size_t xs_stride = 0;
+    float *d_phase = nullptr;              // NCO phase [channels]
+    float2 *d_yhist[2] = { nullptr, nullptr }; // mixed AGC history [channels][511], ping-pong
+    float2 *d_ctail[2] = { nullptr, nullptr }; // overlap-add tail [channels][L-1], ping-pong
+    int yh_cur = 0, ct_cur = 0;
+    int *d_unc = nullptr, *d_nold = nullptr;
+    TailCarry *d_tcarry = nullptr;
 };
 
 extern "C" int b200ais_demod_default_config(b200ais_demod_config *cfg)
@@ -832,11 +848,15 @@ extern "C" int b200ais_demod_create(b200ais_demod **out, const b200ais_demod_con
     h->mp.gain_omega = (float)((double)(cfg->gain * cfg->gain) * 0.25);
     h->mp.limit = cfg->limit;
     h->mp.osps = cfg->osps;
-    h->HP = (int)round_up((size_t)nsymbols + 2, 4);
-    h->a_stride = round_up((size_t)h->HP + (size_t)max_samples + 16, 4);
-    h->mask_stride = corr_mask_stride_bytes(nsymbols, max_samples);
-    h->corr_stride = round_up((size_t)max_samples, 2);
-    h->nvec_max = (cfg->stages & B200AIS_STAGE_FREQSYNC) ? max_samples / cfg->fftlen : 0;
+    // rows are sized for a stream call: up to fftlen-1 waiting input items and nsamples-1
+    // waiting AGC outputs come on top of the call's own samples
+    const bool fsync = cfg->stages & B200AIS_STAGE_FREQSYNC;
+    const size_t cap_n = (size_t)max_samples + (fsync ? cfg->fftlen : 0) + h->nsamples;
+    h->HP = (int)round_up((size_t)nsymbols + kKeep, 4);
+    h->a_stride = round_up((size_t)h->HP + cap_n + 16, 4);
+    h->mask_stride = corr_mask_stride_bytes(nsymbols, (int)cap_n);
+    h->corr_stride = round_up(cap_n, 2);
+    h->nvec_max = fsync ? max_samples / cfg->fftlen + 1 : 0;
 
     const size_t C = (size_t)channels;
     // corr_est ctor: taps = reverse(conj(symbols)); fft_filter::set_taps transforms them once
@@ -893,7 +913,9 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
         return B200AIS_OK;
     void *ptrs[] = { h->d_taps_time, h->d_corr, h->d_x, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
                      h->d_tags, h->d_ntags, h->d_nbits, h->d_ncons, h->d_state, h->d_bits,
-                     h->d_status };
+                     h->d_status, h->d_xcarry, h->d_phase, h->d_yhist[0], h->d_yhist[1],
+                     h->d_ctail[0], h->d_ctail[1], h->d_unc, h->d_nold, h->d_tcarry };
+    h->xs.release();
     for (void *p : ptrs)
         if (p)
             cudaFree(p);
@@ -909,6 +931,7 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
     h->t_err.release();
     h->t_mu.release();
     h->t_soft.release();
+    h->t_otags.release();
     for (auto *pool : { &h->ev_used, &h->ev_free })
         for (auto &set : *pool)
             for (auto e : set)
@@ -967,14 +990,14 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     }
     B200_MARK(B200AIS_STAGE_T_SQFFT);
     if (fs) {
-        if ((rc = launch_nco_phase(raw, cn, nvec, vs, cfg.fftlen, h->binsize, h->sens, fhat, ckpt, kSeg, s)))
+        if ((rc = launch_nco_phase(raw, cn, nvec, vs, cfg.fftlen, h->binsize, h->sens, fhat, ckpt, kSeg, nullptr, s)))
             return rc;
     }
     B200_MARK(B200AIS_STAGE_T_NCO);
     if (!in_a) {
         if ((rc = launch_mix_agc(iq, iq_stride, cn, n1, cfg.fftlen, fhat, vs, ckpt, kSeg, h->sens,
                                  cfg.stages, cfg.agc_nsamples, cfg.agc_reference, a_rows,
-                                 h->a_stride, s)))
+                                 h->a_stride, nullptr, nullptr, s)))
             return rc;
     }
     B200_MARK(B200AIS_STAGE_T_MIXAGC);
@@ -991,7 +1014,7 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     B200_MARK(B200AIS_STAGE_T_CORR);
     if ((rc = launch_detect(corr, h->corr_stride, cn, n2, h->chunk, h->nsamples, h->isps,
                             h->mark_delay, mask, h->mask_stride, 0, 0, tags, h->max_tags, ntags,
-                            d_status, s)))
+                            d_status, 0, s)))
         return rc;
     B200_MARK(B200AIS_STAGE_T_DETECT);
     if ((rc = launch_msk_reset(h->d_state + c0, cn, h->mp.sps_half, s)))
@@ -1003,10 +1026,10 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     // msk reads corr_est output 0: out0[k] = in[k - L] (history delay), zeros for k < L
     rc = launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, n2, 0, tags, h->max_tags, ntags,
                     h->mp, h->d_state + c0, t_sym, t_err, t_mu, (size_t)max_bits, nbits,
-                    h->d_ncons + c0, 1, d_status, s);
+                    h->d_ncons + c0, 1, d_status, nullptr, s);
     B200_MARK(B200AIS_STAGE_T_MSK);
     if (!rc)
-        rc = launch_tail(t_sym, (size_t)max_bits, nbits, cn, max_bits, bits, (size_t)max_bits, t_soft, s);
+        rc = launch_tail(t_sym, (size_t)max_bits, nbits, cn, max_bits, bits, (size_t)max_bits, t_soft, nullptr, s);
     B200_MARK(B200AIS_STAGE_T_TAIL);
 #undef B200_MARK
     return rc;
@@ -1079,6 +1102,14 @@ static int demod_prepare(b200ais_demod *h, int n, int max_bits)
             (rc = h->t_mu.reserve(items * sizeof(float))) || (rc = h->t_soft.reserve(items * sizeof(float))))
             return rc;
     }
+    if (h->pad_dirty) { // a stream left items in the history pads the batch path reads as zeros
+        B200_CU(cudaDeviceSynchronize());
+        B200_CU(cudaMemset2D(h->d_a, h->a_stride * sizeof(float2), 0, (size_t)h->HP * sizeof(float2),
+                             (size_t)h->channels));
+        B200_CU(cudaDeviceSynchronize());
+        h->pad_dirty = false;
+    }
+    h->st_ready = false; // a batch call overwrites the rows a stream lives in: the next stream call starts fresh
     h->last_n = n;
     h->last_max_bits = max_bits;
     h->last_n1 = (h->cfg.stages & B200AIS_STAGE_FREQSYNC) ? (n / h->cfg.fftlen) * h->cfg.fftlen : n;
@@ -1214,6 +1245,297 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
     }
     for (int g = 0; g < ngroups; g++)
         B200_CU(cudaStreamSynchronize(h->streams[g]));
+    return b200ais_demod_status(h);
+}
+
+
+// =============================================== the chain as a stream
+//
+// b200ais_demod_work() restarts every block on each call (one record = one flowgraph run).
+// The stream entry points keep what GNU Radio's scheduler and the blocks keep between work()
+// calls, so a capture can be fed in pieces of any size:
+//   - input items waiting for a whole FFT vector (stream_to_vector),
+//   - the NCO phase (frequency_modulator_fc d_phase),
+//   - the last 511 mixed items (feedforward_agc_cc history),
+//   - AGC outputs waiting for a whole corr_est output multiple, the filter's overlap-add tail
+//     and the L history items behind them (lib/corr_est_cc_impl.cc:77-78,188),
+//   - corr_est output-0 items the timing loop has not consumed, its loop state and the tags it
+//     may still meet (lib/msk_timing_recovery_cc_impl.cc:125-130,203),
+//   - the previous symbol / slicer decision of quadrature_demod_cf / diff_decoder_bb.
+// One call = one scheduler pass in which every block runs once over what is available to it.
+// Row layout of d_a in stream mode: [HP items behind corr_est's read pointer | waiting AGC
+// outputs | this call's AGC outputs]; corr_est's filter reads from row + HP, the timing loop
+// from row + HP - L - unconsumed[c].
+
+static int stream_alloc(b200ais_demod *h)
+{
+    if (h->d_unc)
+        return B200AIS_OK;
+    const size_t C = (size_t)h->channels;
+    const bool fs = h->cfg.stages & B200AIS_STAGE_FREQSYNC;
+    h->xs_stride = round_up((size_t)h->max_samples + (fs ? h->cfg.fftlen : 0) + 4, 4);
+    B200_CU(cudaMalloc(&h->d_xcarry, sizeof(float2) * C * (size_t)std::max(h->cfg.fftlen, 1)));
+    B200_CU(cudaMalloc(&h->d_phase, sizeof(float) * C));
+    for (int k = 0; k < 2; k++) {
+        B200_CU(cudaMalloc(&h->d_yhist[k], sizeof(float2) * C * 511));
+        B200_CU(cudaMalloc(&h->d_ctail[k], sizeof(float2) * C * (size_t)(h->L - 1)));
+    }
+    B200_CU(cudaMalloc(&h->d_nold, sizeof(int) * C));
+    B200_CU(cudaMalloc(&h->d_tcarry, sizeof(TailCarry) * C));
+    B200_CU(cudaMalloc(&h->d_unc, sizeof(int) * C));
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_stream_reset(b200ais_demod *h, void *stream)
+{
+    if (!h) {
+        set_error("demod_stream_reset: null handle");
+        return B200AIS_E_INVALID;
+    }
+    if (!(h->cfg.stages & B200AIS_STAGE_AGC) || h->cfg.agc_nsamples != 512) {
+        set_error("demod_stream: needs the AGC stage with the reference's 512-sample window");
+        return B200AIS_E_INVALID;
+    }
+    if ((int)std::ceil(3.0 * h->mp.sps_half) + 6 > kKeep) {
+        set_error("demod_stream: samples per symbol too large for the %d-item carry", kKeep);
+        return B200AIS_E_INVALID;
+    }
+    int rc = stream_alloc(h);
+    if (rc)
+        return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t C = (size_t)h->channels;
+    B200_CU(cudaMemset2DAsync(h->d_a, h->a_stride * sizeof(float2), 0,
+                              (size_t)(h->HP + h->nsamples) * sizeof(float2), C, s));
+    B200_CU(cudaMemsetAsync(h->d_phase, 0, sizeof(float) * C, s));
+    for (int k = 0; k < 2; k++) {
+        B200_CU(cudaMemsetAsync(h->d_yhist[k], 0, sizeof(float2) * C * 511, s));
+        B200_CU(cudaMemsetAsync(h->d_ctail[k], 0, sizeof(float2) * C * (size_t)(h->L - 1), s));
+    }
+    B200_CU(cudaMemsetAsync(h->d_unc, 0, sizeof(int) * C, s));
+    B200_CU(cudaMemsetAsync(h->d_nold, 0, sizeof(int) * C, s));
+    B200_CU(cudaMemsetAsync(h->d_ntags, 0, sizeof(int) * C, s));
+    B200_CU(cudaMemsetAsync(h->d_tcarry, 0, sizeof(TailCarry) * C, s));
+    if ((rc = launch_msk_reset(h->d_state, h->channels, h->mp.sps_half, s)))
+        return rc;
+    h->st_nx = h->st_na = 0;
+    h->st_written = 0;
+    h->yh_cur = h->ct_cur = 0;
+    h->st_ready = true;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_stream_max_bits(const b200ais_demod *h, int nsamples)
+{
+    if (!h)
+        return 0;
+    const int extra = ((h->cfg.stages & B200AIS_STAGE_FREQSYNC) ? h->cfg.fftlen : 0) + h->nsamples + kKeep;
+    return demod_max_bits(h, nsamples + extra);
+}
+
+extern "C" int b200ais_demod_stream_pending(const b200ais_demod *h, int *input_items, int *agc_items,
+                                            uint64_t *corr_written)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    if (input_items)
+        *input_items = h->st_ready ? h->st_nx : 0;
+    if (agc_items)
+        *agc_items = h->st_ready ? h->st_na : 0;
+    if (corr_written)
+        *corr_written = h->st_ready ? h->st_written : 0;
+    return B200AIS_OK;
+}
+
+// xin: this call's input rows on the device.  When items are waiting (st_nx > 0) or host_rows
+// is set, the rows are [waiting | new] in h->xs and xin is ignored / already there.
+static int stream_run(b200ais_demod *h, const float2 *xin, size_t xin_stride, bool in_xs, int n,
+                      uint8_t *bits, int max_bits, int *nbits, b200ais_tag *tags, int *ntags,
+                      cudaStream_t s)
+{
+    const b200ais_demod_config &cfg = h->cfg;
+    const int C = h->channels;
+    const bool fs = cfg.stages & B200AIS_STAGE_FREQSYNC;
+    const int nx = h->st_nx, navail = nx + n;
+    int rc;
+    if (!in_xs && nx > 0) { // [waiting | new] into the assembly rows
+        if ((rc = h->xs.reserve(h->xs_stride * (size_t)C * sizeof(float2))))
+            return rc;
+        float2 *xs = h->xs.as<float2>();
+        B200_CU(cudaMemcpy2DAsync(xs + nx, h->xs_stride * sizeof(float2), xin, xin_stride * sizeof(float2),
+                                  (size_t)n * sizeof(float2), C, cudaMemcpyDeviceToDevice, s));
+        xin = xs;
+        xin_stride = h->xs_stride;
+        in_xs = true;
+    }
+    if (in_xs && nx > 0) {
+        float2 *xs = h->xs.as<float2>();
+        B200_CU(cudaMemcpy2DAsync(xs, h->xs_stride * sizeof(float2), h->d_xcarry,
+                                  (size_t)cfg.fftlen * sizeof(float2), (size_t)nx * sizeof(float2), C,
+                                  cudaMemcpyDeviceToDevice, s));
+    }
+    const int n1 = fs ? (navail / cfg.fftlen) * cfg.fftlen : navail;
+    const int nvec = fs ? n1 / cfg.fftlen : 0;
+    const int vs = std::max(h->nvec_max, 1);
+    if (fs && nvec > 0) {
+        if ((rc = launch_sqfft_freqest(xin, xin_stride, C, nvec, vs, cfg.fftlen, h->offset, h->d_raw, s)))
+            return rc;
+        if ((rc = launch_nco_phase(h->d_raw, C, nvec, vs, cfg.fftlen, h->binsize, h->sens, h->d_fhat,
+                                   h->d_ckpt, kSeg, h->d_phase, s)))
+            return rc;
+    }
+    const int na = h->st_na;
+    if (n1 > 0) {
+        if ((rc = launch_mix_agc(xin, xin_stride, C, n1, cfg.fftlen, h->d_fhat, vs, h->d_ckpt, kSeg,
+                                 h->sens, cfg.stages, cfg.agc_nsamples, cfg.agc_reference,
+                                 h->d_a + h->HP + na, h->a_stride, h->d_yhist[h->yh_cur],
+                                 h->d_yhist[h->yh_cur ^ 1], s)))
+            return rc;
+        h->yh_cur ^= 1;
+    }
+    const int nx_new = navail - n1; // < fftlen
+    if (nx_new > 0)
+        B200_CU(cudaMemcpy2DAsync(h->d_xcarry, (size_t)cfg.fftlen * sizeof(float2), xin + n1,
+                                  xin_stride * sizeof(float2), (size_t)nx_new * sizeof(float2), C,
+                                  cudaMemcpyDeviceToDevice, s));
+    // corr_est: whole output multiples, in work chunks, from the carried filter tail
+    const int avail = na + n1;
+    const int n2 = (avail / h->nsamples) * h->nsamples;
+    const float2 *tw = nullptr;
+    if ((rc = get_twiddles(corr_fft_size(h->L), &tw)))
+        return rc;
+    if (n2 > 0) {
+        if ((rc = launch_corr_fft(h->d_a + h->HP, h->a_stride, C, n2, h->L, tw, h->d_taps_time,
+                                  h->thresh, h->d_ctail[h->ct_cur], h->d_ctail[h->ct_cur ^ 1], h->d_mask,
+                                  h->mask_stride, h->d_corr, h->corr_stride, s)))
+            return rc;
+        h->ct_cur ^= 1;
+    }
+    if ((rc = launch_tags_compact(h->d_tags, h->max_tags, h->d_ntags, h->d_unc, h->st_written, C,
+                                  h->d_nold, s)))
+        return rc;
+    if ((rc = launch_detect(h->d_corr, h->corr_stride, C, n2, h->chunk, h->nsamples, h->isps,
+                            h->mark_delay, h->d_mask, h->mask_stride, h->st_written, 0, h->d_tags,
+                            h->max_tags, h->d_ntags, h->d_status, 1, s)))
+        return rc;
+    // the timing loop over everything corr_est has produced and it has not consumed
+    float2 *t_sym = h->t_sym.as<float2>();
+    float *t_err = h->taps_enabled ? h->t_err.as<float>() : nullptr;
+    float *t_mu = h->taps_enabled ? h->t_mu.as<float>() : nullptr;
+    float *t_soft = h->taps_enabled ? h->t_soft.as<float>() : nullptr;
+    if ((rc = launch_msk(h->d_a + h->HP - h->L, h->a_stride, C, max_bits, n2, h->st_written, h->d_tags,
+                         h->max_tags, h->d_ntags, h->mp, h->d_state, t_sym, t_err, t_mu,
+                         (size_t)max_bits, nbits, h->d_ncons, 1, h->d_status, h->d_unc, s)))
+        return rc;
+    if ((rc = launch_tail(t_sym, (size_t)max_bits, nbits, C, max_bits, bits, (size_t)max_bits, t_soft,
+                          h->d_tcarry, s)))
+        return rc;
+    if (tags || ntags) {
+        if (!tags) {
+            set_error("demod_stream_work: ntags without tags");
+            return B200AIS_E_INVALID;
+        }
+        if ((rc = launch_tags_emit(h->d_tags, h->max_tags, h->d_ntags, h->d_nold, C, tags, ntags,
+                                   h->d_status, s)))
+            return rc;
+    }
+    // keep HP items behind corr_est's new read pointer and what it has not taken
+    if ((rc = launch_roll_rows(h->d_a, h->a_stride, C, n2, h->HP + avail - n2, s)))
+        return rc;
+    h->st_nx = nx_new;
+    h->st_na = avail - n2;
+    h->st_written += (uint64_t)n2;
+    h->pad_dirty = true;
+    h->last_n = n;
+    h->last_max_bits = max_bits;
+    h->last_n1 = n1;
+    return B200AIS_OK;
+}
+
+static int stream_prepare(b200ais_demod *h, int n, int max_bits, cudaStream_t s)
+{
+    if (n < 0 || n > h->max_samples) {
+        set_error("demod_stream_work: nsamples %d outside [0, %d]", n, h->max_samples);
+        return B200AIS_E_INVALID;
+    }
+    if (max_bits < 1) {
+        set_error("demod_stream_work: max_bits must be positive");
+        return B200AIS_E_INVALID;
+    }
+    int rc;
+    if (!h->st_ready && (rc = b200ais_demod_stream_reset(h, s)))
+        return rc;
+    if ((rc = h->t_sym.reserve((size_t)h->channels * max_bits * sizeof(float2))))
+        return rc;
+    if (h->taps_enabled) {
+        const size_t items = (size_t)h->channels * max_bits;
+        if ((rc = h->t_err.reserve(items * sizeof(float))) ||
+            (rc = h->t_mu.reserve(items * sizeof(float))) || (rc = h->t_soft.reserve(items * sizeof(float))))
+            return rc;
+    }
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_stream_work_dev(b200ais_demod *h, const float *iq, int nsamples,
+                                             uint8_t *bits, int max_bits, int *nbits,
+                                             b200ais_tag *tags, int *ntags, void *stream)
+{
+    if (!h || (!iq && nsamples > 0) || !bits || !nbits) {
+        set_error("demod_stream_work: null argument");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = stream_prepare(h, nsamples, max_bits, s);
+    if (rc)
+        return rc;
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
+    return stream_run(h, reinterpret_cast<const float2 *>(iq), (size_t)nsamples, false, nsamples, bits,
+                      max_bits, nbits, tags, ntags, s);
+}
+
+extern "C" int b200ais_demod_stream_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
+                                         int max_bits, int *nbits, b200ais_tag *tags, int *ntags)
+{
+    if (!h || (!iq && nsamples > 0) || !bits || !nbits) {
+        set_error("demod_stream_work: null argument");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = h->streams[0];
+    int rc = stream_prepare(h, nsamples, max_bits, s);
+    if (rc)
+        return rc;
+    const int C = h->channels, n = nsamples;
+    if ((rc = h->xs.reserve(h->xs_stride * (size_t)C * sizeof(float2))))
+        return rc;
+    if (h->bits_cap < (size_t)max_bits * C) {
+        if (h->d_bits)
+            cudaFree(h->d_bits);
+        h->d_bits = nullptr;
+        h->bits_cap = 0;
+        B200_CU(cudaMalloc(&h->d_bits, (size_t)max_bits * C));
+        h->bits_cap = (size_t)max_bits * C;
+    }
+    DevBuf &ot = h->t_otags; // this call's tags before they go to the host
+    if (tags && (rc = ot.reserve(sizeof(b200ais_tag) * (size_t)h->max_tags * C)))
+        return rc;
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
+    float2 *xs = h->xs.as<float2>();
+    if (n > 0)
+        B200_CU(cudaMemcpy2DAsync(xs + h->st_nx, h->xs_stride * sizeof(float2), iq, (size_t)n * sizeof(float2),
+                                  (size_t)n * sizeof(float2), C, cudaMemcpyHostToDevice, s));
+    rc = stream_run(h, xs, h->xs_stride, true, n, h->d_bits, max_bits, h->d_nbits,
+                    tags ? ot.as<b200ais_tag>() : nullptr, tags ? h->d_ncons : nullptr, s);
+    if (rc)
+        return rc;
+    B200_CU(cudaMemcpyAsync(bits, h->d_bits, (size_t)max_bits * C, cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaMemcpyAsync(nbits, h->d_nbits, sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, s));
+    if (tags) {
+        B200_CU(cudaMemcpyAsync(tags, ot.as<b200ais_tag>(), sizeof(b200ais_tag) * (size_t)h->max_tags * C,
+                                cudaMemcpyDeviceToHost, s));
+        if (ntags)
+            B200_CU(cudaMemcpyAsync(ntags, h->d_ncons, sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, s));
+    }
+    B200_CU(cudaStreamSynchronize(s));
     return b200ais_demod_status(h);
 }
 

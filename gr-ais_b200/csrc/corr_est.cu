@@ -33,7 +33,7 @@ __global__ void k_detect(const float2 *__restrict__ corr, size_t corr_stride, in
                          const uint8_t *__restrict__ mask, size_t mask_stride, uint64_t base_offset,
                          int two_ports, const float *__restrict__ atan_tab,
                          b200ais_tag *__restrict__ tags, int max_tags, int *__restrict__ ntags,
-                         int *__restrict__ status)
+                         int *__restrict__ status, int append)
 {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -43,7 +43,7 @@ __global__ void k_detect(const float2 *__restrict__ corr, size_t corr_stride, in
     const float2 *cc = corr + (size_t)c * corr_stride;
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mask + (size_t)c * mask_stride);
     b200ais_tag *tg = tags + (size_t)c * max_tags;
-    int cnt = 0;
+    int cnt = append ? ntags[c] : 0; // stream mode: the list persists from call to call
     int cs = 0;
     while (n_total - cs >= ns) {
         int nn = n_total - cs;
@@ -141,12 +141,99 @@ __global__ void k_detect(const float2 *__restrict__ corr, size_t corr_stride, in
     }
 }
 
+__global__ void k_tags_compact(b200ais_tag *__restrict__ tags, int max_tags, int *__restrict__ ntags,
+                               const int *__restrict__ unconsumed, uint64_t written, int channels,
+                               int *__restrict__ nold)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels)
+        return;
+    b200ais_tag *tg = tags + (size_t)c * max_tags;
+    const uint64_t read = written - (uint64_t)unconsumed[c]; // msk's nitems_read
+    const int n = min(ntags[c], max_tags);
+    int keep = 0;
+    for (int k = 0; k < n; k++) {
+        const b200ais_tag t = tg[k];
+        if (t.offset >= read)
+            tg[keep++] = t;
+    }
+    ntags[c] = keep;
+    nold[c] = keep;
+}
+
+__global__ void k_tags_emit(const b200ais_tag *__restrict__ tags, int max_tags,
+                            const int *__restrict__ ntags, const int *__restrict__ nold, int channels,
+                            b200ais_tag *__restrict__ out_tags, int *__restrict__ out_ntags,
+                            int *__restrict__ status)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels)
+        return;
+    const int first = nold[c], cnt = ntags[c];
+    const int last = min(cnt, max_tags);
+    for (int k = first; k < last; k++)
+        out_tags[(size_t)c * max_tags + (k - first)] = tags[(size_t)c * max_tags + k];
+    if (out_ntags)
+        out_ntags[c] = cnt - first;
+    if (cnt > max_tags)
+        atomicMin(status, (int)B200AIS_E_TAG_OVERFLOW);
+}
+
+__global__ void k_roll_rows(float2 *__restrict__ rows, size_t stride, int from, int len)
+{
+    extern __shared__ float2 hold[];
+    float2 *r = rows + (size_t)blockIdx.x * stride;
+    for (int i = threadIdx.x; i < len; i += blockDim.x)
+        hold[i] = r[from + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x)
+        r[i] = hold[i];
+}
+
 } // namespace
+
+int launch_tags_compact(b200ais_tag *tags, int max_tags, int *ntags, const int *unconsumed,
+                        uint64_t written, int channels, int *nold, cudaStream_t s)
+{
+    if (channels <= 0)
+        return B200AIS_OK;
+    k_tags_compact<<<(channels + 127) / 128, 128, 0, s>>>(tags, max_tags, ntags, unconsumed, written,
+                                                          channels, nold);
+    B200_LAUNCH_CHECK("k_tags_compact");
+    return B200AIS_OK;
+}
+
+int launch_tags_emit(const b200ais_tag *tags, int max_tags, const int *ntags, const int *nold,
+                     int channels, b200ais_tag *out_tags, int *out_ntags, int *status, cudaStream_t s)
+{
+    if (channels <= 0)
+        return B200AIS_OK;
+    k_tags_emit<<<(channels + 127) / 128, 128, 0, s>>>(tags, max_tags, ntags, nold, channels, out_tags,
+                                                       out_ntags, status);
+    B200_LAUNCH_CHECK("k_tags_emit");
+    return B200AIS_OK;
+}
+
+int launch_roll_rows(float2 *rows, size_t stride, int channels, int from, int len, cudaStream_t s)
+{
+    if (channels <= 0 || len <= 0 || from <= 0)
+        return B200AIS_OK;
+    const size_t smem = (size_t)len * sizeof(float2);
+    if (smem > 200 * 1024) {
+        set_error("roll_rows: %d items do not fit in shared memory", len);
+        return B200AIS_E_INVALID;
+    }
+    if (smem > 48 * 1024)
+        B200_CU(cudaFuncSetAttribute(k_roll_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_roll_rows<<<channels, 256, smem, s>>>(rows, stride, from, len);
+    B200_LAUNCH_CHECK("k_roll_rows");
+    return B200AIS_OK;
+}
 
 int launch_detect(const float2 *corr, size_t corr_stride, int channels, int n_total, int chunk,
                   int nsamples_mult, int isps, unsigned mark_delay, const uint8_t *mask,
                   size_t mask_stride, uint64_t base_offset, int two_ports, b200ais_tag *tags,
-                  int max_tags, int *ntags, int *status, cudaStream_t s)
+                  int max_tags, int *ntags, int *status, int append, cudaStream_t s)
 {
     if (channels <= 0)
         return B200AIS_OK;
@@ -158,7 +245,7 @@ int launch_detect(const float2 *corr, size_t corr_stride, int channels, int n_to
     const int blocks = (channels * 32 + threads - 1) / threads;
     k_detect<<<blocks, threads, 0, s>>>(corr, corr_stride, channels, n_total, chunk, nsamples_mult,
                                         isps, mark_delay, mask, mask_stride, base_offset, two_ports,
-                                        tb.atan, tags, max_tags, ntags, status);
+                                        tb.atan, tags, max_tags, ntags, status, append);
     B200_LAUNCH_CHECK("k_detect");
     return B200AIS_OK;
 }

@@ -333,12 +333,12 @@ __global__ void k_freqest_resolve(const int *__restrict__ raw, int channels, int
 template <int kSeg>
 __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec, int vstride, int n,
                             float binsize, float sens, float *__restrict__ fhat,
-                            float *__restrict__ ckpt, int seg)
+                            float *__restrict__ ckpt, int seg, float *__restrict__ phase_state)
 {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels)
         return;
-    float ph = 0.0f;
+    float ph = phase_state ? phase_state[c] : 0.0f; // NCO phase carried by the stream (0 when fresh)
     int maxpos = 0;
     const int segs_per_vec = n / seg;
     float *cp = ckpt + c; // ckpt[segment * channels + c], walked with a running pointer
@@ -369,6 +369,8 @@ __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec,
             }
         }
     }
+    if (phase_state)
+        phase_state[c] = ph;
 }
 
 } // namespace
@@ -397,10 +399,14 @@ int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nve
         return rc;
     size_t smem = (size_t)fftlen * (sizeof(float2) + sizeof(float));
     dim3 grid(nvec, channels);
-    if (fftlen == 1024)
+    if (fftlen == 1024) {
         k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw);
-    else
+    } else {
+        if (smem > 48 * 1024)
+            B200_CU(cudaFuncSetAttribute(k_sqfft_freqest, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
         k_sqfft_freqest<<<grid, kFftThreads, smem, s>>>(x, x_stride, vstride, fftlen, lg, tw, offset, raw);
+    }
     B200_LAUNCH_CHECK("k_sqfft_freqest");
     return B200AIS_OK;
 }
@@ -429,7 +435,7 @@ int launch_freqest_resolve(const int *raw, int channels, int nvec, int fftlen, f
 }
 
 int launch_nco_phase(const int *raw, int channels, int nvec, int vstride, int fftlen, float binsize,
-                     float sens, float *fhat, float *ckpt, int seg, cudaStream_t s)
+                     float sens, float *fhat, float *ckpt, int seg, float *phase_state, cudaStream_t s)
 {
     if (nvec <= 0 || channels <= 0)
         return B200AIS_OK;
@@ -437,10 +443,10 @@ int launch_nco_phase(const int *raw, int channels, int nvec, int vstride, int ff
     const int blocks = (channels + threads - 1) / threads;
     if (seg == 16)
         k_nco_phase<16><<<blocks, threads, 0, s>>>(raw, channels, nvec, vstride, fftlen, binsize, sens,
-                                                   fhat, ckpt, seg);
+                                                   fhat, ckpt, seg, phase_state);
     else
         k_nco_phase<0><<<blocks, threads, 0, s>>>(raw, channels, nvec, vstride, fftlen, binsize, sens,
-                                                  fhat, ckpt, seg);
+                                                  fhat, ckpt, seg, phase_state);
     B200_LAUNCH_CHECK("k_nco_phase");
     return B200AIS_OK;
 }

@@ -58,6 +58,12 @@ struct MskState {
     int pad;
 };
 
+// Stream state of the bit tail: the last two symbols and the last slicer decision.
+struct TailCarry {
+    float m2x, m2y, m1x, m1y;
+    int bprev, pad;
+};
+
 // ---- launch wrappers (each returns B200AIS_OK or an error code) ----
 
 // G1 + A8 first half: square -> FFT -> shifted |.| -> argmax, one block per (vector, channel).
@@ -73,14 +79,15 @@ int launch_freqest_resolve(const int *raw, int channels, int nvec, int fftlen, f
                            float *out, cudaStream_t s);
 // G2 serial part: maxpos carry-over, Hz conversion and the NCO phase recurrence, one thread
 // per channel; phase checkpoints every `seg` samples, ckpt[(n/seg)*channels + c].
+// phase_state (nullable): [channels] NCO phase carried across calls (read, then updated).
 int launch_nco_phase(const int *raw, int channels, int nvec, int vstride, int fftlen, float binsize,
-                     float sens, float *fhat, float *ckpt, int seg, cudaStream_t s);
+                     float sens, float *fhat, float *ckpt, int seg, float *phase_state, cudaStream_t s);
 // G2 parallel part + G3: mix with the NCO and apply feedforward_agc_cc.
 // stages: B200AIS_STAGE_* mask.  out rows have `out_stride` items; out[c*out_stride + t].
 int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int fftlen,
                    const float *fhat, int vstride, const float *ckpt, int seg, float sens, int stages,
                    int agc_nsamples, float agc_reference, float2 *out, size_t out_stride,
-                   cudaStream_t s);
+                   const float2 *hist_in, float2 *hist_out, cudaStream_t s);
 // A3: the correlation filter (GNU Radio's fft_filter_ccc: FFT overlap-add), |.|^2 > thresh
 // bitmask and the correlator stream.  in rows: in[c*in_stride + t], t in [0, n), n a multiple
 // of the block size fftsize - L + 1.  tw: fftsize/2 twiddles, hbr: fftsize transformed taps in
@@ -98,16 +105,27 @@ int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int
 int launch_detect(const float2 *corr, size_t corr_stride, int channels, int n_total, int chunk,
                   int nsamples_mult, int isps, unsigned mark_delay, const uint8_t *mask,
                   size_t mask_stride, uint64_t base_offset, int two_ports, b200ais_tag *tags,
-                  int max_tags, int *ntags, int *status, cudaStream_t s);
+                  int max_tags, int *ntags, int *status, int append, cudaStream_t s);
 // A7: the timing-loop recurrence, one lane per channel (symbols out).
+// unconsumed (nullable, stream mode): [channels] items in front of `in` that the last call left
+// unconsumed (read, then updated); the rows must hold them and one more item in front.
 int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
                const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
                float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
-               int require_unbounded, int *status, cudaStream_t s);
+               int require_unbounded, int *status, int *unconsumed, cudaStream_t s);
 // G4-G6 + A9: quadrature demod -> slicer -> diff decoder -> invert on the symbol stream.
 int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int channels, int max_sym,
-                uint8_t *bits, size_t bits_stride, float *soft, cudaStream_t s);
+                uint8_t *bits, size_t bits_stride, float *soft, TailCarry *carry, cudaStream_t s);
+// stream mode of the tag list: drop the tags the timing loop can no longer see (offset <
+// written - unconsumed[c]); nold[c] = tags kept.  k_detect then appends (append != 0).
+int launch_tags_compact(b200ais_tag *tags, int max_tags, int *ntags, const int *unconsumed,
+                        uint64_t written, int channels, int *nold, cudaStream_t s);
+// copy the tags appended since launch_tags_compact to the caller's rows
+int launch_tags_emit(const b200ais_tag *tags, int max_tags, const int *ntags, const int *nold,
+                     int channels, b200ais_tag *out_tags, int *out_ntags, int *status, cudaStream_t s);
+// move items [from, from+len) of every row to the front of the row (regions may overlap)
+int launch_roll_rows(float2 *rows, size_t stride, int channels, int from, int len, cudaStream_t s);
 int launch_msk_reset(MskState *state, int channels, float sps_half, cudaStream_t s);
 int launch_msk_set_omega(MskState *state, int channels, float omega, cudaStream_t s);
 int launch_invert(const uint8_t *in, uint8_t *out, size_t n, cudaStream_t s);

@@ -71,7 +71,8 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
       const int *__restrict__ ntags, MskParams p, MskState *__restrict__ state,
       const float *__restrict__ g_mmse, float2 *__restrict__ out, float *__restrict__ out_err,
       float *__restrict__ out_mu, size_t out_stride, int *__restrict__ nproduced,
-      int *__restrict__ nconsumed, int require_unbounded, int *__restrict__ status)
+      int *__restrict__ nconsumed, int require_unbounded, int *__restrict__ status,
+      int *__restrict__ unconsumed)
 {
     __shared__ __align__(16) float s_mmse[129 * 8];
     __shared__ __align__(16) float2 ring[32 * kMskPitch];
@@ -84,13 +85,27 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         return;
 
     MskState st = state[c];
-    int oidx = 0, iidx = 0;
-    const int ninp = (int)((double)ninput_items - 3.0 * (double)p.sps_half); // :119
-    if (ninp <= 0 || noutput_items <= 0) {
+    // Stream mode (unconsumed != nullptr): `in` points at the first NEW item of every row and
+    // the unc items the last call left unconsumed sit right in front of it, so this channel's
+    // read pointer is in - unc.  The row is then moved back by one more item where that makes
+    // it 16-byte aligned (the item in front of the read pointer is in[-1] of the stream).
+    const int unc = unconsumed ? unconsumed[c] : 0;
+    const float2 *row = in + (size_t)c * in_stride - unc;
+    const int mis = (unconsumed && (reinterpret_cast<uintptr_t>(row) & 15)) ? 1 : 0;
+    row -= mis;
+    const int navail = ninput_items + unc; // ninput_items[0] of this channel
+    ninput_items = navail + mis;
+    nitems_read -= (uint64_t)(unc + mis);
+    int oidx = 0, iidx = mis;
+    const int ninp0 = (int)((double)navail - 3.0 * (double)p.sps_half); // :119
+    if (ninp0 <= 0 || noutput_items <= 0) {
         nproduced[c] = 0;
         nconsumed[c] = 0;
+        if (unconsumed)
+            unconsumed[c] = navail;
         return;
     }
+    const int ninp = ninp0 + mis;
 
     // ring preset: slots before sample 0 are zero, in[-1] is the item carried from the last call
     float2 *my = ring + lane * kMskPitch;
@@ -98,7 +113,6 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         my[k] = make_float2(0.0f, 0.0f);
     my[kMskRing - 1] = make_float2(st.prev_re, st.prev_im);
     const unsigned my_s = (unsigned)__cvta_generic_to_shared(my);
-    const float2 *row = in + (size_t)c * in_stride;
     const bool row16 = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 
     // time_est tags inside [read, read+ninp), in offset order (:125-130)
@@ -282,7 +296,9 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     if (err_code)
         atomicMin(status, err_code);
     nproduced[c] = oidx;
-    nconsumed[c] = iidx;
+    nconsumed[c] = iidx - mis;
+    if (unconsumed)
+        unconsumed[c] = navail - (iidx - mis);
 }
 
 // G4-G6 + A9 on the symbol stream: quadrature_demod_cf(pi/2) -> binary_slicer_fb ->
@@ -291,7 +307,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
 __global__ void __launch_bounds__(128)
 k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict__ nsym,
        int channels, const float *__restrict__ g_atan, uint8_t *__restrict__ bits,
-       size_t bits_stride, float *__restrict__ soft_out)
+       size_t bits_stride, float *__restrict__ soft_out, const TailCarry *__restrict__ carry)
 {
     __shared__ float s_atan[257];
     for (int i = threadIdx.x; i < 257; i += blockDim.x)
@@ -305,10 +321,16 @@ k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict_
     const float2 *sc = sym + (size_t)c * sym_stride;
     const float qgain = 1.57079632679489661923f; // (float)(pi/2), python/ais_demod.py:48
     const float2 zero = make_float2(0.0f, 0.0f);
-    float2 prev = k0 >= 2 ? sc[k0 - 2] : zero;
-    float2 cur = k0 >= 1 ? sc[k0 - 1] : zero;
+    // symbols -2 and -1 and the last slicer decision come from the previous call of a stream
+    TailCarry tc;
+    tc.m2x = tc.m2y = tc.m1x = tc.m1y = 0.0f;
+    tc.bprev = 0;
+    if (carry && k0 < 2)
+        tc = carry[c];
+    float2 prev = k0 >= 2 ? sc[k0 - 2] : (k0 == 1 ? make_float2(tc.m1x, tc.m1y) : make_float2(tc.m2x, tc.m2y));
+    float2 cur = k0 >= 1 ? sc[k0 - 1] : make_float2(tc.m1x, tc.m1y);
     // slicer decision of symbol k0-1 (0 before the first symbol: diff_decoder history)
-    unsigned bprev = 0;
+    unsigned bprev = (unsigned)tc.bprev;
     if (k0 >= 1) {
         const float re = __fmaf_rn(cur.x, prev.x, cur.y * prev.y);
         const float im = __fmaf_rn(cur.y, prev.x, -(cur.x * prev.y));
@@ -337,6 +359,34 @@ k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict_
         for (int q = 0; q < kend; q++)
             ob[q] = (uint8_t)((pack >> (8 * q)) & 0xffu);
     }
+}
+
+// after k_tail of a stream call: remember the last two symbols and the last slicer decision
+__global__ void k_tail_carry(const float2 *__restrict__ sym, size_t sym_stride,
+                             const int *__restrict__ nsym, int channels,
+                             const float *__restrict__ atan_tab, TailCarry *__restrict__ carry)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels)
+        return;
+    const int n = nsym[c];
+    if (n <= 0)
+        return;
+    TailCarry tc = carry[c];
+    const float2 *sc = sym + (size_t)c * sym_stride;
+    if (n >= 2) {
+        tc.m2x = sc[n - 2].x;
+        tc.m2y = sc[n - 2].y;
+    } else {
+        tc.m2x = tc.m1x;
+        tc.m2y = tc.m1y;
+    }
+    tc.m1x = sc[n - 1].x;
+    tc.m1y = sc[n - 1].y;
+    const float re = __fmaf_rn(tc.m1x, tc.m2x, tc.m1y * tc.m2y);
+    const float im = __fmaf_rn(tc.m1y, tc.m2x, -(tc.m1x * tc.m2y));
+    tc.bprev = (1.57079632679489661923f * fast_atan2f_tab(im, re, atan_tab)) >= 0 ? 1 : 0;
+    carry[c] = tc;
 }
 
 __global__ void k_msk_reset(MskState *state, int channels, float sps_half)
@@ -393,7 +443,7 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
                const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
                float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
-               int require_unbounded, int *status, cudaStream_t s)
+               int require_unbounded, int *status, int *unconsumed, cudaStream_t s)
 {
     if (channels <= 0)
         return B200AIS_OK;
@@ -406,18 +456,18 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
         k_msk<true><<<blocks, 32, 0, s>>>(in, in_stride, channels, noutput_items, ninput_items,
                                           nitems_read, tags, max_tags, ntags, p, state, tb.mmse, out,
                                           out_err, out_mu, out_stride, nproduced, nconsumed,
-                                          require_unbounded, status);
+                                          require_unbounded, status, unconsumed);
     else
         k_msk<false><<<blocks, 32, 0, s>>>(in, in_stride, channels, noutput_items, ninput_items,
                                            nitems_read, tags, max_tags, ntags, p, state, tb.mmse, out,
                                            out_err, out_mu, out_stride, nproduced, nconsumed,
-                                           require_unbounded, status);
+                                           require_unbounded, status, unconsumed);
     B200_LAUNCH_CHECK("k_msk");
     return B200AIS_OK;
 }
 
 int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int channels, int max_sym,
-                uint8_t *bits, size_t bits_stride, float *soft, cudaStream_t s)
+                uint8_t *bits, size_t bits_stride, float *soft, TailCarry *carry, cudaStream_t s)
 {
     if (channels <= 0 || max_sym <= 0)
         return B200AIS_OK;
@@ -426,8 +476,14 @@ int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int chann
     if (rc)
         return rc;
     dim3 grid((max_sym + 4 * 128 - 1) / (4 * 128), channels);
-    k_tail<<<grid, 128, 0, s>>>(sym, sym_stride, nsym, channels, tb.atan, bits, bits_stride, soft);
+    k_tail<<<grid, 128, 0, s>>>(sym, sym_stride, nsym, channels, tb.atan, bits, bits_stride, soft,
+                                carry);
     B200_LAUNCH_CHECK("k_tail");
+    if (carry) {
+        k_tail_carry<<<(channels + 127) / 128, 128, 0, s>>>(sym, sym_stride, nsym, channels, tb.atan,
+                                                            carry);
+        B200_LAUNCH_CHECK("k_tail_carry");
+    }
     return B200AIS_OK;
 }
 

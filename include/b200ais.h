@@ -204,6 +204,35 @@ B200AIS_API int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int ns
 /* after a *_dev call has completed: 0 or the B200AIS_E_* a kernel flagged */
 B200AIS_API int b200ais_demod_status(b200ais_demod *h);
 
+/* The same chain fed as a stream: a capture arrives in pieces of any size (0..max_samples
+ * items per call, the same count on every channel) and every block keeps, from call to
+ * call, what it keeps between work() calls under the GNU Radio scheduler:
+ *   stream_to_vector's partial vector           python/gmsk_sync.py:23
+ *   frequency_modulator_fc's phase              python/gmsk_sync.py:27
+ *   feedforward_agc_cc's 511-item history       python/ais_demod.py:35
+ *   corr_est_cc's history, output multiple and
+ *     fft_filter tail                           lib/corr_est_cc_impl.cc:77-78,105-117,188
+ *   msk_timing_recovery_cc's loop state, its
+ *     unconsumed input and the tags in it       lib/msk_timing_recovery_cc_impl.cc:125-130,203
+ *   quadrature_demod_cf / diff_decoder_bb history   python/ais_demod.py:48-51
+ * One call is one scheduler pass: every block runs once over what is available to it.  bits /
+ * nbits / tags / ntags hold THIS call's output (tag offsets are absolute corr_est item
+ * offsets).  Needs the AGC stage with the reference's 512-sample window.  The first stream
+ * call after create / a batch call / stream_reset starts from freshly constructed blocks.
+ * max_bits per call: b200ais_demod_stream_max_bits(h, nsamples). */
+B200AIS_API int b200ais_demod_stream_reset(b200ais_demod *h, void *stream);
+B200AIS_API int b200ais_demod_stream_max_bits(const b200ais_demod *h, int nsamples);
+B200AIS_API int b200ais_demod_stream_work(b200ais_demod *h, const float *iq, int nsamples,
+                                          uint8_t *bits, int max_bits, int *nbits,
+                                          b200ais_tag *tags, int *ntags);
+B200AIS_API int b200ais_demod_stream_work_dev(b200ais_demod *h, const float *iq, int nsamples,
+                                              uint8_t *bits, int max_bits, int *nbits,
+                                              b200ais_tag *tags, int *ntags, void *stream);
+/* items waiting inside the stream (all nullable): input items short of an FFT vector, AGC
+ * outputs short of a corr_est output multiple, corr_est's nitems_written */
+B200AIS_API int b200ais_demod_stream_pending(const b200ais_demod *h, int *input_items,
+                                             int *agc_items, uint64_t *corr_written);
+
 /* Per-stage device timing of the *_dev chain (CUDA events around every launch, on the
  * caller's stream).  stage_ms: sums over the work_dev calls since profiling was enabled
  * or last read; index = B200AIS_STAGE_T_*.  Reading synchronises the recorded events. */

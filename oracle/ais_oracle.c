@@ -1008,3 +1008,179 @@ int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, c
     }
     return status;
 }
+
+/* ----------------------------------------------------- the chain as a stream */
+
+int ao_stream_init(ao_stream *s, const ao_chain_cfg *cfg, const float *symbols, int L)
+{
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    s->L = L;
+    if (ao_corr_est_init(&s->ce, symbols, L, cfg->sps, cfg->mark_delay, cfg->threshold))
+        return -1;
+    int rc = ao_msk_init(&s->mk, cfg->sps, cfg->gain, cfg->limit, cfg->osps);
+    if (rc)
+        return rc;
+    ao_freqest_init(&s->fe, cfg->sample_rate, cfg->data_rate, cfg->fftlen);
+    s->xcarry = (float *)calloc((size_t)cfg->fftlen * 2, sizeof(float));
+    s->agc_hist = (float *)calloc((size_t)(cfg->agc_nsamples > 1 ? cfg->agc_nsamples - 1 : 1) * 2, sizeof(float));
+    s->acarry = (float *)calloc((size_t)(L + s->ce.nsamples) * 2, sizeof(float)); /* L zeros of history */
+    s->ocarry = (float *)calloc(64 * 2, sizeof(float));
+    s->captags = 64;
+    s->tags = (ao_tag *)calloc((size_t)s->captags, sizeof(ao_tag));
+    return 0;
+}
+
+ao_stream *ao_stream_new(const ao_chain_cfg *cfg, const float *symbols, int L)
+{
+    ao_stream *s = (ao_stream *)malloc(sizeof(ao_stream));
+    if (s && ao_stream_init(s, cfg, symbols, L)) {
+        free(s);
+        s = 0;
+    }
+    return s;
+}
+
+void ao_stream_delete(ao_stream *s)
+{
+    if (s) {
+        ao_stream_free(s);
+        free(s);
+    }
+}
+
+void ao_stream_free(ao_stream *s)
+{
+    ao_corr_est_free(&s->ce);
+    free(s->xcarry);
+    free(s->agc_hist);
+    free(s->acarry);
+    free(s->ocarry);
+    free(s->tags);
+    memset(s, 0, sizeof(*s));
+}
+
+int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_bits, int *nbits,
+                   ao_tag *tags_out, int max_tags, int *ntags_out)
+{
+    const ao_chain_cfg *cfg = &s->cfg;
+    const int L = s->L, fftlen = cfg->fftlen, W = cfg->agc_nsamples, ns = s->ce.nsamples;
+    int rc = 0;
+    *nbits = 0;
+    *ntags_out = 0;
+    /* ---- freq sync on whole vectors; the rest of the input waits in xcarry ---- */
+    int navail = s->nxcarry + n;
+    float *xin = (float *)malloc(sizeof(float) * 2 * (size_t)(navail + 1));
+    memcpy(xin, s->xcarry, sizeof(float) * 2 * (size_t)s->nxcarry);
+    memcpy(xin + 2 * (size_t)s->nxcarry, x, sizeof(float) * 2 * (size_t)n);
+    int n1 = (cfg->stages & AO_STAGE_FREQSYNC) ? (navail / fftlen) * fftlen : navail;
+    float *mixed = (float *)malloc(sizeof(float) * 2 * (size_t)(n1 + 1));
+    if (cfg->stages & AO_STAGE_FREQSYNC) {
+        int nvec = n1 / fftlen;
+        float *sq = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
+        float *sp = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
+        float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen * (size_t)(nvec + 1));
+        float *fh = (float *)malloc(sizeof(float) * (size_t)(nvec + 1));
+        for (int b = 0; b < nvec; b++) {
+            ao_square(xin + 2 * (size_t)b * fftlen, sq, fftlen);
+            ao_fft_forward(sq, sp, fftlen);
+            ao_fft_shift(sp, spec + 2 * (size_t)b * fftlen, fftlen);
+        }
+        ao_freqest_work(&s->fe, spec, nvec, fh, 0); /* one work() call: maxpos starts at 0 */
+        float sens = (float)(-1.0 / ((double)cfg->sample_rate / (2 * M_PI)));
+        ao_nco_mix(&s->nco_phase, sens, fh, fftlen, xin, n1, mixed);
+        free(sq);
+        free(sp);
+        free(spec);
+        free(fh);
+    } else {
+        memcpy(mixed, xin, sizeof(float) * 2 * (size_t)n1);
+    }
+    s->nxcarry = navail - n1;
+    memcpy(s->xcarry, xin + 2 * (size_t)n1, sizeof(float) * 2 * (size_t)s->nxcarry);
+    free(xin);
+    /* ---- AGC over every mixed item, history carried ---- */
+    int hist = (cfg->stages & AO_STAGE_AGC) ? W - 1 : 0;
+    int nac_old = s->nacarry;
+    s->acarry = (float *)realloc(s->acarry, sizeof(float) * 2 * (size_t)(L + nac_old + n1 + 1));
+    float *agc_out = s->acarry + 2 * (size_t)(L + nac_old);
+    if (cfg->stages & AO_STAGE_AGC) {
+        float *buf = (float *)malloc(sizeof(float) * 2 * (size_t)(hist + n1 + 1));
+        memcpy(buf, s->agc_hist, sizeof(float) * 2 * (size_t)hist);
+        memcpy(buf + 2 * (size_t)hist, mixed, sizeof(float) * 2 * (size_t)n1);
+        ao_agc_work(buf, n1, W, cfg->agc_reference, agc_out);
+        memcpy(s->agc_hist, buf + 2 * (size_t)n1, sizeof(float) * 2 * (size_t)hist);
+        free(buf);
+    } else {
+        memcpy(agc_out, mixed, sizeof(float) * 2 * (size_t)n1);
+    }
+    free(mixed);
+    /* ---- corr_est in work chunks over whole output multiples ---- */
+    int avail = nac_old + n1;
+    int chunk = cfg->corr_chunk > 0 ? cfg->corr_chunk : ao_default_corr_chunk(L);
+    chunk = (chunk / ns) * ns;
+    if (chunk <= 0)
+        chunk = ns;
+    s->ocarry = (float *)realloc(s->ocarry, sizeof(float) * 2 * (size_t)(s->nocarry + avail + 64));
+    int done = 0, ntag_new = 0;
+    while (avail - done >= ns) {
+        int nn = avail - done;
+        nn = nn > chunk ? chunk : (nn / ns) * ns;
+        int nt = 0;
+        if (s->ntags + 8 * (nn / 5 + 2) > s->captags) {
+            s->captags = s->ntags + 8 * (nn / 5 + 2) + 64;
+            s->tags = (ao_tag *)realloc(s->tags, sizeof(ao_tag) * (size_t)s->captags);
+        }
+        ao_corr_est_work(&s->ce, nn, s->acarry + 2 * (size_t)done, s->written,
+                         s->ocarry + 2 * (size_t)s->nocarry, 0, 0, 0, s->tags + s->ntags,
+                         s->captags - s->ntags, &nt);
+        for (int k = 0; k < nt; k++) { /* this call's tags for the caller */
+            if (ntag_new < max_tags)
+                tags_out[ntag_new] = s->tags[s->ntags + k];
+            ntag_new++;
+        }
+        s->ntags += nt;
+        s->nocarry += nn;
+        s->written += (uint64_t)nn;
+        done += nn;
+    }
+    *ntags_out = ntag_new;
+    if (ntag_new > max_tags)
+        rc = -3;
+    /* keep L items of history + what corr_est has not taken */
+    memmove(s->acarry, s->acarry + 2 * (size_t)done, sizeof(float) * 2 * (size_t)(L + avail - done));
+    s->nacarry = avail - done;
+    /* ---- msk over everything corr_est has produced and msk has not consumed ---- */
+    int maxsym = max_bits;
+    float *sym = (float *)malloc(sizeof(float) * 2 * (size_t)(maxsym + 1));
+    float *soft = (float *)malloc(sizeof(float) * (size_t)(maxsym + 1));
+    uint8_t *b0 = (uint8_t *)malloc((size_t)maxsym + 1), *b1 = (uint8_t *)malloc((size_t)maxsym + 1);
+    int consumed = 0;
+    int k = ao_msk_general_work(&s->mk, maxsym, s->nocarry, s->ocarry, s->read, s->tags, s->ntags, sym,
+                                0, 0, &consumed);
+    if (k < 0) {
+        rc = -4;
+        k = 0;
+    } else if (k >= maxsym && consumed < (int)((double)s->nocarry - 3.0 * (double)s->mk.sps)) {
+        rc = -7; /* output row too small */
+    }
+    memmove(s->ocarry, s->ocarry + 2 * (size_t)consumed, sizeof(float) * 2 * (size_t)(s->nocarry - consumed));
+    s->nocarry -= consumed;
+    s->read += (uint64_t)consumed;
+    int keep = 0; /* drop the tags msk can no longer see */
+    for (int t = 0; t < s->ntags; t++)
+        if (s->tags[t].offset >= s->read)
+            s->tags[keep++] = s->tags[t];
+    s->ntags = keep;
+    /* ---- bit tail with carried history ---- */
+    ao_quad_demod(s->qprev, sym, k, (float)(M_PI / 2), soft);
+    ao_binary_slicer(soft, k, b0);
+    ao_diff_decoder(&s->dprev, b0, k, 2, b1);
+    ao_invert(b1, k, bits);
+    *nbits = k;
+    free(sym);
+    free(soft);
+    free(b0);
+    free(b1);
+    return rc;
+}

@@ -191,6 +191,40 @@ int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, c
                          int channels, int n, uint8_t *bits, int max_bits, int *nbits,
                          ao_tag *tags, int max_tags, int *ntags, int nthreads);
 
+/* ---- the same chain as a stream: blocks keep their state from call to call ----
+ * One call = one scheduler pass in which every block runs once, in flowgraph order, over all
+ * the items available to it: whole FFT vectors (the remainder waits), every mixed item through
+ * the AGC, whole corr_est output multiples in work chunks (the remainder waits), everything
+ * corr_est has produced so far through one msk general_work(), then the bit tail. */
+typedef struct ao_stream {
+    ao_chain_cfg cfg;
+    ao_corr_est ce;
+    ao_msk mk;
+    ao_freqest fe;
+    int L;
+    float nco_phase;
+    float *xcarry;   /* input items waiting for a whole FFT vector */
+    int nxcarry;
+    float *agc_hist; /* last agc_nsamples-1 mixed items */
+    float *acarry;   /* L history items + AGC outputs corr_est has not taken yet */
+    int nacarry;     /* items after the L history */
+    float *ocarry;   /* corr_est output-0 items msk has not consumed */
+    int nocarry;
+    ao_tag *tags;    /* tags msk may still need */
+    int ntags, captags;
+    uint64_t written; /* corr_est nitems_written */
+    uint64_t read;    /* msk nitems_read */
+    float qprev[2];
+    uint8_t dprev;
+} ao_stream;
+int ao_stream_init(ao_stream *s, const ao_chain_cfg *cfg, const float *symbols, int L);
+ao_stream *ao_stream_new(const ao_chain_cfg *cfg, const float *symbols, int L);
+void ao_stream_delete(ao_stream *s);
+void ao_stream_free(ao_stream *s);
+/* bits/tags of this call only; returns 0 or a negative status */
+int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_bits, int *nbits,
+                   ao_tag *tags_out, int max_tags, int *ntags_out);
+
 #ifdef __cplusplus
 }
 #endif

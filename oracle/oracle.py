@@ -440,6 +440,44 @@ def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096):
     return res
 
 
+class DemodStream:
+    """The chain as a stream (ao_stream): state carried from work() call to work() call."""
+
+    def __init__(self, symbols, cfg=None):
+        self.cfg = cfg or chain_cfg()
+        symbols = _c64(symbols)
+        L = lib()
+        L.ao_stream_new.restype = C.c_void_p
+        L.ao_stream_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ao_stream_delete.argtypes = [C.c_void_p]
+        L.ao_stream_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]
+        self._s = L.ao_stream_new(C.addressof(self.cfg), _fp(symbols), len(symbols))
+        if not self._s:
+            raise RuntimeError("ao_stream_new failed")
+
+    def __del__(self):
+        try:
+            if self._s:
+                lib().ao_stream_delete(self._s)
+                self._s = None
+        except Exception:
+            pass
+
+    def work(self, x, max_tags=4096):
+        """Returns (bits, tags) produced by this call."""
+        x = _c64(x)
+        mb = max_bits_for(len(x) + 2 * self.cfg.fftlen + 4096, self.cfg.sps, self.cfg.osps)
+        bits = np.zeros(mb, dtype=np.uint8)
+        tags = np.zeros(max_tags, dtype=TAG_DTYPE)
+        nb, nt = C.c_int(0), C.c_int(0)
+        rc = lib().ao_stream_work(self._s, _fp(x), len(x), _fp(bits), mb, C.byref(nb), _fp(tags), max_tags,
+                                  C.byref(nt))
+        if rc:
+            raise RuntimeError("ao_stream_work failed: %d" % rc)
+        return bits[:nb.value].copy(), tags[:nt.value].copy()
+
+
 def demod_chain_batch(x, symbols, cfg=None, max_tags=256, nthreads=0):
     """x: [C, n] complex64.  Returns bits [C, max_bits], nbits [C], tags [C, max_tags], ntags [C]."""
     cfg = cfg or chain_cfg()
