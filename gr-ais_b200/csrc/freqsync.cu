@@ -402,7 +402,7 @@ int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nve
     if (fftlen == 1024) {
         k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw);
     } else {
-        if (smem > 48 * 1024)
+        if (smem > 40 * 1024) // static shared memory counts towards the 48 KB default limit
             B200_CU(cudaFuncSetAttribute(k_sqfft_freqest, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
         k_sqfft_freqest<<<grid, kFftThreads, smem, s>>>(x, x_stride, vstride, fftlen, lg, tw, offset, raw);

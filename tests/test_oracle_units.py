@@ -362,3 +362,42 @@ def test_bit_tail(oracle):
     assert np.array_equal(dd, b ^ np.concatenate([[0], b[:-1]]).astype(np.uint8))
     assert np.array_equal(oracle.invert(dd), 1 - dd)        # lib/invert_impl.cc:63
     assert np.array_equal(oracle.invert(np.array([0, 1, 2, 3, 255], np.uint8)), [1, 0, 1, 0, 0])
+
+
+def test_stream_single_call_equals_batch_chain(oracle, templates):
+    """the stream restatement fed a whole record in one call is the batch chain"""
+    from gr_ais_b200 import synth
+    x, truth = synth.make_record(3, n=20000, nbursts=3, snr_db=25)
+    ref = oracle.demod_chain(x, templates[120])
+    s = oracle.DemodStream(templates[120])
+    bits, tags = s.work(x)
+    assert np.array_equal(bits, ref["bits"])
+    assert np.array_equal(tags, ref["tags"])
+
+
+def test_stream_pieces_carry_every_block_state(oracle, templates):
+    """cut a record on whole FFT vectors / corr_est multiples / work chunks (137 * 1024 items):
+    every block resumes exactly where it stopped, so only the timing loop's call boundary (the
+    3*sps/2 items it leaves unconsumed) can move a decision"""
+    from gr_ais_b200 import synth
+    n = 2 * 137 * 1024
+    x, truth = synth.make_record(1, n=n, nbursts=10, snr_db=25)
+    cfg = oracle.chain_cfg(corr_chunk=137 * 64)
+    whole, _ = oracle.DemodStream(templates[120], cfg).work(x)
+    s = oracle.DemodStream(templates[120], cfg)
+    parts = [s.work(x[:n // 2])[0], s.work(x[n // 2:])[0]]
+    cut = np.concatenate(parts)
+    assert abs(len(cut) - len(whole)) <= 1
+    k = min(len(cut), len(whole))
+    assert np.mean(cut[:k] == whole[:k]) > 0.99
+    # ragged pieces: nothing is lost or duplicated, every payload still comes out
+    s = oracle.DemodStream(templates[120])
+    rng = np.random.default_rng(2)
+    pos, out = 0, []
+    while pos < n:
+        m = int(min(n - pos, rng.integers(0, 9000)))
+        out.append(s.work(x[pos:pos + m])[0])
+        pos += m
+    ragged = np.concatenate(out)
+    assert abs(len(ragged) - n // 5) < 40
+    assert sum(synth.payloads_found(ragged, truth)) >= sum(synth.payloads_found(whole, truth)) - 1 >= 6
