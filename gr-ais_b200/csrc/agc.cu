@@ -176,6 +176,7 @@ constexpr int kFHalo = 512;
 constexpr int kFOut = kFSpan - kFHalo;
 constexpr int kFPad = kFSpan + kFSpan / 16; // 1-in-16 padding: a thread's 16 items hit 16 banks
 
+template <bool kHist> // kHist: stream mode, AGC history in / out
 __global__ void __launch_bounds__(256, 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
@@ -202,7 +203,7 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
             float2 v0 = make_float2(0.0f, 0.0f);
             if (n >= 0 && n < n1)
                 v0 = xc[n];
-            else if (n < 0 && n >= -(kFHalo - 1) && hist_in) // already mixed: the stream's AGC history
+            else if (kHist && n < 0 && n >= -(kFHalo - 1)) // already mixed: the stream's AGC history
                 v0 = hist_in[(size_t)c * (kFHalo - 1) + (kFHalo - 1 + n)];
             ys[li + (li >> 4)] = v0;
         }
@@ -238,7 +239,7 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
             }
         }
     }
-    if (hist_out) { // the last 511 mixed items become the next call's AGC history
+    if (kHist) { // the last 511 mixed items become the next call's AGC history
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const int n = n0 + k;
@@ -316,14 +317,26 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
     if ((stages & B200AIS_STAGE_AGC) && agc_nsamples == 512 && seg == 16 &&
         (!(stages & B200AIS_STAGE_FREQSYNC) || (fftlen % 16 == 0 && n1 % fftlen == 0))) {
         const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float));
-        B200_CU(cudaFuncSetAttribute(k_mix_agc512, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem512));
         dim3 grid512((n1 + kFOut - 1) / kFOut, channels);
-        k_mix_agc512<<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat, vstride,
-                                                   ckpt, sens, (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0,
-                                                   agc_reference,
-                                                   reinterpret_cast<const float2 *>(tb.sine), out,
-                                                   out_stride, hist_in, hist_out);
+        const int do_mix = (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0;
+        const float2 *sine = reinterpret_cast<const float2 *>(tb.sine);
+        if (hist_in || hist_out) {
+            if (!hist_in || !hist_out || hist_in == hist_out) {
+                set_error("mix_agc: stream mode needs distinct history buffers in and out");
+                return B200AIS_E_INVALID;
+            }
+            B200_CU(cudaFuncSetAttribute(k_mix_agc512<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem512));
+            k_mix_agc512<true><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,
+                                                             vstride, ckpt, sens, do_mix, agc_reference,
+                                                             sine, out, out_stride, hist_in, hist_out);
+        } else {
+            B200_CU(cudaFuncSetAttribute(k_mix_agc512<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem512));
+            k_mix_agc512<false><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,
+                                                              vstride, ckpt, sens, do_mix, agc_reference,
+                                                              sine, out, out_stride, nullptr, nullptr);
+        }
         B200_LAUNCH_CHECK("k_mix_agc512");
         return B200AIS_OK;
     }

@@ -38,13 +38,15 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
     return true;
 }
 
-constexpr int kMskChunk = 32;              // samples per prefetch chunk
-constexpr int kMskRing = 128;               // ring slots per channel (4 chunks)
-constexpr int kMskMirror = 8;               // slots 0..7 repeated after the ring: 8-sample reads never wrap
-constexpr int kMskPitch = kMskRing + kMskMirror + 2; // 138 float2: rows stay 16-byte aligned
-constexpr int kMskInner = 4;                // half-symbol steps per round of warp votes
-constexpr int kMskNeed = 5 * kMskInner + 10; // samples past iidx kMskInner steps may touch (advance <= 3, tag jump <= 2, 8 taps)
-constexpr int kMskAhead = 64;               // issue a chunk once the lane is this close to it
+constexpr int kMskChunk = 32;   // samples per prefetch chunk
+constexpr int kMskRing = 128;   // ring samples per channel (4 chunks)
+constexpr int kMskMirror = 8;   // samples 0..7 repeated after the ring: 10-sample reads never wrap
+constexpr int kMskUnits = (kMskRing + kMskMirror) / 2; // 16-byte units (2 samples) per lane
+constexpr int kMskInner = 4;    // half-symbol steps per careful round
+constexpr int kMskFast = 8;     // half-symbol steps per straight-line round
+constexpr int kMskNeed = 32;    // samples past iidx a round may touch
+constexpr int kMskAhead = 63;   // request the next chunk once fewer than this many samples are requested ahead
+constexpr int kMskTagCap = 32;  // time_est tags per channel staged in shared memory
 
 __device__ __forceinline__ void cp_async_8(unsigned smem, const void *gmem, int src_bytes)
 {
@@ -57,13 +59,95 @@ __device__ __forceinline__ void cp_async_16(unsigned smem, const void *gmem, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Loop registers of one channel (lib/msk_timing_recovery_cc_impl.h:37-46), in registers.
+struct MskLane {
+    float mu, omega;
+    float psq_re, psq_im;     // previous interpolant squared (conj(dly2^2) = conj of this)
+    float diff1_re, diff1_im;
+    float2 vlast;
+    int div, iidx, oidx;
+    float2 *op;               // next symbol slot
+    bool bad_imu;
+};
+
+// One half-symbol step from the row index imu (:170-201 without the tag test): interpolate,
+// error detector, loop filter on odd steps, output on even steps, advance.  ring4: this lane's
+// column of the 16-byte-unit ring.  Returns x = mu + omega before the floor.
+template <bool kDebug>
+__device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *__restrict__ ring4,
+                                          const float *__restrict__ s_mmse, const MskParams &p,
+                                          float *oe, float *om)
+{
+    // mmse_fir_interpolator_cc::interpolate: in[0..7] . reversed row.  The 8 samples start at
+    // ring sample iidx: five 16-byte units (conflict-free: the lane picks the banks), then the
+    // odd/even start is a select
+    const int k = L.iidx;
+    const int u0 = (k >> 1) & (kMskRing / 2 - 1);
+    const bool par = k & 1;
+    const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8);
+    const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8 + 4);
+    const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
+    const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
+    const float2 s0 = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
+    const float2 s1 = par ? make_float2(U1.x, U1.y) : make_float2(U0.z, U0.w);
+    const float2 s2 = par ? make_float2(U1.z, U1.w) : make_float2(U1.x, U1.y);
+    const float2 s3 = par ? make_float2(U2.x, U2.y) : make_float2(U1.z, U1.w);
+    const float2 s4 = par ? make_float2(U2.z, U2.w) : make_float2(U2.x, U2.y);
+    const float2 s5 = par ? make_float2(U3.x, U3.y) : make_float2(U2.z, U2.w);
+    const float2 s6 = par ? make_float2(U3.z, U3.w) : make_float2(U3.x, U3.y);
+    const float2 s7 = par ? make_float2(U4.x, U4.y) : make_float2(U3.z, U3.w);
+    // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
+    const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
+    const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
+    const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
+    const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
+    float2 v;
+    v.x = (p0r + p1r) + (p2r + p3r);
+    v.y = (p0i + p1i) + (p2i + p3i);
+    // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
+    const float vxy = v.x * v.y;
+    const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
+    const float d_re = L.psq_re, d_im = -L.psq_im;
+    const float nl_re = sq_re * d_re - sq_im * d_im;
+    const float nl_im = sq_re * d_im + sq_im * d_re;
+    const float err_raw = nl_re - L.diff1_re;
+    // odd half-steps run the loop filter (:179-184); evaluated always, selected by parity
+    const bool odd = L.div & 1;
+    const float err_c = branchless_clip(err_raw, 3.0f);
+    const float om_t = L.omega + p.gain_omega * err_c;
+    const float om_n = p.sps_half + branchless_clip(om_t - p.sps_half, p.limit);
+    const float mu_n = L.mu + p.gain * err_c;
+    L.omega = odd ? om_n : L.omega;
+    L.mu = odd ? mu_n : L.mu;
+    if (!odd || p.osps == 2) {
+        *L.op = v;
+        L.op++;
+        if (kDebug) {
+            if (oe)
+                oe[L.oidx] = odd ? err_c : err_raw;
+            if (om)
+                om[L.oidx] = L.mu;
+        }
+        L.oidx++;
+    }
+    L.div++;
+    L.vlast = v;
+    L.psq_re = sq_re;
+    L.psq_im = sq_im;
+    L.diff1_re = nl_re;
+    L.diff1_im = nl_im;
+    return L.mu + L.omega;
+}
+
 // The serial core of msk_timing_recovery_cc: one lane per channel.  A channel's loop is a
 // recurrence on (mu, omega, iidx, div, previous interpolant), so the kernel's run time is
 // (#half-symbols) x (latency of one step) however many channels run: the step is kept as
 // short as possible and everything off the recurrence (the bit tail) lives in k_tail.
 // Each lane streams its own channel through a private shared-memory ring (4 chunks of 32
-// samples) with cp.async, issuing a 256-byte chunk kMskAhead samples before it is needed,
-// so no step waits on HBM.
+// samples, stored as 16-byte units interleaved across lanes so that a lane's reads never
+// meet another lane's banks) with cp.async, requesting a 256-byte chunk ~60 samples before it
+// is needed, so no step waits on HBM.  The lane's time_est tags are staged in shared memory
+// by a prologue (a tag fetched from HBM on the loop's critical path costs a DRAM round trip).
 template <bool kDebug>
 __global__ void __launch_bounds__(32)
 k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput_items,
@@ -75,7 +159,8 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
       int *__restrict__ unconsumed)
 {
     __shared__ __align__(16) float s_mmse[129 * 8];
-    __shared__ __align__(16) float2 ring[32 * kMskPitch];
+    __shared__ __align__(16) float4 ring[kMskUnits * 32];
+    __shared__ int2 s_tags[kMskTagCap * 32];
     const int lane = threadIdx.x;
     for (int i = lane; i < 129 * 8; i += 32)
         s_mmse[i] = g_mmse[i];
@@ -96,7 +181,6 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     const int navail = ninput_items + unc; // ninput_items[0] of this channel
     ninput_items = navail + mis;
     nitems_read -= (uint64_t)(unc + mis);
-    int oidx = 0, iidx = mis;
     const int ninp0 = (int)((double)navail - 3.0 * (double)p.sps_half); // :119
     if (ninp0 <= 0 || noutput_items <= 0) {
         nproduced[c] = 0;
@@ -107,27 +191,51 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     }
     const int ninp = ninp0 + mis;
 
-    // ring preset: slots before sample 0 are zero, in[-1] is the item carried from the last call
-    float2 *my = ring + lane * kMskPitch;
-    for (int k = 0; k < kMskRing + kMskMirror; k++)
-        my[k] = make_float2(0.0f, 0.0f);
-    my[kMskRing - 1] = make_float2(st.prev_re, st.prev_im);
-    const unsigned my_s = (unsigned)__cvta_generic_to_shared(my);
+    // ring preset: samples before 0 are zero, in[-1] is the item carried from the last call
+    float4 *ring4 = ring + lane;
+    for (int u = 0; u < kMskUnits; u++)
+        ring4[u * 32] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    ring4[(kMskRing / 2 - 1) * 32] = make_float4(0.0f, 0.0f, st.prev_re, st.prev_im);
+    const unsigned my_s = (unsigned)__cvta_generic_to_shared(ring4);
     const bool row16 = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 
-    // time_est tags inside [read, read+ninp), in offset order (:125-130)
+    // time_est tags inside [read, read+ninp), in offset order (:125-130): staged in shared
+    // memory; a channel with more than kMskTagCap of them reads them from HBM as it goes
     const b200ais_tag *tg = tags ? tags + (size_t)c * max_tags : nullptr;
     const int nt = (tags && ntags) ? min(ntags[c], max_tags) : 0;
-    int thead = 0;
+    auto matches = [&](const b200ais_tag &t) {
+        return t.key == B200AIS_TAG_TIME_EST && t.port == 0 && t.offset >= nitems_read &&
+               t.offset < nitems_read + (uint64_t)ninp;
+    };
+    int nstaged = 0;
+#pragma unroll 4
+    for (int k = 0; k < nt; k++) {
+        const b200ais_tag t = tg[k];
+        if (matches(t)) {
+            if (nstaged < kMskTagCap)
+                s_tags[nstaged * 32 + lane] =
+                    make_int2((int)(t.offset - nitems_read), __float_as_int((float)t.value));
+            nstaged++;
+        }
+    }
+    const bool tags_global = nstaged > kMskTagCap;
+    int thead = 0;            // next entry of the staged list, or index into tg[] (tags_global)
     int tag_off = 0x7fffffff; // pending tag, relative to the read pointer
     float tag_val = 0.0f;
-    auto fetch_tag = [&](int from) {
-        int k = from;
+    auto fetch_tag = [&]() { // the first tag at or after thead
         tag_off = 0x7fffffff;
+        if (!tags_global) {
+            if (thead < nstaged) {
+                const int2 e = s_tags[thead * 32 + lane];
+                tag_off = e.x;
+                tag_val = __int_as_float(e.y);
+            }
+            return;
+        }
+        int k = thead;
         while (k < nt) {
             const b200ais_tag t = tg[k];
-            if (t.key == B200AIS_TAG_TIME_EST && t.port == 0 && t.offset >= nitems_read &&
-                t.offset < nitems_read + (uint64_t)ninp) {
+            if (matches(t)) {
                 tag_off = (int)(t.offset - nitems_read);
                 tag_val = (float)t.value;
                 break;
@@ -136,7 +244,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         }
         thead = k;
     };
-    fetch_tag(0);
+    fetch_tag();
     const int tag_span = (int)ceilf(p.sps_half) + 1; // integer pre-test before the float compare
 
     float2 *oc = out + (size_t)c * out_stride;
@@ -145,160 +253,162 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
 
     // conj(dly2^2) of the reference equals conj(previous v^2): d_dly_conj_1 and _2 are always
     // assigned together (:194-195), so only the squared previous interpolant is carried.
-    float psq_re = st.dly2_re * st.dly2_re - st.dly2_im * st.dly2_im;
-    float psq_im = st.dly2_re * st.dly2_im + st.dly2_im * st.dly2_re;
-    float2 vlast = make_float2(st.dly1_re, st.dly1_im);
-    float mu = st.mu, omega = st.omega, diff1_re = st.diff1_re, diff1_im = st.diff1_im;
-    int div = st.div;
+    MskLane L;
+    L.psq_re = st.dly2_re * st.dly2_re - st.dly2_im * st.dly2_im;
+    L.psq_im = st.dly2_re * st.dly2_im + st.dly2_im * st.dly2_re;
+    L.vlast = make_float2(st.dly1_re, st.dly1_im);
+    L.mu = st.mu;
+    L.omega = st.omega;
+    L.diff1_re = st.diff1_re;
+    L.diff1_im = st.diff1_im;
+    L.div = st.div;
+    L.iidx = mis;
+    L.oidx = 0;
+    L.op = oc;
+    L.bad_imu = false;
 
     int issue_end = 0; // samples [0, issue_end) of this lane's channel have been requested
     int ready_end = 0; // samples [0, ready_end) are known to have landed
     int err_code = 0;
-    bool bad_imu = false;
     bool active = true;
-    float2 *op = oc; // next symbol slot
     const unsigned FULL = __activemask(); // the lanes that own a channel (a prefix of the warp)
 
-    // cp.async groups are tracked per warp, not per lane, so issuing and waiting happen in
-    // warp-wide rounds: when any lane gets within kMskAhead samples of the end of what it
-    // has requested, every lane that has room in its ring requests its next chunk, and the
-    // (rare) wait is a wait for rounds issued ~20 steps earlier.
-    while (__any_sync(FULL, active)) {
-        const bool want = active && (iidx + kMskAhead >= issue_end);
-        if (__any_sync(FULL, want)) {
-            // room: the chunk being replaced (4 back) must be behind this lane's read position
-            if (active && (iidx + kMskRing - kMskChunk - 1 >= issue_end)) {
-                const int slot = issue_end & (kMskRing - 1);
+    // One step advances the read index by floor(mu + omega) <= advmax items.  The straight-line
+    // round needs kMskFast steps' worth of samples inside what a round may touch.
+    const int advmax = (int)floorf(1.0f + 3.0f * p.gain + p.sps_half + fabsf(p.limit) + 1e-3f);
+    const int fast_in = kMskFast * advmax;
+    const bool fast_ok = advmax >= 1 && fast_in + 8 <= kMskNeed && 3.0f * p.gain < 0.5f;
+
+    // cp.async groups are tracked per warp, not per lane, so requests and waits happen in
+    // warp-wide rounds, decided by one warp-wide OR per round: a round first waits (only for
+    // chunks requested in EARLIER rounds, microseconds ago), then requests the next chunk for
+    // every lane that is within kMskAhead samples of the end of what it has requested, then
+    // runs its steps.
+    //
+    // When no lane can meet a tag, the end of its input or the end of its output row within
+    // kMskFast steps, the steps run as one straight-line block: no per-step tests, and the
+    // interpolator row of the next step comes from rint(128 x) - 128 floor(x), x = mu + omega
+    // -- equal to rint(128 (x - floor(x))) because x - floor(x) is exact and 128 floor(x) is an
+    // even integer -- so that conversion runs beside the floor instead of after it.
+    for (;;) {
+        const bool need = active && (L.iidx + kMskNeed > ready_end);
+        const bool want = active && (issue_end <= L.iidx + kMskAhead);
+        const bool easy = fast_ok && (L.iidx + fast_in < ninp) && (L.oidx + kMskFast <= noutput_items) &&
+                          ((unsigned)(tag_off - L.iidx) >= (unsigned)(fast_in + tag_span));
+        const unsigned code = (active ? 1u : 0u) | (need ? 2u : 0u) | (want ? 4u : 0u) |
+                              ((active && easy) ? 0u : 8u);
+        const unsigned any = __reduce_or_sync(FULL, code);
+        if (!(any & 1u))
+            break;
+        bool starved = false;
+        if (any & 2u) {
+            cp_async_wait_all();
+            ready_end = issue_end;
+            starved = __any_sync(FULL, active && (L.iidx + kMskNeed > ready_end));
+        }
+        if (any & 4u) {
+            // (want implies room: the chunk being replaced ends at issue_end - 96 <= iidx - 33)
+            if (want) {
+                const unsigned dst = my_s + ((issue_end >> 1) & (kMskRing / 2 - 1)) * 512;
                 const float2 *src = row + issue_end;
-                const unsigned dst = my_s + slot * 8;
+                const bool first = (issue_end & (kMskRing - 1)) == 0; // also feeds the mirror units
                 if (row16 && issue_end + kMskChunk <= ninput_items) {
 #pragma unroll
-                    for (int k = 0; k < kMskChunk / 2; k++)
-                        cp_async_16(dst + 16 * k, src + 2 * k, 16);
-                    if (slot == 0) {
+                    for (int u = 0; u < kMskChunk / 2; u++)
+                        cp_async_16(dst + 512 * u, src + 2 * u, 16);
+                    if (first) {
 #pragma unroll
-                        for (int k = 0; k < kMskMirror / 2; k++)
-                            cp_async_16(dst + kMskRing * 8 + 16 * k, src + 2 * k, 16);
+                        for (int u = 0; u < kMskMirror / 2; u++)
+                            cp_async_16(my_s + (kMskRing / 2 + u) * 512, src + 2 * u, 16);
                     }
                 } else {
                     for (int k = 0; k < kMskChunk; k++) {
                         const int nb = issue_end + k < ninput_items ? 8 : 0;
-                        cp_async_8(dst + 8 * k, nb ? src + k : row, nb);
-                        if (slot == 0 && k < kMskMirror)
-                            cp_async_8(dst + kMskRing * 8 + 8 * k, nb ? src + k : row, nb);
+                        const unsigned d = dst + 512 * (k >> 1) + 8 * (k & 1);
+                        cp_async_8(d, nb ? src + k : row, nb);
+                        if (first && k < kMskMirror)
+                            cp_async_8(my_s + (kMskRing / 2 + (k >> 1)) * 512 + 8 * (k & 1), nb ? src + k : row, nb);
                     }
                 }
                 issue_end += kMskChunk;
             }
             cp_async_commit();
-            continue; // (at start-up several chunks are requested back to back)
         }
-        if (__any_sync(FULL, active && (iidx + kMskNeed > ready_end))) {
-            cp_async_wait_all();
-            ready_end = issue_end;
+        if (starved)
+            continue; // start-up only: go around and wait for what was just requested
+        if (!(any & 8u)) {
+            // ---- straight-line round: every lane runs kMskFast steps ----
+            int imu = __float2int_rn(L.mu * 128.0f);
+#pragma unroll
+            for (int it = 0; it < kMskFast; it++) {
+                const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
+                L.bad_imu |= (imu_c != (unsigned)imu);
+                const float x = msk_step<kDebug>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
+                const int fl_i = __float2int_rd(x);
+                imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
+                L.iidx += fl_i;
+                L.mu = x - floorf(x);
+            }
+            active = (L.oidx < noutput_items) && (L.iidx < ninp);
+            continue;
         }
-        // kMskInner half-symbol steps between two rounds of votes; the steps are written
-        // without data-dependent branches (a lone warp pays ~20 cycles per taken branch)
+        // ---- careful round: kMskInner steps with every test ----
 #pragma unroll
         for (int it = 0; it < kMskInner; it++) {
             if (active) {
                 // tag reset (:139-164); rare: an integer window test guards the float compare
-                if (((unsigned)tag_off - (unsigned)iidx) < (unsigned)tag_span) {
-                    if ((float)tag_off < ((float)iidx + p.sps_half)) {
+                if (((unsigned)tag_off - (unsigned)L.iidx) < (unsigned)tag_span) {
+                    if ((float)tag_off < ((float)L.iidx + p.sps_half)) {
                         if (tag_val == tag_val) { // NaN: drop the tag, no reset (:144-147)
-                            mu = tag_val;
-                            iidx = tag_off;
-                            if (mu < 0) {
-                                mu = mu + 1.0f;
-                                iidx--;
+                            L.mu = tag_val;
+                            L.iidx = tag_off;
+                            if (L.mu < 0) {
+                                L.mu = L.mu + 1.0f;
+                                L.iidx--;
                             }
-                            div = 0;
-                            omega = p.sps_half;
+                            L.div = 0;
+                            L.omega = p.sps_half;
                         }
-                        fetch_tag(thead + 1);
+                        thead++;
+                        fetch_tag();
                     }
                 }
-                // mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), in[0..7] . reversed row
-                const int imu = __float2int_rn(mu * 128.0f);
+                // imu = rint(mu*128); the reference's interpolator throws outside [0, 128]
+                const int imu = __float2int_rn(L.mu * 128.0f);
                 const int imu_c = min(max(imu, 0), 128);
-                bad_imu |= (imu != imu_c); // the reference's interpolator throws here
-                const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8);
-                const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8 + 4);
-                const float2 *sp = my + (iidx & (kMskRing - 1));
-                const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
-                const float2 s4 = sp[4], s5 = sp[5], s6 = sp[6], s7 = sp[7];
-                // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
-                const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
-                const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
-                const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
-                const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
-                float2 v;
-                v.x = (p0r + p1r) + (p2r + p3r);
-                v.y = (p0i + p1i) + (p2i + p3i);
-                // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
-                const float vxy = v.x * v.y;
-                const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
-                const float d_re = psq_re, d_im = -psq_im;
-                const float nl_re = sq_re * d_re - sq_im * d_im;
-                const float nl_im = sq_re * d_im + sq_im * d_re;
-                const float err_raw = nl_re - diff1_re;
-                // odd half-steps run the loop filter (:179-184); evaluated always, selected by parity
-                const bool odd = div & 1;
-                const float err_c = branchless_clip(err_raw, 3.0f);
-                const float om_t = omega + p.gain_omega * err_c;
-                const float om_n = p.sps_half + branchless_clip(om_t - p.sps_half, p.limit);
-                const float mu_n = mu + p.gain * err_c;
-                omega = odd ? om_n : omega;
-                mu = odd ? mu_n : mu;
-                if (!odd || p.osps == 2) {
-                    *op = v;
-                    op++;
-                    if (kDebug) {
-                        if (oe)
-                            oe[oidx] = odd ? err_c : err_raw;
-                        if (om)
-                            om[oidx] = mu;
-                    }
-                    oidx++;
-                }
-                div++;
-                vlast = v;
-                psq_re = sq_re;
-                psq_im = sq_im;
-                diff1_re = nl_re;
-                diff1_im = nl_im;
-                mu = mu + omega;
-                const float fl = floorf(mu);
-                iidx += (int)fl;
-                mu = mu - fl;
-                active = (oidx < noutput_items) && (iidx < ninp);
+                L.bad_imu |= (imu != imu_c);
+                const float x = msk_step<kDebug>(L, imu_c, ring4, s_mmse, p, oe, om);
+                const float fl = floorf(x);
+                L.iidx += (int)fl;
+                L.mu = x - fl;
+                active = (L.oidx < noutput_items) && (L.iidx < ninp);
             }
         }
     }
-    if (bad_imu)
+    if (L.bad_imu)
         err_code = B200AIS_E_INTERP;
     cp_async_wait_all();
-    st.mu = mu;
-    st.omega = omega;
-    st.div = div;
-    st.diff1_re = diff1_re;
-    st.diff1_im = diff1_im;
-    st.dly1_re = st.dly2_re = vlast.x;
-    st.dly1_im = st.dly2_im = vlast.y;
-    if (iidx > 0) {
-        const float2 pv = row[iidx - 1];
+    st.mu = L.mu;
+    st.omega = L.omega;
+    st.div = L.div;
+    st.diff1_re = L.diff1_re;
+    st.diff1_im = L.diff1_im;
+    st.dly1_re = st.dly2_re = L.vlast.x;
+    st.dly1_im = st.dly2_im = L.vlast.y;
+    if (L.iidx > 0) {
+        const float2 pv = row[L.iidx - 1];
         st.prev_re = pv.x;
         st.prev_im = pv.y;
     }
     state[c] = st;
-    if (!err_code && require_unbounded && oidx >= noutput_items && iidx < ninp)
+    if (!err_code && require_unbounded && L.oidx >= noutput_items && L.iidx < ninp)
         err_code = B200AIS_E_OUT_OVERFLOW;
     if (err_code)
         atomicMin(status, err_code);
-    nproduced[c] = oidx;
-    nconsumed[c] = iidx - mis;
+    nproduced[c] = L.oidx;
+    nconsumed[c] = L.iidx - mis;
     if (unconsumed)
-        unconsumed[c] = navail - (iidx - mis);
+        unconsumed[c] = navail - (L.iidx - mis);
 }
 
 // G4-G6 + A9 on the symbol stream: quadrature_demod_cf(pi/2) -> binary_slicer_fb ->
