@@ -33,10 +33,19 @@ template <int LOGF> struct Plan {
     static constexpr int GROUPS = THREADS / NT;             // transforms in flight per CTA
     static constexpr int NPASS = (LOGF + 3) / 4;
     static constexpr int REM = LOGF % 4;                    // width of the lowest pass (0 = full)
+    // Twiddles of the passes above the lowest one, re-ordered per stage so that the threads of a
+    // transform read consecutive entries (the plain table is read with strides of 2, 4, 8 ...
+    // entries there: 2- to 8-way bank conflicts).  Pass over bits [S0, S0+4): stage bq uses
+    // W[((jq << S0) | lo) << (LOGF - S0 - bq - 1)], jq < 2^bq, lo < 2^S0; stored at
+    // ((2^bq - 1 + jq) << S0) + lo, 15 << S0 entries per pass.
+    static constexpr int TOP = LOGF - 4;
+    static constexpr int TWP_TOP = (LOGF > 4) ? (15 << TOP) : 0;
+    static constexpr int TWP_MID = (NPASS >= 3) ? (15 << (TOP - 4)) : 0;
+    static constexpr int TWP = TWP_TOP + TWP_MID;
 };
 
 // element index of slot (g, q) of thread t for a pass over index bits [S0, S0+R)
-template <int S0, int R> __device__ __forceinline__ int elem(int t, int g, int q)
+template <int S0, int R> __host__ __device__ constexpr __forceinline__ int elem(int t, int g, int q)
 {
     const int u = t * (16 >> R) + g;
     const int lo = u & ((1 << S0) - 1), hi = u >> S0;
@@ -45,7 +54,8 @@ template <int S0, int R> __device__ __forceinline__ int elem(int t, int g, int q
 
 // one pass: R radix-2 stages on index bits [S0, S0+R), forward DIF or inverse DIT
 template <int LOGF, int S0, int R, bool INV>
-__device__ __forceinline__ void run_pass(float2 (&v)[16], int t, const float2 *__restrict__ tw)
+__device__ __forceinline__ void run_pass(float2 (&v)[16], int t, const float2 *__restrict__ tw,
+                                         const float2 *__restrict__ twp)
 {
     constexpr int G = 16 >> R, Q = 1 << R, F = 1 << LOGF;
 #pragma unroll
@@ -76,7 +86,11 @@ __device__ __forceinline__ void run_pass(float2 (&v)[16], int t, const float2 *_
                         b = make_float2(dy, -dx);
                     }
                 } else {
-                    float2 w = tw[(jq | lo) << (LOGF - beta - 1)];
+                    float2 w;
+                    if constexpr (S0 > 0) // same table entry, conflict-free position
+                        w = twp[((((1 << bq) - 1) + (q & ((1 << bq) - 1))) << S0) + lo];
+                    else
+                        w = tw[(jq | lo) << (LOGF - beta - 1)];
                     if (INV) {
                         w.y = -w.y;
                         const float2 tt = cmul_fma(w, b0);
@@ -111,10 +125,12 @@ __device__ __forceinline__ void from_smem(float2 (&v)[16], int t, const float2 *
 // the top-pass mapping (element t + NT*q in slot q)
 template <int LOGF>
 __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float2 *__restrict__ tw,
-                                             const float2 *__restrict__ hbr, float2 *xb)
+                                             const float2 *__restrict__ twp,
+                                             const float4 *__restrict__ h4, float2 *xb)
 {
-    constexpr int NP = Plan<LOGF>::NPASS, REM = Plan<LOGF>::REM;
+    constexpr int NP = Plan<LOGF>::NPASS, REM = Plan<LOGF>::REM, NT = Plan<LOGF>::NT;
     constexpr int TOP = LOGF - 4;
+    const float2 *twp_mid = twp + Plan<LOGF>::TWP_TOP;
     // the exchange buffer belongs to one transform: only its own threads have to meet
     auto xsync = [&]() {
         if constexpr (Plan<LOGF>::NT <= 32)
@@ -126,7 +142,7 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
                          "r"(Plan<LOGF>::NT));
     };
     // ---- forward, top bits first ----
-    run_pass<LOGF, TOP, 4, false>(v, t, tw);
+    run_pass<LOGF, TOP, 4, false>(v, t, tw, twp);
     if constexpr (NP >= 2) {
         to_smem<TOP, 4>(v, t, xb);
         xsync();
@@ -134,25 +150,31 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
         constexpr int R1 = (NP == 2 && REM) ? REM : 4;
         from_smem<S1, R1>(v, t, xb);
         xsync();
-        run_pass<LOGF, S1, R1, false>(v, t, tw);
+        run_pass<LOGF, S1, R1, false>(v, t, tw, twp_mid);
         if constexpr (NP >= 3) {
             to_smem<S1, R1>(v, t, xb);
             xsync();
             constexpr int R2 = REM ? REM : 4;
             from_smem<0, R2>(v, t, xb);
             xsync();
-            run_pass<LOGF, 0, R2, false>(v, t, tw);
+            run_pass<LOGF, 0, R2, false>(v, t, tw, nullptr);
         }
     }
     // ---- pointwise product with the (bit-reversed) transformed taps: volk multiply(X, H) ----
     {
         constexpr int SL = 0;
         constexpr int RL = (NP == 1) ? 4 : (REM ? REM : 4);
+        // slot s of thread t holds spectrum element 16 t + s in every lowest-pass mapping; the
+        // taps are staged as float4 {H[16t+2k], H[16t+2k+1]} at [k][t]: conflict-free 16-byte reads
+        static_assert(elem<SL, RL>(3, 5 >> RL, 5 & ((1 << RL) - 1)) == 16 * 3 + 5, "slot order");
 #pragma unroll
-        for (int s = 0; s < 16; s++)
-            v[s] = cmul_fma(v[s], hbr[elem<SL, RL>(t, s >> RL, s & ((1 << RL) - 1))]);
+        for (int k = 0; k < 8; k++) {
+            const float4 hh = h4[k * NT + t];
+            v[2 * k] = cmul_fma(v[2 * k], make_float2(hh.x, hh.y));
+            v[2 * k + 1] = cmul_fma(v[2 * k + 1], make_float2(hh.z, hh.w));
+        }
         // ---- inverse, low bits first ----
-        run_pass<LOGF, SL, RL, true>(v, t, tw);
+        run_pass<LOGF, SL, RL, true>(v, t, tw, nullptr);
     }
     if constexpr (NP >= 3) {
         constexpr int R2 = REM ? REM : 4;
@@ -161,19 +183,19 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
         xsync();
         from_smem<S1, 4>(v, t, xb);
         xsync();
-        run_pass<LOGF, S1, 4, true>(v, t, tw);
+        run_pass<LOGF, S1, 4, true>(v, t, tw, twp_mid);
         to_smem<S1, 4>(v, t, xb);
         xsync();
         from_smem<TOP, 4>(v, t, xb);
         xsync();
-        run_pass<LOGF, TOP, 4, true>(v, t, tw);
+        run_pass<LOGF, TOP, 4, true>(v, t, tw, twp);
     } else if constexpr (NP == 2) {
         constexpr int R1 = REM ? REM : 4;
         to_smem<0, R1>(v, t, xb);
         xsync();
         from_smem<TOP, 4>(v, t, xb);
         xsync();
-        run_pass<LOGF, TOP, 4, true>(v, t, tw);
+        run_pass<LOGF, TOP, 4, true>(v, t, tw, twp);
     }
 }
 
@@ -189,8 +211,9 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
     constexpr int F = P::F, NT = P::NT, GROUPS = P::GROUPS;
     extern __shared__ float4 smem_raw[];
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);     // [F/2]
-    float2 *s_h = s_tw + F / 2;                              // [F]
-    float2 *s_x = s_h + F;                                   // [GROUPS][F + F/16]
+    float2 *s_h = s_tw + F / 2;                              // [F] as float4 pairs [8][NT]
+    float2 *s_twp = s_h + F;                                 // [TWP] per-stage twiddles of the upper passes
+    float2 *s_x = s_twp + P::TWP;                            // [GROUPS][F + F/16]
     float2 *s_tail = s_x + GROUPS * (F + F / 16);            // [3][GROUPS][L-1], round r uses r % 3
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_tail + 3 * GROUPS * (L > 1 ? L - 1 : 1));
 
@@ -201,8 +224,18 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
     const int nwords = (nb_per_cta * ns) >> 5;
     for (int i = threadIdx.x; i < F / 2; i += blockDim.x)
         s_tw[i] = tw[i];
-    for (int i = threadIdx.x; i < F; i += blockDim.x)
-        s_h[i] = hbr[i];
+    for (int i = threadIdx.x; i < F; i += blockDim.x) { // H[16 t + s] -> pair k = s/2 of thread t
+        const int tt = i >> 4, sl = i & 15;
+        s_h[(((sl >> 1) * NT + tt) << 1) | (sl & 1)] = hbr[i];
+    }
+    for (int i = threadIdx.x; i < P::TWP; i += blockDim.x) {
+        const bool mid = i >= P::TWP_TOP;
+        const int j = mid ? i - P::TWP_TOP : i;
+        const int s0 = mid ? P::TOP - 4 : P::TOP;
+        const int k1 = (j >> s0) + 1, lo = j & ((1 << s0) - 1); // k1 = 2^bq + jq, 1..15
+        const int bq = 31 - __clz(k1), jq = k1 - (1 << bq);
+        s_twp[i] = tw[((jq << s0) | lo) << (LOGF - s0 - bq - 1)];
+    }
     for (int i = threadIdx.x; i < nwords; i += blockDim.x)
         s_mask[i] = 0u;
     __syncthreads();
@@ -221,7 +254,7 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
             const int e = t + NT * q;
             v[q] = (valid && e < ns) ? xc[(size_t)b * ns + e] : make_float2(0.0f, 0.0f);
         }
-        block_filter<LOGF>(v, t, s_tw, s_h, xb);
+        block_filter<LOGF>(v, t, s_tw, s_twp, reinterpret_cast<const float4 *>(s_h), xb);
         // stash this block's tail (outputs ns .. F-1) for the next block
         float2 *my_tail = s_tail + ((r % 3) * GROUPS + g) * tl;
 #pragma unroll
@@ -286,7 +319,7 @@ int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, in
 {
     using P = Plan<LOGF>;
     const int ns = P::F - L + 1;
-    size_t smem = sizeof(float2) * (size_t)(P::F / 2 + P::F + P::GROUPS * (P::F + P::F / 16) +
+    size_t smem = sizeof(float2) * (size_t)(P::F / 2 + P::F + P::TWP + P::GROUPS * (P::F + P::F / 16) +
                                             3 * P::GROUPS * (L > 1 ? L - 1 : 1)) +
                   sizeof(uint32_t) * (size_t)((nb * ns) >> 5) + 16;
     if (smem > 200 * 1024) {
