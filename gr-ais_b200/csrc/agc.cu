@@ -197,15 +197,22 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     // reads sample i of each 256-sample row), then every thread picks up its own 16
     {
         const int base = t0 - kFHalo;
+        if (base >= 0 && base + kFSpan <= n1) { // interior block: no edge tests
+            const float2 *xb = xc + base + tid;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int li = k * 256 + tid, n = base + li;
-            float2 v0 = make_float2(0.0f, 0.0f);
-            if (n >= 0 && n < n1)
-                v0 = xc[n];
-            else if (kHist && n < 0 && n >= -(kFHalo - 1)) // already mixed: the stream's AGC history
-                v0 = hist_in[(size_t)c * (kFHalo - 1) + (kFHalo - 1 + n)];
-            ys[li + (li >> 4)] = v0;
+            for (int k = 0; k < 16; k++)
+                ys[k * 272 + tid + (tid >> 4)] = xb[k * 256]; // li + (li >> 4), li = 256 k + tid
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int li = k * 256 + tid, n = base + li;
+                float2 v0 = make_float2(0.0f, 0.0f);
+                if (n >= 0 && n < n1)
+                    v0 = xc[n];
+                else if (kHist && n < 0 && n >= -(kFHalo - 1)) // already mixed: the stream's AGC history
+                    v0 = hist_in[(size_t)c * (kFHalo - 1) + (kFHalo - 1 + n)];
+                ys[li + (li >> 4)] = v0;
+            }
         }
     }
     __syncthreads();
@@ -217,15 +224,23 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
         const float ph0 = ckpt[(size_t)(n0 >> 4) * channels + c];
         const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
         const float F_PI = 3.14159265358979323846f;
-        // straight-line fast path: every phase inside [-pi, pi) (always, for |inc| < 2 pi)
+        // straight-line fast path.  frequency_modulator_fc leaves d_phase = fmod(u, 2 pi) - pi in
+        // (-3 pi, pi): below -pi whenever the frequency is negative (fmod keeps the sign).  There
+        // float_to_fixed folds with d = floor(x / 2 pi + 0.5) = -1, i.e. x - (float)d * 2 pi =
+        // x + 2 pi with one rounding.  d = -1 exactly for the floats in [RN(-1.5 * 2pi_f), -pi_f):
+        // their float quotient x / 2pi_f lies in [-1.5, -0.5) (checked float by float at both
+        // ends), and d_phase cannot go below RN(-1.5 * 2pi_f) = RN(nextabove(-2pi_f) - pi_f).
+        // Anything else takes the general path below.
+        const float F_2PI = 2.0f * F_PI;
         float ph = ph0;
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             ph = nco_step_nobranch(ph, inc, bad);
-            bad = bad || !(ph >= -F_PI && ph < F_PI);
+            bad = bad || !(ph >= -1.5f * F_2PI && ph < F_PI);
+            const float folded = (ph < -F_PI) ? ph + F_2PI : ph;
             float sn, cs;
-            fxpt_sincos(float_to_fixed_inrange(ph), sine, &sn, &cs);
+            fxpt_sincos(float_to_fixed_inrange(folded), sine, &sn, &cs);
             v[k] = cmul_fma(v[k], make_float2(cs, sn));
         }
         if (bad) { // general path (fmod, fold, true division) from the raw samples still in ys
