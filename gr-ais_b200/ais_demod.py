@@ -224,6 +224,18 @@ class ais_demod:
                                                int(max_bits), B.ptr(nbits_ptr), B.ptr(tags_ptr),
                                                B.ptr(ntags_ptr), stream))
 
+    def enqueue_dev(self, iq_ptr, nsamples, bits_ptr, max_bits, nbits_ptr, tags_ptr=None,
+                    ntags_ptr=None, stream=None):
+        """work_dev for a run of independent records: the timing loop of this record runs on
+        an internal high-priority stream under the front half of the next one.  bits / nbits
+        are complete after join(stream)."""
+        B.check(B.lib().b200ais_demod_enqueue_dev(self._h, B.ptr(iq_ptr), int(nsamples), B.ptr(bits_ptr),
+                                                  int(max_bits), B.ptr(nbits_ptr), B.ptr(tags_ptr),
+                                                  B.ptr(ntags_ptr), stream))
+
+    def join(self, stream=None):
+        B.check(B.lib().b200ais_demod_join(self._h, stream))
+
     # ---- the chain as a stream: the blocks keep their state from call to call ----
 
     def stream_reset(self, stream=None):

@@ -730,7 +730,7 @@ struct b200ais_demod {
     cudaStream_t streams[kMaxGroups] = {};
     cudaEvent_t done[kMaxGroups] = {};
     cudaEvent_t ev_fork = nullptr;
-    int overlap_groups = 4; // channel groups a *_dev call forks over internal streams (1 = none)
+    int overlap_groups = 1; // channel groups a *_dev call forks over internal streams (1 = none)
     bool taps_enabled = false;
     DevBuf t_sym, t_err, t_mu, t_soft, t_otags;
     bool profiling = false;
@@ -738,6 +738,15 @@ struct b200ais_demod {
     double stage_ms[B200AIS_STAGE_T_COUNT] = { 0, 0, 0, 0, 0, 0, 0 };
     int prof_calls = 0;
     int last_n = 0, last_max_bits = 0, last_n1 = 0;
+    // ---- pipelined submission (b200ais_demod_enqueue_dev): the timing loop + bit tail of call k
+    // run on a high-priority side stream under the front half of call k+1 ----
+    cudaStream_t back_stream = nullptr;
+    float2 *d_a_alt = nullptr;        // second set of corr_est input rows (set 1)
+    b200ais_tag *d_tags_alt = nullptr;
+    int *d_ntags_alt = nullptr;
+    cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_back[2] = { nullptr, nullptr };
+    bool back_pending[2] = { false, false };
+    unsigned pipe_calls = 0;
     // ---- stream mode (b200ais_demod_stream_*): what every block keeps between calls ----
     bool st_ready = false;     // state allocated and reset
     bool pad_dirty = false;    // stream calls used the rows' history pads: batch calls re-zero them
@@ -914,8 +923,17 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
     void *ptrs[] = { h->d_taps_time, h->d_corr, h->d_x, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
                      h->d_tags, h->d_ntags, h->d_nbits, h->d_ncons, h->d_state, h->d_bits,
                      h->d_status, h->d_xcarry, h->d_phase, h->d_yhist[0], h->d_yhist[1],
-                     h->d_ctail[0], h->d_ctail[1], h->d_unc, h->d_nold, h->d_tcarry };
+                     h->d_ctail[0], h->d_ctail[1], h->d_unc, h->d_nold, h->d_tcarry, h->d_a_alt,
+                     h->d_tags_alt, h->d_ntags_alt };
     h->xs.release();
+    if (h->back_stream)
+        cudaStreamDestroy(h->back_stream);
+    for (int k = 0; k < 2; k++) {
+        if (h->ev_front[k])
+            cudaEventDestroy(h->ev_front[k]);
+        if (h->ev_back[k])
+            cudaEventDestroy(h->ev_back[k]);
+    }
     for (void *p : ptrs)
         if (p)
             cudaFree(p);
@@ -951,15 +969,19 @@ extern "C" int b200ais_demod_enable_taps(b200ais_demod *h, int enable)
 // Launch the chain for channels [c0, c0+cn) on stream s.  iq rows: iq + c*iq_stride.
 // in_a != 0 means the samples already sit in the corr_est input rows (host variant with
 // neither freq sync nor AGC enabled).
+// back != nullptr: the timing loop and the bit tail go to that stream (after ev_front), reading
+// the rows of a_base; everything up to the detector stays on s.
 static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq, size_t iq_stride,
                               int n, int in_a, uint8_t *bits, int max_bits, int *nbits,
-                              b200ais_tag *tags, int *ntags, int *d_status, cudaStream_t s)
+                              b200ais_tag *tags, int *ntags, int *d_status, cudaStream_t s,
+                              float2 *a_base = nullptr, cudaStream_t back = nullptr,
+                              cudaEvent_t ev_front = nullptr)
 {
     const b200ais_demod_config &cfg = h->cfg;
     const bool fs = cfg.stages & B200AIS_STAGE_FREQSYNC;
     const int n1 = fs ? (n / cfg.fftlen) * cfg.fftlen : n;
     const int nvec = fs ? n1 / cfg.fftlen : 0;
-    float2 *a_rows = h->d_a + (size_t)c0 * h->a_stride + h->HP;
+    float2 *a_rows = (a_base ? a_base : h->d_a) + (size_t)c0 * h->a_stride + h->HP;
     uint8_t *mask = h->d_mask + (size_t)c0 * h->mask_stride;
     int *raw = h->d_raw + (size_t)c0 * std::max(h->nvec_max, 1);
     float *fhat = h->d_fhat + (size_t)c0 * std::max(h->nvec_max, 1);
@@ -1017,6 +1039,11 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
                             d_status, 0, s)))
         return rc;
     B200_MARK(B200AIS_STAGE_T_DETECT);
+    if (back) {
+        B200_CU(cudaEventRecord(ev_front, s));
+        B200_CU(cudaStreamWaitEvent(back, ev_front, 0));
+        s = back;
+    }
     if ((rc = launch_msk_reset(h->d_state + c0, cn, h->mp.sps_half, s)))
         return rc;
     float2 *t_sym = h->t_sym.as<float2>() + (size_t)c0 * max_bits;
@@ -1080,6 +1107,19 @@ extern "C" int b200ais_demod_stage_ms(b200ais_demod *h, double *stage_ms, int *c
     return B200AIS_OK;
 }
 
+static int demod_join(b200ais_demod *h, cudaStream_t s);
+
+// wait (on the host) for every back half still in flight: the paths that run on the handle's
+// own streams cannot be ordered behind them any other way
+static int demod_drain(b200ais_demod *h)
+{
+    if (h->back_pending[0] || h->back_pending[1]) {
+        B200_CU(cudaStreamSynchronize(h->back_stream));
+        h->back_pending[0] = h->back_pending[1] = false;
+    }
+    return B200AIS_OK;
+}
+
 static int demod_prepare(b200ais_demod *h, int n, int max_bits)
 {
     if (n < 1 || n > h->max_samples) {
@@ -1124,10 +1164,12 @@ extern "C" int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsa
         set_error("demod_work: null argument");
         return B200AIS_E_INVALID;
     }
-    int rc = demod_prepare(h, nsamples, max_bits);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = demod_join(h, s);
     if (rc)
         return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((rc = demod_prepare(h, nsamples, max_bits)))
+        return rc;
     const float2 *iq2 = reinterpret_cast<const float2 *>(iq);
     B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
     int groups = h->profiling ? 1 : std::min(std::min(h->overlap_groups, kMaxGroups), h->channels / 64);
@@ -1165,6 +1207,86 @@ extern "C" int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsa
     return B200AIS_OK;
 }
 
+// make `s` wait for every back half still in flight
+static int demod_join(b200ais_demod *h, cudaStream_t s)
+{
+    for (int k = 0; k < 2; k++)
+        if (h->back_pending[k]) {
+            B200_CU(cudaStreamWaitEvent(s, h->ev_back[k], 0));
+            h->back_pending[k] = false;
+        }
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_join(b200ais_demod *h, void *stream)
+{
+    if (!h) {
+        set_error("demod_join: null handle");
+        return B200AIS_E_INVALID;
+    }
+    return demod_join(h, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200ais_demod_enqueue_dev(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
+                                         int max_bits, int *nbits, b200ais_tag *tags, int *ntags,
+                                         void *stream)
+{
+    if (!h || !iq || !bits || !nbits) {
+        set_error("demod_enqueue: null argument");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t C = (size_t)h->channels;
+    if (!h->back_stream) {
+        int lo = 0, hi = 0;
+        B200_CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        B200_CU(cudaStreamCreateWithPriority(&h->back_stream, cudaStreamNonBlocking, hi));
+        B200_CU(cudaMalloc(&h->d_a_alt, sizeof(float2) * h->a_stride * C));
+        B200_CU(cudaMemset(h->d_a_alt, 0, sizeof(float2) * h->a_stride * C));
+        B200_CU(cudaMalloc(&h->d_tags_alt, sizeof(b200ais_tag) * (size_t)h->max_tags * C));
+        B200_CU(cudaMalloc(&h->d_ntags_alt, sizeof(int) * C));
+        for (int k = 0; k < 2; k++) {
+            B200_CU(cudaEventCreateWithFlags(&h->ev_front[k], cudaEventDisableTiming));
+            B200_CU(cudaEventCreateWithFlags(&h->ev_back[k], cudaEventDisableTiming));
+        }
+    }
+    const bool idle = !h->back_pending[0] && !h->back_pending[1];
+    if (h->t_sym.cap < C * (size_t)max_bits * sizeof(float2) || h->pad_dirty || h->taps_enabled) {
+        // scratch has to grow (or a stream left its items in the rows): drain the pipeline first
+        int rc = demod_join(h, s);
+        if (rc)
+            return rc;
+        B200_CU(cudaStreamSynchronize(s));
+    }
+    int rc = demod_prepare(h, nsamples, max_bits);
+    if (rc)
+        return rc;
+    if (idle)
+        B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
+    const int set = (int)(h->pipe_calls & 1u);
+    if (h->back_pending[set]) { // the back half of call k-2 read this set of rows and tags
+        B200_CU(cudaStreamWaitEvent(s, h->ev_back[set], 0));
+        h->back_pending[set] = false;
+    }
+    b200ais_tag *dtags = set ? h->d_tags_alt : h->d_tags;
+    int *dntags = set ? h->d_ntags_alt : h->d_ntags;
+    rc = demod_launch_group(h, 0, h->channels, reinterpret_cast<const float2 *>(iq), (size_t)nsamples,
+                            nsamples, 0, bits, max_bits, nbits, dtags, dntags, h->d_status, s,
+                            set ? h->d_a_alt : h->d_a, h->back_stream, h->ev_front[set]);
+    if (rc)
+        return rc;
+    B200_CU(cudaEventRecord(h->ev_back[set], h->back_stream));
+    h->back_pending[set] = true;
+    h->pipe_calls++;
+    // the tags are final once the detector has run: they go out on the caller's stream
+    if (tags)
+        B200_CU(cudaMemcpyAsync(tags, dtags, sizeof(b200ais_tag) * (size_t)h->max_tags * C,
+                                cudaMemcpyDeviceToDevice, s));
+    if (ntags)
+        B200_CU(cudaMemcpyAsync(ntags, dntags, sizeof(int) * C, cudaMemcpyDeviceToDevice, s));
+    return B200AIS_OK;
+}
+
 extern "C" int b200ais_demod_status(b200ais_demod *h)
 {
     if (!h)
@@ -1186,8 +1308,10 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
         set_error("demod_work: null argument");
         return B200AIS_E_INVALID;
     }
-    int rc = demod_prepare(h, nsamples, max_bits);
+    int rc = demod_drain(h);
     if (rc)
+        return rc;
+    if ((rc = demod_prepare(h, nsamples, max_bits)))
         return rc;
     const int C = h->channels, n = nsamples;
     const bool direct = (h->cfg.stages & (B200AIS_STAGE_FREQSYNC | B200AIS_STAGE_AGC)) == 0;
@@ -1203,7 +1327,7 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
     }
     B200_CU(cudaMemset(h->d_status, 0, sizeof(int) * (kMaxGroups + 1)));
     // channel groups pipelined over streams: copy-in of group g+1 overlaps compute of group g
-    const int ngroups = std::max(1, std::min(std::min(2 * h->overlap_groups, kMaxGroups), C / 64));
+    const int ngroups = std::max(1, std::min(kMaxGroups, C / 64));
     for (int g = 0; g < ngroups; g++) {
         const int c0 = (int)((long long)C * g / ngroups), c1 = (int)((long long)C * (g + 1) / ngroups);
         const int cn = c1 - c0;
@@ -1462,7 +1586,9 @@ static int stream_prepare(b200ais_demod *h, int n, int max_bits, cudaStream_t s)
         set_error("demod_stream_work: max_bits must be positive");
         return B200AIS_E_INVALID;
     }
-    int rc;
+    int rc = demod_drain(h);
+    if (rc)
+        return rc;
     if (!h->st_ready && (rc = b200ais_demod_stream_reset(h, s)))
         return rc;
     if ((rc = h->t_sym.reserve((size_t)h->channels * max_bits * sizeof(float2))))

@@ -204,6 +204,19 @@ B200AIS_API int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int ns
 /* after a *_dev call has completed: 0 or the B200AIS_E_* a kernel flagged */
 B200AIS_API int b200ais_demod_status(b200ais_demod *h);
 
+/* Pipelined submission of independent records (same arguments and results as work_dev).  The
+ * two per-channel recurrences (NCO phase, timing loop) take the same time for any batch size,
+ * so a strictly ordered call always exposes one full timing-loop pass.  enqueue_dev orders
+ * everything up to the corr_est detector on `stream` and hands msk_timing_recovery + the bit
+ * tail to an internal high-priority stream, where they run under the front half of the NEXT
+ * enqueue (corr_est input rows and tags are double-buffered).  tags / ntags are complete in
+ * `stream` order; bits / nbits are complete once a later b200ais_demod_join(h, stream) has
+ * been reached in `stream` order (any other b200ais_demod_* work call joins by itself). */
+B200AIS_API int b200ais_demod_enqueue_dev(b200ais_demod *h, const float *iq, int nsamples,
+                                          uint8_t *bits, int max_bits, int *nbits,
+                                          b200ais_tag *tags, int *ntags, void *stream);
+B200AIS_API int b200ais_demod_join(b200ais_demod *h, void *stream);
+
 /* The same chain fed as a stream: a capture arrives in pieces of any size (0..max_samples
  * items per call, the same count on every channel) and every block keeps, from call to
  * call, what it keeps between work() calls under the GNU Radio scheduler:
@@ -247,8 +260,10 @@ enum {
     B200AIS_STAGE_T_COUNT = 7
 };
 B200AIS_API int b200ais_demod_profile(b200ais_demod *h, int enable);
-/* Number of channel groups a work call forks over internal CUDA streams (default 4; 1 = run
- * every kernel on the caller's stream).  The caller's stream still orders the whole call. */
+/* Number of channel groups a work_dev call forks over internal CUDA streams (default 1 = run
+ * every kernel on the caller's stream; measured: no gain device-resident).  The caller's stream
+ * still orders the whole call.  The host-buffer variant always pipelines 8 channel groups so
+ * that copies overlap kernels. */
 B200AIS_API int b200ais_demod_set_overlap(b200ais_demod *h, int groups);
 B200AIS_API int b200ais_demod_stage_ms(b200ais_demod *h, double *stage_ms, int *calls);
 

@@ -147,3 +147,55 @@ def test_two_outputs_per_symbol(oracle, templates):
     """osps = 2: msk_timing_recovery emits every half-symbol step (:186)"""
     x, _ = _records(2, 8192, nbursts=2, snr_db=20)
     _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC, osps=2)
+
+
+def test_pipelined_enqueue_equals_strict_calls(oracle, templates):
+    """enqueue_dev x K + join gives, record by record, what K work_dev calls give"""
+    torch = pytest.importorskip("torch")
+    C, n, K = 96, 16384, 5
+    recs = [np.stack([synth.make_record(100 * k + c, n=n, nbursts=3, snr_db=22)[0] for c in range(C)])
+            for k in range(K)]
+    d = ais_demod(channels=C, max_samples=n, template=templates[120], max_tags=512)
+    mb = d.max_bits(n)
+    st = torch.cuda.Stream()
+    xs = [torch.from_numpy(r.view(np.float32).reshape(C, n, 2)).cuda() for r in recs]
+    ref_bits, ref_n, ref_tags, ref_nt = [], [], [], []
+    for k in range(K):
+        bits = torch.zeros((C, mb), dtype=torch.uint8, device="cuda")
+        nb = torch.zeros(C, dtype=torch.int32, device="cuda")
+        tg = torch.zeros((C, d.max_tags, 24), dtype=torch.uint8, device="cuda")
+        nt = torch.zeros(C, dtype=torch.int32, device="cuda")
+        d.work_dev(xs[k].data_ptr(), n, bits.data_ptr(), mb, nb.data_ptr(), tg.data_ptr(), nt.data_ptr(),
+                   st.cuda_stream)
+        st.synchronize()
+        d.status()
+        ref_bits.append(bits.cpu().numpy()); ref_n.append(nb.cpu().numpy())
+        ref_tags.append(tg.cpu().numpy()); ref_nt.append(nt.cpu().numpy())
+    outs = []
+    for k in range(K):
+        bits = torch.zeros((C, mb), dtype=torch.uint8, device="cuda")
+        nb = torch.zeros(C, dtype=torch.int32, device="cuda")
+        tg = torch.zeros((C, d.max_tags, 24), dtype=torch.uint8, device="cuda")
+        nt = torch.zeros(C, dtype=torch.int32, device="cuda")
+        d.enqueue_dev(xs[k].data_ptr(), n, bits.data_ptr(), mb, nb.data_ptr(), tg.data_ptr(), nt.data_ptr(),
+                      st.cuda_stream)
+        outs.append((bits, nb, tg, nt))
+    d.join(st.cuda_stream)
+    st.synchronize()
+    d.status()
+    for k in range(K):
+        bits, nb, tg, nt = (t.cpu().numpy() for t in outs[k])
+        assert np.array_equal(nb, ref_n[k]) and np.array_equal(nt, ref_nt[k]), k
+        for c in range(C):
+            assert np.array_equal(bits[c, :nb[c]], ref_bits[k][c, :nb[c]]), (k, c)
+            assert np.array_equal(tg[c, :nt[c]], ref_tags[k][c, :nt[c]]), (k, c)
+    # a strict call right after enqueues joins by itself
+    bits = torch.zeros((C, mb), dtype=torch.uint8, device="cuda")
+    nb = torch.zeros(C, dtype=torch.int32, device="cuda")
+    d.enqueue_dev(xs[0].data_ptr(), n, outs[0][0].data_ptr(), mb, outs[0][1].data_ptr(), None, None, st.cuda_stream)
+    d.work_dev(xs[1].data_ptr(), n, bits.data_ptr(), mb, nb.data_ptr(), None, None, st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(nb.cpu().numpy(), ref_n[1])
+    assert np.array_equal(outs[0][1].cpu().numpy(), ref_n[0])
+    b0, _, _, _ = d.work(recs[2])  # host path drains the pipeline too
+    d.close()

@@ -4,10 +4,11 @@ import json
 import subprocess
 import sys
 
-points = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(4096, 4)]
+sys.argv_extra = [a for a in sys.argv[1:] if a.startswith("--")]
+points = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:] if not a.startswith("--")] or [(4096, 4)]
 for ch, ov in points:
     r = subprocess.run([sys.executable, "bench.py", "--no-cpu-baseline", "--channels", str(ch),
-                        "--overlap", str(ov)], capture_output=True, text=True)
+                        "--overlap", str(ov)] + sys.argv_extra, capture_output=True, text=True)
     try:
         d = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception:
