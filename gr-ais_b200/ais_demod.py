@@ -224,6 +224,13 @@ class ais_demod:
                                                int(max_bits), B.ptr(nbits_ptr), B.ptr(tags_ptr),
                                                B.ptr(ntags_ptr), stream))
 
+    def set_symbols(self, symbols, stream=None):
+        """corr_est_cc::set_symbols on the chain's correlator: taps replaced verbatim, threshold
+        unchanged (lib/corr_est_cc_impl.cc:132-162); same length as at construction."""
+        symbols = np.ascontiguousarray(symbols, dtype=np.complex64)
+        B.check(B.lib().b200ais_demod_set_symbols(self._h, B.ptr(symbols), len(symbols), stream))
+        self.mod_vector = symbols
+
     def enqueue_dev(self, iq_ptr, nsamples, bits_ptr, max_bits, nbits_ptr, tags_ptr=None,
                     ntags_ptr=None, stream=None):
         """work_dev for a run of independent records: the timing loop of this record runs on

@@ -42,7 +42,7 @@ EXPORTS = [
     "b200ais_demod_read_tap", "b200ais_demod_profile", "b200ais_demod_stage_ms",
     "b200ais_demod_set_overlap", "b200ais_demod_stream_reset", "b200ais_demod_stream_max_bits",
     "b200ais_demod_stream_work", "b200ais_demod_stream_work_dev", "b200ais_demod_stream_pending",
-    "b200ais_demod_enqueue_dev", "b200ais_demod_join",
+    "b200ais_demod_enqueue_dev", "b200ais_demod_join", "b200ais_demod_set_symbols",
 ]
 STAGE_NAMES = ["sqfft_freqest", "nco_phase", "mix_agc", "corr", "detect", "msk", "tail"]
 
@@ -137,6 +137,7 @@ def lib():
     L.b200ais_demod_stage_ms.argtypes = [vp, vp, vp]
     L.b200ais_demod_enqueue_dev.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp]
     L.b200ais_demod_join.argtypes = [vp, vp]
+    L.b200ais_demod_set_symbols.argtypes = [vp, vp, i, vp]
     L.b200ais_demod_stream_reset.argtypes = [vp, vp]
     L.b200ais_demod_stream_max_bits.argtypes = [vp, i]
     L.b200ais_demod_stream_work.argtypes = [vp, vp, i, vp, i, vp, vp, vp]

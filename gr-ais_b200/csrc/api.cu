@@ -966,6 +966,8 @@ extern "C" int b200ais_demod_enable_taps(b200ais_demod *h, int enable)
     return B200AIS_OK;
 }
 
+static int demod_drain(b200ais_demod *h);
+
 // Launch the chain for channels [c0, c0+cn) on stream s.  iq rows: iq + c*iq_stride.
 // in_a != 0 means the samples already sit in the corr_est input rows (host variant with
 // neither freq sync nor AGC enabled).
@@ -1060,6 +1062,32 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     B200_MARK(B200AIS_STAGE_T_TAIL);
 #undef B200_MARK
     return rc;
+}
+
+// corr_est_cc::set_symbols on the chain's correlator (lib/corr_est_cc_impl.cc:132-162): the taps
+// are replaced verbatim -- no conjugate, no reversal -- and d_thresh keeps the constructor's
+// value.  The template length is fixed at create (it sizes every buffer).
+extern "C" int b200ais_demod_set_symbols(b200ais_demod *h, const float *symbols_iq, int nsymbols,
+                                         void *stream)
+{
+    if (!h || !symbols_iq) {
+        set_error("demod_set_symbols: null argument");
+        return B200AIS_E_INVALID;
+    }
+    if (nsymbols != h->L) {
+        set_error("demod_set_symbols: the chain was created for %d symbols, got %d", h->L, nsymbols);
+        return B200AIS_E_INVALID;
+    }
+    int rc = demod_drain(h);
+    if (rc)
+        return rc;
+    B200_CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    for (int g = 0; g < kMaxGroups; g++)
+        B200_CU(cudaStreamSynchronize(h->streams[g]));
+    std::vector<float2> g((size_t)corr_fft_size(nsymbols));
+    make_corr_spectrum(symbols_iq, nsymbols, g.data());
+    B200_CU(cudaMemcpy(h->d_taps_time, g.data(), sizeof(float2) * g.size(), cudaMemcpyHostToDevice));
+    return B200AIS_OK;
 }
 
 extern "C" int b200ais_demod_set_overlap(b200ais_demod *h, int groups)

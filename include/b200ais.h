@@ -193,6 +193,12 @@ B200AIS_API int b200ais_demod_create(b200ais_demod **h, const b200ais_demod_conf
                                      int max_samples, int max_tags);
 B200AIS_API int b200ais_demod_destroy(b200ais_demod *h);
 B200AIS_API int b200ais_demod_max_bits(const b200ais_demod *h, int nsamples);
+/* corr_est_cc::set_symbols (lib/corr_est_cc_impl.cc:132-162) on the chain's correlator: the taps
+ * are replaced verbatim (no conjugate / reversal, unlike the constructor) and d_thresh keeps its
+ * value; nsymbols must equal the count given at create.  Synchronises `stream`; applies to every
+ * later batch and stream call. */
+B200AIS_API int b200ais_demod_set_symbols(b200ais_demod *h, const float *symbols_iq, int nsymbols,
+                                          void *stream);
 /* One record per channel, every block freshly constructed (ais_demod on a new stream).
  * iq: [channels][nsamples] complex; bits: [channels][max_bits] unpacked 0/1 bytes;
  * nbits: [channels]; tags (nullable): [channels][max_tags]; ntags (nullable): [channels]. */

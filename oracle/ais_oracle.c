@@ -1060,6 +1060,15 @@ void ao_stream_free(ao_stream *s)
     memset(s, 0, sizeof(*s));
 }
 
+/* corr_est_cc::set_symbols on the running stream (same length: the chain's buffers are sized by it) */
+int ao_stream_set_symbols(ao_stream *s, const float *symbols, int L)
+{
+    if (L != s->L)
+        return -1;
+    ao_corr_est_set_symbols(&s->ce, symbols, L);
+    return 0;
+}
+
 int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_bits, int *nbits,
                    ao_tag *tags_out, int max_tags, int *ntags_out)
 {

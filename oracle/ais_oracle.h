@@ -221,6 +221,7 @@ int ao_stream_init(ao_stream *s, const ao_chain_cfg *cfg, const float *symbols, 
 ao_stream *ao_stream_new(const ao_chain_cfg *cfg, const float *symbols, int L);
 void ao_stream_delete(ao_stream *s);
 void ao_stream_free(ao_stream *s);
+int ao_stream_set_symbols(ao_stream *s, const float *symbols, int L);
 /* bits/tags of this call only; returns 0 or a negative status */
 int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_bits, int *nbits,
                    ao_tag *tags_out, int max_tags, int *ntags_out);

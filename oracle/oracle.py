@@ -464,6 +464,12 @@ class DemodStream:
         except Exception:
             pass
 
+    def set_symbols(self, symbols):
+        symbols = _c64(symbols)
+        lib().ao_stream_set_symbols.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        if lib().ao_stream_set_symbols(self._s, _fp(symbols), len(symbols)):
+            raise ValueError("set_symbols: the stream was built for another template length")
+
     def work(self, x, max_tags=4096):
         """Returns (bits, tags) produced by this call."""
         x = _c64(x)

@@ -150,3 +150,32 @@ def test_stream_many_channels_dev(oracle, templates):
             assert np.array_equal(hb[c, :hn[c]], rb), (pos, c)
         pos += m
     d.close()
+
+
+def test_stream_set_symbols_hot_swap(oracle, templates):
+    """set_symbols between stream calls: taps swapped verbatim, threshold and filter tail kept
+    (lib/corr_est_cc_impl.cc:132-162); same call sequence on the oracle stream"""
+    x, _ = _records(4, 30000, nbursts=4, snr_db=25)
+    t0 = templates[120]
+    # the taps the constructor would have built from a time-shifted copy of the preamble, handed
+    # over the way set_symbols stores them (no conjugate / reversal)
+    t1 = np.ascontiguousarray(np.conj(np.roll(t0, 3))[::-1])
+    d = ais_demod(channels=4, max_samples=12000, template=t0, max_tags=2048)
+    refs = [oracle.DemodStream(t0, _cfg(oracle, d, B.STAGE_FREQSYNC | B.STAGE_AGC)) for _ in range(4)]
+    pos = 0
+    for call, m in enumerate([9000, 12000, 9000]):
+        if call == 1:
+            d.set_symbols(t1)
+            for r in refs:
+                r.set_symbols(t1)
+        bits, nbits, tags, ntags = d.stream_work(x[:, pos:pos + m])
+        for c in range(4):
+            rb, rt = refs[c].work(x[c, pos:pos + m])
+            assert nbits[c] == len(rb) and np.array_equal(bits[c, :nbits[c]], rb), (call, c)
+            assert ntags[c] == len(rt), (call, c)
+            for f in ("offset", "key", "port", "value"):
+                assert np.array_equal(tags[c, :ntags[c]][f], rt[f]), (call, c, f)
+        pos += m
+    with pytest.raises(B.B200AisError):
+        d.set_symbols(templates[140])
+    d.close()
