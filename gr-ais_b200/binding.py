@@ -43,7 +43,17 @@ EXPORTS = [
     "b200ais_demod_set_overlap", "b200ais_demod_stream_reset", "b200ais_demod_stream_max_bits",
     "b200ais_demod_stream_work", "b200ais_demod_stream_work_dev", "b200ais_demod_stream_pending",
     "b200ais_demod_enqueue_dev", "b200ais_demod_join", "b200ais_demod_set_symbols",
+    "b200ais_firdes_low_pass", "b200ais_xlat_create", "b200ais_xlat_destroy",
+    "b200ais_xlat_history", "b200ais_xlat_decimation", "b200ais_xlat_set_center_freq",
+    "b200ais_xlat_set_taps", "b200ais_xlat_reset", "b200ais_xlat_work", "b200ais_xlat_work_dev",
+    "b200ais_hdlc_create", "b200ais_hdlc_destroy", "b200ais_hdlc_reset", "b200ais_hdlc_work",
+    "b200ais_hdlc_work_dev", "b200ais_hdlc_status",
+    "b200ais_nmea_slot_bytes", "b200ais_nmea_format", "b200ais_nmea_format_dev",
 ]
+FRAME_MAX = 248
+FRAME_DTYPE = np.dtype([("end_bit", "<u8"), ("len", "<i4"), ("channel", "<i4"),
+                        ("data", "u1", (FRAME_MAX,))])
+E_FRAME_OVERFLOW = -8
 STAGE_NAMES = ["sqfft_freqest", "nco_phase", "mix_agc", "corr", "detect", "msk", "tail"]
 
 
@@ -143,6 +153,24 @@ def lib():
     L.b200ais_demod_stream_work.argtypes = [vp, vp, i, vp, i, vp, vp, vp]
     L.b200ais_demod_stream_work_dev.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp]
     L.b200ais_demod_stream_pending.argtypes = [vp, vp, vp, vp]
+    f64 = C.c_double
+    L.b200ais_firdes_low_pass.argtypes = [f64, f64, f64, f64, vp, i, C.POINTER(i)]
+    L.b200ais_xlat_create.argtypes = [C.POINTER(vp), i, vp, i, vp, i, f64, i]
+    for f in ("b200ais_xlat_destroy", "b200ais_xlat_history", "b200ais_xlat_decimation",
+              "b200ais_xlat_reset"):
+        getattr(L, f).argtypes = [vp]
+    L.b200ais_xlat_set_center_freq.argtypes = [vp, i, f64]
+    L.b200ais_xlat_set_taps.argtypes = [vp, vp, i]
+    L.b200ais_xlat_work.argtypes = [vp, i, vp, sz, vp, sz]
+    L.b200ais_xlat_work_dev.argtypes = [vp, i, vp, sz, vp, sz, vp]
+    L.b200ais_hdlc_create.argtypes = [C.POINTER(vp), i, i, i]
+    for f in ("b200ais_hdlc_destroy", "b200ais_hdlc_reset", "b200ais_hdlc_status"):
+        getattr(L, f).argtypes = [vp]
+    L.b200ais_hdlc_work.argtypes = [vp, vp, sz, vp, i, vp, i, vp]
+    L.b200ais_hdlc_work_dev.argtypes = [vp, vp, sz, vp, i, vp, i, vp, vp]
+    L.b200ais_nmea_slot_bytes.argtypes = [i, C.c_char_p]
+    L.b200ais_nmea_format.argtypes = [vp, vp, i, i, vp, vp, i, vp]
+    L.b200ais_nmea_format_dev.argtypes = [vp, vp, i, i, vp, vp, i, vp, vp]
     _lib = L
     return L
 

@@ -260,3 +260,159 @@ class invert:
         B.check(B.lib().b200ais_invert_work(B.ptr(inp), B.ptr(tmp), n))
         output_items[0].reshape(-1)[:n] = tmp
         return n
+
+
+# ------------------------------------------------------------------------------------
+# The blocks either side of ais_demod inside the reference's ais_rx (python/radio.py:39-72)
+
+def firdes_low_pass(gain, sampling_freq, cutoff_freq, transition_width):
+    """filter.firdes.low_pass (Hamming window), as python/radio.py:49 calls it."""
+    n = C.c_int(0)
+    B.check(B.lib().b200ais_firdes_low_pass(gain, sampling_freq, cutoff_freq, transition_width,
+                                            None, 0, C.byref(n)))
+    taps = np.zeros(n.value, dtype=np.float32)
+    B.check(B.lib().b200ais_firdes_low_pass(gain, sampling_freq, cutoff_freq, transition_width,
+                                            B.ptr(taps), n.value, C.byref(n)))
+    return taps
+
+
+class freq_xlating_fir_filter_ccf:
+    """filter.freq_xlating_fir_filter_ccf(decimation, taps, center_freq, sampling_freq)
+    (python/radio.py:51-54).  center_freq may be a list: that many filters share each of the
+    `sources` inputs (the A and B rx paths of python/radio.py:86-91); output row
+    s*len(center_freq) + k is source s translated by center_freq[k]."""
+
+    def __init__(self, decimation, taps, center_freq, sampling_freq, sources=1):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        freqs = np.atleast_1d(np.asarray(center_freq, dtype=np.float64)).copy()
+        self._h = C.c_void_p()
+        self.sources, self.nfreqs, self.ntaps = int(sources), len(freqs), len(taps)
+        self._decim = int(decimation)
+        B.check(B.lib().b200ais_xlat_create(C.byref(self._h), self._decim, B.ptr(taps), len(taps),
+                                            B.ptr(freqs), len(freqs), float(sampling_freq),
+                                            self.sources))
+
+    def __del__(self):
+        try:
+            if self._h:
+                B.lib().b200ais_xlat_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def history(self):
+        return B.lib().b200ais_xlat_history(self._h)
+
+    def decimation(self):
+        return B.lib().b200ais_xlat_decimation(self._h)
+
+    def set_center_freq(self, center_freq, k=0):
+        B.check(B.lib().b200ais_xlat_set_center_freq(self._h, int(k), float(center_freq)))
+
+    def set_taps(self, taps):
+        taps = np.ascontiguousarray(taps, dtype=np.float32)
+        B.check(B.lib().b200ais_xlat_set_taps(self._h, B.ptr(taps), len(taps)))
+        self.ntaps = len(taps)
+
+    def reset(self):
+        B.check(B.lib().b200ais_xlat_reset(self._h))
+
+    def work(self, noutput_items, input_items, output_items):
+        """input_items[0]: [sources, >= history()-1 + noutput_items*decimation()] (history
+        first); output_items[0]: [sources*nfreqs, >= noutput_items].  Returns noutput_items."""
+        x = _as_c64(input_items[0], self.sources)
+        need = self.ntaps - 1 + noutput_items * self._decim
+        if x.shape[1] < need:
+            raise ValueError("work: %d input items per row, need %d" % (x.shape[1], need))
+        out = output_items[0]
+        if out.dtype != np.complex64 or out.shape[0] != self.sources * self.nfreqs or \
+                out.shape[1] < noutput_items or not out.flags.c_contiguous:
+            raise ValueError("work: bad output array")
+        B.check(B.lib().b200ais_xlat_work(self._h, int(noutput_items), B.ptr(x), x.shape[1],
+                                          B.ptr(out), out.shape[1]))
+        return noutput_items
+
+
+class hdlc_deframer_bp:
+    """digital.hdlc_deframer_bp(length_min, length_max) (python/radio.py:64): unpacked bits in,
+    one PDU (bytes, CRC checked and removed) per good frame out."""
+
+    def __init__(self, length_min=11, length_max=64, channels=1):
+        self._h = C.c_void_p()
+        self.channels = int(channels)
+        B.check(B.lib().b200ais_hdlc_create(C.byref(self._h), int(length_min), int(length_max),
+                                            self.channels))
+
+    def __del__(self):
+        try:
+            if self._h:
+                B.lib().b200ais_hdlc_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def reset(self):
+        B.check(B.lib().b200ais_hdlc_reset(self._h))
+
+    def work(self, bits, nbits=None, max_frames=64):
+        """bits: [channels, n] unpacked 0/1 bytes; nbits: valid items per row (default: all).
+        Returns (frames [channels, max_frames] of binding.FRAME_DTYPE, nframes [channels])."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        if bits.ndim == 1:
+            bits = bits.reshape(1, -1)
+        if bits.shape[0] != self.channels:
+            raise ValueError("expected %d rows" % self.channels)
+        frames = np.zeros((self.channels, max_frames), dtype=B.FRAME_DTYPE)
+        nframes = np.zeros(self.channels, dtype=np.int32)
+        nb = None if nbits is None else np.ascontiguousarray(nbits, dtype=np.int32)
+        B.check(B.lib().b200ais_hdlc_work(self._h, B.ptr(bits), bits.shape[1], B.ptr(nb),
+                                          bits.shape[1], B.ptr(frames), max_frames, B.ptr(nframes)))
+        return frames, nframes
+
+    @staticmethod
+    def pdus(frames, nframes):
+        """the published PDUs per channel, as bytes"""
+        return [[bytes(f["data"][:f["len"]]) for f in frames[c, :nframes[c]]]
+                for c in range(frames.shape[0])]
+
+
+class pdu_to_nmea:
+    """gr::ais::pdu_to_nmea(designator) (include/ais/pdu_to_nmea.h:37-54)."""
+
+    def __init__(self, designator="A"):
+        self.designator = str(designator)
+        if not 0 < len(self.designator.encode()) <= 8:
+            raise ValueError("designator: 1..8 characters")
+
+    @classmethod
+    def make(cls, designator):
+        return cls(designator)
+
+    def format(self, frames, nframes, designators=None):
+        """msg_to_sentence for every frame of hdlc_deframer_bp.work(); returns a list (per
+        channel) of lists of sentence strings.  designators: per-channel override."""
+        frames = np.ascontiguousarray(frames)
+        nframes = np.ascontiguousarray(nframes, dtype=np.int32)
+        channels, max_frames = frames.shape
+        des = np.zeros((channels, 8), dtype=np.uint8)
+        for c in range(channels):
+            d = (designators[c] if designators is not None else self.designator).encode()
+            des[c, :len(d)] = np.frombuffer(d, dtype=np.uint8)
+        max_len = int(frames["len"].max()) if frames.size else 1
+        slot = B.lib().b200ais_nmea_slot_bytes(max(max_len, 1), b"12345678")
+        B.check(min(slot, 0))
+        sent = np.zeros((channels, max_frames, slot), dtype=np.uint8)
+        lens = np.zeros((channels, max_frames), dtype=np.int32)
+        B.check(B.lib().b200ais_nmea_format(B.ptr(frames), B.ptr(nframes), channels, max_frames,
+                                            B.ptr(des), B.ptr(sent), slot, B.ptr(lens)))
+        if (lens < 0).any():
+            raise B.B200AisError(B.E_OUT_OVERFLOW, "a sentence did not fit its slot")
+        return [[bytes(sent[c, f, :lens[c, f]]).decode("latin-1") for f in range(nframes[c])]
+                for c in range(channels)]
+
+    def to_nmea(self, pdu: bytes) -> str:
+        """the to_nmea / print message handlers for one PDU"""
+        fr = np.zeros((1, 1), dtype=B.FRAME_DTYPE)
+        fr[0, 0]["len"] = len(pdu)
+        fr[0, 0]["data"][:len(pdu)] = np.frombuffer(bytes(pdu), dtype=np.uint8)
+        return self.format(fr, np.array([1], dtype=np.int32))[0][0]

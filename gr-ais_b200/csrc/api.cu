@@ -13,32 +13,6 @@ using namespace b200ais;
 
 namespace {
 
-// ---- small device-buffer helper: grow-only scratch owned by a handle ----
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes)
-    {
-        if (bytes <= cap)
-            return B200AIS_OK;
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        B200_CU(cudaMalloc(&p, bytes));
-        cap = bytes;
-        return B200AIS_OK;
-    }
-    void release()
-    {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-
 size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
 // kernel::fft_filter_ccc block size: fftsize = 2 * 2^ceil(log2 ntaps), nsamples = fftsize - ntaps + 1

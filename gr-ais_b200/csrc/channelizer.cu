@@ -1,0 +1,548 @@
+// channelizer.cu -- the step before the demod path in the reference's receiver
+// (python/radio.py:49-54): firdes.low_pass + freq_xlating_fir_filter_ccf, batched over
+// wideband sources, with its C-ABI (b200ais_firdes_low_pass, b200ais_xlat_*).
+//
+// GNU Radio's block [G] is a decimating FIR with complex band-pass taps
+// ctaps[i] = taps[i] * exp(j i fwT0) followed by a rotator at the output rate.  The canonical
+// dot product (VOLK's order is machine dependent) visits the taps
+// polyphase-major on four real fma chains
+//     Pr += cr*xr   Pi += cr*xi   Qr += ci*xr   Qi += ci*xi,     y = (Pr - Qi, Pi + Qr),
+// so two filters whose taps are complex conjugates of each other -- the reference's A and B
+// channels at -/+25 kHz around 162 MHz (python/radio.py:88-89) -- share one pass:
+// y_B = (Pr + Qi, Pi - Qr).
+//
+// k_xlat_fir: a CTA owns THREADS*8 consecutive outputs of one source.  It stages the input
+// tile in shared memory de-interleaved by residue mod D (each polyphase branch is then a
+// plain FIR over a contiguous row), and every thread slides an 8-item register window down
+// that row: one 8-byte shared load + one broadcast tap load feed 32 fused multiply-adds.
+// Rows are padded by one item in eight so the 64-byte lane stride maps to distinct banks.
+// FP32-pipe bound: 4*ntaps/D fma per input item (482 at the reference's 250 ksps default).
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "device_math.cuh"
+#include "internal.h"
+
+using namespace b200ais;
+
+namespace {
+
+constexpr int kR = 8;          // outputs per thread
+constexpr int kMaxFreqs = 16;
+constexpr int kFront = 2;      // slack items in front of every residue row (window prefetch)
+
+struct RotState {
+    float pr, pi, ir, ii;
+    unsigned counter;
+};
+
+__host__ __device__ __forceinline__ int pad8(int u) { return u + (u >> 3); }
+
+// gr::blocks::rotator [G]: table[j] = phase before item j; phase *= incr (std::complex product,
+// separate multiplies and adds); every 512th item phase /= |phase|.  One lane per frequency.
+__global__ void k_rot_phase(RotState *__restrict__ st, int nfreqs, int n, float2 *__restrict__ tab,
+                            size_t tab_stride)
+{
+    const int k = threadIdx.x;
+    if (k >= nfreqs)
+        return;
+    float pr = st[k].pr, pi = st[k].pi;
+    const float ir = st[k].ir, ii = st[k].ii;
+    unsigned counter = st[k].counter;
+    float2 *t = tab + (size_t)k * tab_stride;
+    for (int j = 0; j < n; j++) {
+        t[j] = make_float2(pr, pi);
+        counter++;
+        float nr = pr * ir - pi * ii;
+        float ni = pr * ii + pi * ir;
+        if ((counter & 511u) == 0) {
+            const float a = hypot_canon(nr, ni);
+            nr = nr / a;
+            ni = ni / a;
+        }
+        pr = nr;
+        pi = ni;
+    }
+    st[k].pr = pr;
+    st[k].pi = pi;
+    st[k].counter = counter;
+}
+
+struct Acc {
+    float Pr[kR], Pi[kR], Qr[kR], Qi[kR];
+};
+
+// eight taps of one polyphase branch; GUARD: stop at `left` taps (warp-uniform)
+template <bool GUARD>
+__device__ __forceinline__ void fir_steps(Acc &a, float2 (&W)[kR], float2 &nxt, float2 &c,
+                                          const float2 *__restrict__ tp, const float2 *__restrict__ xp,
+                                          int u_next, int left)
+{
+#pragma unroll
+    for (int s = 0; s < kR; s++) {
+        if (GUARD && s >= left)
+            break;
+        const float2 cc = c;
+        c = tp[s + 1]; // the tap array has one slack item behind it
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            const float2 x = W[(r - s) & (kR - 1)];
+            a.Pr[r] = __fmaf_rn(cc.x, x.x, a.Pr[r]);
+            a.Pi[r] = __fmaf_rn(cc.x, x.y, a.Pi[r]);
+            a.Qr[r] = __fmaf_rn(cc.y, x.x, a.Qr[r]);
+            a.Qi[r] = __fmaf_rn(cc.y, x.y, a.Qi[r]);
+        }
+        W[(kR - 1 - s) & (kR - 1)] = nxt;
+        nxt = xp[pad8(u_next - s)];
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int ntaps,
+           const float2 *__restrict__ taps_pm, const int *__restrict__ pass_a,
+           const int *__restrict__ pass_b, int nfreqs, const float2 *__restrict__ rot,
+           size_t rot_stride, float2 *__restrict__ out, size_t out_stride, int Mp)
+{
+    extern __shared__ float2 smem[];
+    float2 *tps = smem;                // [ntaps + 1] this pass's taps, polyphase-major
+    float2 *xs = smem + ntaps + 1;     // [D][Mp] input tile by residue mod D
+    constexpr int J = THREADS * kR;
+    const int tid = threadIdx.x;
+    const int src = blockIdx.y, pass = blockIdx.z;
+    const int jb = blockIdx.x * J;
+    const int jt = min(J, n - jb);
+
+    const float2 *tp_g = taps_pm + (size_t)pass * ntaps;
+    for (int k = tid; k < ntaps; k += THREADS)
+        tps[k] = tp_g[k];
+    if (tid == 0)
+        tps[ntaps] = make_float2(0.f, 0.f);
+
+    // stage items [jb*D, jb*D + (jt-1)*D + ntaps) of the row: item t -> xs[t % D][t / D + kFront]
+    const float2 *row = in + (size_t)src * in_stride + (size_t)jb * D;
+    const int T = (jt - 1) * D + ntaps;
+    {
+        int a = tid % D, m = tid / D;
+        const int da = THREADS % D, dm = THREADS / D;
+        for (int t = tid; t < T; t += THREADS) {
+            xs[a * Mp + pad8(m + kFront)] = row[t];
+            a += da;
+            m += dm;
+            if (a >= D) {
+                a -= D;
+                m++;
+            }
+        }
+    }
+    __syncthreads();
+
+    Acc acc;
+#pragma unroll
+    for (int r = 0; r < kR; r++)
+        acc.Pr[r] = acc.Pi[r] = acc.Qr[r] = acc.Qi[r] = 0.f;
+
+    const int r0 = tid * kR;
+    const float2 *tp = tps;
+    for (int p = 0; p < D; p++) {
+        const int lag = ntaps - 1 - p;
+        const int b_p = lag / D, a_p = lag - b_p * D;
+        const int Q = b_p + 1; // taps p, p+D, ... < ntaps
+        const float2 *xp = xs + a_p * Mp;
+        const int u0 = r0 + b_p + kFront; // window at tap 0: items u0 .. u0+7
+        float2 W[kR];
+#pragma unroll
+        for (int i = 0; i < kR; i++)
+            W[i] = xp[pad8(u0 + i)];
+        float2 nxt = xp[pad8(u0 - 1)];
+        float2 c = tp[0];
+        int q = 0;
+        for (; q + kR <= Q; q += kR)
+            fir_steps<false>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, kR);
+        if (q < Q)
+            fir_steps<true>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, Q - q);
+        tp += Q;
+    }
+
+    const int ka = pass_a[pass], kb = pass_b[pass];
+    float2 *oa = out + ((size_t)src * nfreqs + ka) * out_stride + jb + r0;
+    const float2 *ra = rot + (size_t)ka * rot_stride + jb + r0;
+#pragma unroll
+    for (int r = 0; r < kR; r++) {
+        if (r0 + r < jt) {
+            const float yr = acc.Pr[r] - acc.Qi[r], yi = acc.Pi[r] + acc.Qr[r];
+            const float2 ph = ra[r];
+            oa[r] = make_float2(yr * ph.x - yi * ph.y, yr * ph.y + yi * ph.x);
+        }
+    }
+    if (kb >= 0) {
+        float2 *ob = out + ((size_t)src * nfreqs + kb) * out_stride + jb + r0;
+        const float2 *rb = rot + (size_t)kb * rot_stride + jb + r0;
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            if (r0 + r < jt) {
+                const float yr = acc.Pr[r] + acc.Qi[r], yi = acc.Pi[r] - acc.Qr[r];
+                const float2 ph = rb[r];
+                ob[r] = make_float2(yr * ph.x - yi * ph.y, yr * ph.y + yi * ph.x);
+            }
+        }
+    }
+}
+
+size_t xlat_smem_bytes(int threads, int D, int ntaps, int *Mp_out)
+{
+    const int J = threads * kR;
+    const int M = J + (ntaps + D - 1) / D + kFront + 1;
+    const int Mp = pad8(M) + 1;
+    if (Mp_out)
+        *Mp_out = Mp;
+    return sizeof(float2) * ((size_t)ntaps + 1 + (size_t)D * Mp);
+}
+
+} // namespace
+
+// ======================================================== firdes::low_pass
+
+// gr::filter::firdes::low_pass(gain, fs, fc, tw, WIN_HAMMING) [G] (python/radio.py:49):
+// ntaps = (int)(53 fs / (22 tw)) made odd; float Hamming window; sinc * window evaluated in
+// double, stored as float; normalised to unit DC gain.  Init-time, host (as in the reference).
+extern "C" int b200ais_firdes_low_pass(double gain, double fs, double cutoff, double tw,
+                                       float *taps, int cap, int *ntaps_out)
+{
+    if (!(fs > 0) || !(cutoff > 0) || !(cutoff <= fs / 2) || !(tw > 0) || !ntaps_out) {
+        set_error("firdes_low_pass: need sampling_freq > 0, 0 < cutoff <= sampling_freq/2, width > 0");
+        return B200AIS_E_RANGE; // firdes::sanity_check_1f throws std::out_of_range
+    }
+    int ntaps = (int)(53.0 * fs / (22.0 * tw));
+    if ((ntaps & 1) == 0)
+        ntaps++;
+    *ntaps_out = ntaps;
+    if (!taps)
+        return B200AIS_OK;
+    if (cap < ntaps) {
+        set_error("firdes_low_pass: %d taps do not fit cap %d", ntaps, cap);
+        return B200AIS_E_INVALID;
+    }
+    const int M = (ntaps - 1) / 2;
+    const double fwT0 = 2 * M_PI * cutoff / fs;
+    for (int n = -M; n <= M; n++) {
+        const float w = (float)(0.54 - 0.46 * cos((2 * M_PI * (n + M)) / (ntaps - 1)));
+        if (n == 0)
+            taps[n + M] = (float)(fwT0 / M_PI * w);
+        else
+            taps[n + M] = (float)(sin(n * fwT0) / (n * M_PI) * w);
+    }
+    double fmax = taps[0 + M];
+    for (int n = 1; n <= M; n++)
+        fmax += 2 * taps[n + M];
+    gain /= fmax;
+    for (int i = 0; i < ntaps; i++)
+        taps[i] = (float)(taps[i] * gain);
+    return B200AIS_OK;
+}
+
+// ============================================= freq_xlating_fir_filter_ccf
+
+struct b200ais_xlat {
+    int D = 0, ntaps = 0, nfreqs = 0, sources = 0, npass = 0;
+    double fs = 0;
+    std::vector<float> proto;
+    std::vector<double> freqs;
+    std::vector<std::vector<float2>> ctaps; // [nfreqs][ntaps]
+    cudaStream_t stream = nullptr;
+    float2 *d_taps = nullptr; // [npass][ntaps] polyphase-major
+    int *d_pass = nullptr;    // [2][kMaxFreqs]
+    RotState *d_rot = nullptr;
+    DevBuf rottab, in, out;
+    bool dirty = true;
+};
+
+// build_composite_fir [G]: ctaps and the rotator increment of filter k
+static void xlat_compose(b200ais_xlat *h, int k, RotState *rs)
+{
+    const float fwT0 = (float)(2 * M_PI * h->freqs[k] / h->fs);
+    h->ctaps[k].resize(h->ntaps);
+    for (int i = 0; i < h->ntaps; i++) {
+        const float th = (float)i * fwT0;
+        h->ctaps[k][i] = make_float2(h->proto[i] * cosf(th), h->proto[i] * sinf(th));
+    }
+    const float th = -fwT0 * (float)h->D;
+    const float ir = cosf(th), ii = sinf(th);
+    const float a = (float)sqrt((double)ir * (double)ir + (double)ii * (double)ii);
+    rs->ir = ir / a; // rotator::set_phase_incr normalises
+    rs->ii = ii / a;
+}
+
+// group filters with conjugate taps into one pass, upload the taps polyphase-major
+static int xlat_upload(b200ais_xlat *h)
+{
+    const int K = h->nfreqs, nt = h->ntaps, D = h->D;
+    int pa[kMaxFreqs], pb[kMaxFreqs];
+    std::vector<char> used(K, 0);
+    int np = 0;
+    for (int k = 0; k < K; k++) {
+        if (used[k])
+            continue;
+        used[k] = 1;
+        pa[np] = k;
+        pb[np] = -1;
+        for (int k2 = k + 1; k2 < K && pb[np] < 0; k2++) {
+            if (used[k2])
+                continue;
+            bool conj = true;
+            for (int i = 0; i < nt && conj; i++)
+                conj = h->ctaps[k][i].x == h->ctaps[k2][i].x && h->ctaps[k][i].y == -h->ctaps[k2][i].y;
+            if (conj) {
+                pb[np] = k2;
+                used[k2] = 1;
+            }
+        }
+        np++;
+    }
+    h->npass = np;
+    std::vector<float2> pm((size_t)np * nt);
+    for (int p = 0; p < np; p++) {
+        size_t o = (size_t)p * nt;
+        for (int ph = 0; ph < D; ph++)
+            for (int k = ph; k < nt; k += D)
+                pm[o++] = h->ctaps[pa[p]][k];
+    }
+    if (h->d_taps)
+        cudaFree(h->d_taps);
+    h->d_taps = nullptr;
+    B200_CU(cudaMalloc(&h->d_taps, sizeof(float2) * pm.size()));
+    B200_CU(cudaMemcpy(h->d_taps, pm.data(), sizeof(float2) * pm.size(), cudaMemcpyHostToDevice));
+    int both[2 * kMaxFreqs];
+    memcpy(both, pa, sizeof(pa));
+    memcpy(both + kMaxFreqs, pb, sizeof(pb));
+    B200_CU(cudaMemcpy(h->d_pass, both, sizeof(both), cudaMemcpyHostToDevice));
+    h->dirty = false;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_xlat_create(b200ais_xlat **out, int decimation, const float *taps, int ntaps,
+                                   const double *center_freqs, int nfreqs, double sampling_freq,
+                                   int sources)
+{
+    if (!out || !taps || !center_freqs || decimation < 1 || ntaps < 1 || nfreqs < 1 ||
+        nfreqs > kMaxFreqs || sources < 1 || !(sampling_freq > 0)) {
+        set_error("xlat_create: bad arguments (1 <= nfreqs <= %d)", kMaxFreqs);
+        return B200AIS_E_INVALID;
+    }
+    if (xlat_smem_bytes(32, decimation, ntaps, nullptr) > 227 * 1024) {
+        set_error("xlat_create: decimation %d x %d taps does not fit shared memory", decimation, ntaps);
+        return B200AIS_E_INVALID;
+    }
+    b200ais_xlat *h = new (std::nothrow) b200ais_xlat;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->D = decimation;
+    h->ntaps = ntaps;
+    h->nfreqs = nfreqs;
+    h->sources = sources;
+    h->fs = sampling_freq;
+    h->proto.assign(taps, taps + ntaps);
+    h->freqs.assign(center_freqs, center_freqs + nfreqs);
+    h->ctaps.resize(nfreqs);
+    std::vector<RotState> rs(nfreqs);
+    for (int k = 0; k < nfreqs; k++) {
+        xlat_compose(h, k, &rs[k]);
+        rs[k].pr = 1.0f;
+        rs[k].pi = 0.0f;
+        rs[k].counter = 0;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_pass, sizeof(int) * 2 * kMaxFreqs);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_rot, sizeof(RotState) * nfreqs);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h->d_rot, rs.data(), sizeof(RotState) * nfreqs, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        b200ais_xlat_destroy(h);
+        return cuda_fail(e, "xlat_create", __FILE__, __LINE__);
+    }
+    int rc = xlat_upload(h);
+    if (rc) {
+        b200ais_xlat_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_xlat_destroy(b200ais_xlat *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    if (h->d_taps)
+        cudaFree(h->d_taps);
+    if (h->d_pass)
+        cudaFree(h->d_pass);
+    if (h->d_rot)
+        cudaFree(h->d_rot);
+    h->rottab.release();
+    h->in.release();
+    h->out.release();
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_xlat_history(const b200ais_xlat *h) { return h ? h->ntaps : 0; }
+extern "C" int b200ais_xlat_decimation(const b200ais_xlat *h) { return h ? h->D : 0; }
+
+// set_center_freq [G]: the composite taps and the rotator increment are rebuilt before the
+// next work(); the rotator keeps its phase and counter.
+extern "C" int b200ais_xlat_set_center_freq(b200ais_xlat *h, int k, double center_freq)
+{
+    if (!h || k < 0 || k >= h->nfreqs) {
+        set_error("xlat_set_center_freq: bad filter index");
+        return B200AIS_E_INVALID;
+    }
+    B200_CU(cudaDeviceSynchronize());
+    h->freqs[k] = center_freq;
+    RotState rs;
+    B200_CU(cudaMemcpy(&rs, h->d_rot + k, sizeof(rs), cudaMemcpyDeviceToHost));
+    xlat_compose(h, k, &rs);
+    B200_CU(cudaMemcpy(h->d_rot + k, &rs, sizeof(rs), cudaMemcpyHostToDevice));
+    return xlat_upload(h);
+}
+
+extern "C" int b200ais_xlat_set_taps(b200ais_xlat *h, const float *taps, int ntaps)
+{
+    if (!h || !taps || ntaps < 1 || xlat_smem_bytes(32, h->D, ntaps, nullptr) > 227 * 1024) {
+        set_error("xlat_set_taps: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    B200_CU(cudaDeviceSynchronize());
+    h->ntaps = ntaps;
+    h->proto.assign(taps, taps + ntaps);
+    std::vector<RotState> rs(h->nfreqs);
+    B200_CU(cudaMemcpy(rs.data(), h->d_rot, sizeof(RotState) * h->nfreqs, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < h->nfreqs; k++)
+        xlat_compose(h, k, &rs[k]);
+    B200_CU(cudaMemcpy(h->d_rot, rs.data(), sizeof(RotState) * h->nfreqs, cudaMemcpyHostToDevice));
+    return xlat_upload(h);
+}
+
+extern "C" int b200ais_xlat_reset(b200ais_xlat *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    B200_CU(cudaDeviceSynchronize());
+    std::vector<RotState> rs(h->nfreqs);
+    B200_CU(cudaMemcpy(rs.data(), h->d_rot, sizeof(RotState) * h->nfreqs, cudaMemcpyDeviceToHost));
+    for (auto &r : rs) {
+        r.pr = 1.0f;
+        r.pi = 0.0f;
+        r.counter = 0;
+    }
+    B200_CU(cudaMemcpy(h->d_rot, rs.data(), sizeof(RotState) * h->nfreqs, cudaMemcpyHostToDevice));
+    return B200AIS_OK;
+}
+
+template <int THREADS>
+static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_stride, float2 *out,
+                       size_t out_stride, int Mp, size_t smem, cudaStream_t s)
+{
+    static bool attr_set[8] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 8 && !attr_set[dev]) {
+        B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+        attr_set[dev] = true;
+    } else if (dev >= 8) {
+        B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    }
+    const int J = THREADS * kR;
+    dim3 grid((unsigned)((n + J - 1) / J), (unsigned)h->sources, (unsigned)h->npass);
+    k_xlat_fir<THREADS><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps, h->d_taps,
+                                                    h->d_pass, h->d_pass + kMaxFreqs, h->nfreqs,
+                                                    h->rottab.as<float2>(), (size_t)n, out,
+                                                    out_stride, Mp);
+    B200_LAUNCH_CHECK("k_xlat_fir");
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const float *in,
+                                     size_t in_stride, float *out, size_t out_stride, void *stream)
+{
+    if (!h || !in || !out || noutput_items < 0 || (size_t)noutput_items > out_stride ||
+        (noutput_items > 0 && (size_t)noutput_items * h->D + h->ntaps - 1 > in_stride)) {
+        set_error("xlat_work: bad arguments (rows need ntaps-1 + noutput*decimation items)");
+        return B200AIS_E_INVALID;
+    }
+    if (h->sources > 65535) {
+        set_error("xlat_work: at most 65535 sources per call");
+        return B200AIS_E_INVALID;
+    }
+    if (noutput_items == 0)
+        return B200AIS_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n = noutput_items;
+    int rc = h->rottab.reserve(sizeof(float2) * (size_t)n * h->nfreqs);
+    if (rc)
+        return rc;
+    k_rot_phase<<<1, 32, 0, s>>>(h->d_rot, h->nfreqs, n, h->rottab.as<float2>(), (size_t)n);
+    B200_LAUNCH_CHECK("k_rot_phase");
+    const float2 *x = reinterpret_cast<const float2 *>(in);
+    float2 *y = reinterpret_cast<float2 *>(out);
+    int Mp = 0;
+    // largest tile that leaves room for at least two CTAs per SM, else whatever fits
+    const int cand[3] = {128, 64, 32};
+    int pick = -1;
+    for (int i = 0; i < 3 && pick < 0; i++)
+        if (xlat_smem_bytes(cand[i], h->D, h->ntaps, nullptr) <= 113 * 1024)
+            pick = cand[i];
+    for (int i = 0; i < 3 && pick < 0; i++)
+        if (xlat_smem_bytes(cand[i], h->D, h->ntaps, nullptr) <= 227 * 1024)
+            pick = cand[i];
+    const size_t smem = xlat_smem_bytes(pick, h->D, h->ntaps, &Mp);
+    switch (pick) {
+    case 128:
+        return xlat_launch<128>(h, n, x, in_stride, y, out_stride, Mp, smem, s);
+    case 64:
+        return xlat_launch<64>(h, n, x, in_stride, y, out_stride, Mp, smem, s);
+    default:
+        return xlat_launch<32>(h, n, x, in_stride, y, out_stride, Mp, smem, s);
+    }
+}
+
+extern "C" int b200ais_xlat_work(b200ais_xlat *h, int noutput_items, const float *in,
+                                 size_t in_stride, float *out, size_t out_stride)
+{
+    if (!h || !in || !out || noutput_items < 0) {
+        set_error("xlat_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    if (noutput_items == 0)
+        return B200AIS_OK;
+    const size_t nin = (size_t)noutput_items * h->D + h->ntaps - 1;
+    if (nin > in_stride || (size_t)noutput_items > out_stride) {
+        set_error("xlat_work: rows need ntaps-1 + noutput*decimation input items");
+        return B200AIS_E_INVALID;
+    }
+    const size_t dis = (nin + 1) & ~(size_t)1, dos = ((size_t)noutput_items + 1) & ~(size_t)1;
+    const size_t rows_out = (size_t)h->sources * h->nfreqs;
+    int rc;
+    if ((rc = h->in.reserve(sizeof(float2) * dis * h->sources)) ||
+        (rc = h->out.reserve(sizeof(float2) * dos * rows_out)))
+        return rc;
+    cudaStream_t s = h->stream;
+    B200_CU(cudaMemcpy2DAsync(h->in.p, dis * sizeof(float2), in, in_stride * sizeof(float2),
+                              nin * sizeof(float2), (size_t)h->sources, cudaMemcpyHostToDevice, s));
+    rc = b200ais_xlat_work_dev(h, noutput_items, h->in.as<float>(), dis, h->out.as<float>(), dos, s);
+    if (rc)
+        return rc;
+    B200_CU(cudaMemcpy2DAsync(out, out_stride * sizeof(float2), h->out.p, dos * sizeof(float2),
+                              (size_t)noutput_items * sizeof(float2), rows_out,
+                              cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaStreamSynchronize(s));
+    return B200AIS_OK;
+}

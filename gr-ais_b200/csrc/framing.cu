@@ -1,0 +1,467 @@
+// framing.cu -- the step after the demod path in the reference's receiver
+// (python/radio.py:64-72): digital.hdlc_deframer_bp(11, 64) and gr::ais::pdu_to_nmea
+// (lib/pdu_to_nmea_impl.cc:63-131), batched over channels, with their C-ABI.
+//
+// Byte/integer work on a 9600 bit/s stream per channel: one lane per channel walks its row of
+// unpacked bits 16 at a time (one 128-bit load), the partial frame lives in the lane's local
+// memory between delimiters, and the per-channel deframer state is carried in HBM between calls.
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+using namespace b200ais;
+
+namespace {
+
+struct HdlcState {
+    int ones, bitctr, bytectr, pad;
+    unsigned long long nitems_read;
+    unsigned char pktbuf[B200AIS_FRAME_MAX + 8];
+};
+
+// hdlc_deframer_bp_impl::crc_ccitt [G]: CRC-16/X.25
+__device__ __forceinline__ unsigned crc_ccitt(const unsigned char *d, int len)
+{
+    unsigned crc = 0xFFFFu;
+    for (int i = 0; i < len; i++) {
+        crc ^= d[i];
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            crc = (crc & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
+    }
+    return (crc ^ 0xFFFFu) & 0xFFFFu;
+}
+
+struct Deframer {
+    int ones, bitctr, bytectr;
+    int length_min, length_max;
+    unsigned char buf[B200AIS_FRAME_MAX + 8];
+    b200ais_frame *frames;
+    int max_frames, nf, channel;
+    unsigned long long base;
+    bool overflow;
+
+    // hdlc_deframer_bp_impl::work [G], one bit
+    __device__ __forceinline__ void step(unsigned bit, int i)
+    {
+        if (ones >= 5) {
+            if (bit) { // six ones: frame delimiter
+                if (bytectr >= length_min) {
+                    const int len = bytectr - 2;
+                    const unsigned crc = crc_ccitt(buf, len);
+                    const unsigned got = (unsigned)buf[len] | ((unsigned)buf[len + 1] << 8);
+                    if (crc == got) {
+                        if (nf < max_frames) {
+                            b200ais_frame *f = frames + nf;
+                            f->end_bit = base + (unsigned long long)i;
+                            f->len = len;
+                            f->channel = channel;
+                            for (int k = 0; k < len; k++)
+                                f->data[k] = buf[k];
+                            for (int k = len; k < B200AIS_FRAME_MAX; k++)
+                                f->data[k] = 0;
+                            nf++;
+                        } else {
+                            overflow = true;
+                        }
+                    }
+                }
+                bitctr = 0;
+                bytectr = 0;
+            } // else: stuffed zero, dropped
+        } else if (bytectr > length_max) {
+            bytectr = 0;
+            bitctr = 0;
+        } else {
+            unsigned v = buf[bytectr] >> 1;
+            if (bit)
+                v |= 0x80u;
+            buf[bytectr] = (unsigned char)v;
+            if (++bitctr == 8) {
+                bitctr = 0;
+                bytectr++;
+            }
+        }
+        ones = bit ? ones + 1 : 0;
+    }
+};
+
+__global__ void __launch_bounds__(64)
+k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restrict__ nbits,
+       int nbits_all, int channels, HdlcState *__restrict__ state, int length_min, int length_max,
+       b200ais_frame *__restrict__ frames, int max_frames, int *__restrict__ nframes, int *status)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels)
+        return;
+    HdlcState *st = state + c;
+    Deframer d;
+    d.ones = st->ones;
+    d.bitctr = st->bitctr;
+    d.bytectr = st->bytectr;
+    d.length_min = length_min;
+    d.length_max = length_max;
+    d.frames = frames + (size_t)c * max_frames;
+    d.max_frames = max_frames;
+    d.nf = 0;
+    d.channel = c;
+    d.base = st->nitems_read;
+    d.overflow = false;
+    for (int k = 0; k < B200AIS_FRAME_MAX + 8; k++)
+        d.buf[k] = st->pktbuf[k];
+
+    const int n = nbits ? nbits[c] : nbits_all;
+    const uint8_t *row = bits + (size_t)c * bits_stride;
+    int i = 0;
+    while (i < n && ((reinterpret_cast<uintptr_t>(row + i)) & 15))
+        d.step(row[i] & 1u, i), i++;
+    for (; i + 16 <= n; i += 16) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(row + i);
+        const unsigned v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                d.step((v[q] >> (8 * b)) & 1u, i + 4 * q + b);
+    }
+    for (; i < n; i++)
+        d.step(row[i] & 1u, i);
+
+    st->ones = d.ones;
+    st->bitctr = d.bitctr;
+    st->bytectr = d.bytectr;
+    st->nitems_read = d.base + (unsigned long long)(n > 0 ? n : 0);
+    for (int k = 0; k < B200AIS_FRAME_MAX + 8; k++)
+        st->pktbuf[k] = d.buf[k];
+    nframes[c] = d.nf;
+    if (d.overflow)
+        atomicExch(status, B200AIS_E_FRAME_OVERFLOW);
+}
+
+__device__ __forceinline__ int put_int(char *o, int v)
+{
+    char tmp[12];
+    int n = 0;
+    if (v == 0)
+        tmp[n++] = '0';
+    while (v > 0) {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    }
+    for (int k = 0; k < n; k++)
+        o[k] = tmp[n - 1 - k];
+    return n;
+}
+
+// pdu_to_nmea_impl::msg_to_sentence (lib/pdu_to_nmea_impl.cc:63-131), one lane per frame.
+__global__ void __launch_bounds__(128)
+k_nmea(const b200ais_frame *__restrict__ frames, const int *__restrict__ nframes, int channels,
+       int max_frames, const char *__restrict__ designators, char *__restrict__ sentences, int slot,
+       int *__restrict__ lens)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= channels * max_frames)
+        return;
+    const int c = idx / max_frames, f = idx - c * max_frames;
+    if (f >= nframes[c]) {
+        lens[idx] = 0;
+        return;
+    }
+    const b200ais_frame *fr = frames + idx;
+    char *out = sentences + (size_t)idx * slot;
+    const int len = fr->len;
+    if (len < 1 || len > B200AIS_FRAME_MAX) {
+        lens[idx] = 0;
+        return;
+    }
+    char des[8];
+    int dl = 0;
+    if (designators) {
+        for (; dl < 8 && designators[c * 8 + dl]; dl++)
+            des[dl] = designators[c * 8 + dl];
+    } else {
+        des[0] = 'A';
+        dl = 1;
+    }
+    const int nbits = len * 8;
+    const int npad = (6 - (nbits % 6)) % 6;          // :67
+    const int nchar = (nbits + npad) / 6;
+    const int num_frags = 1 + ((nchar - 1) / 56);    // :103-104
+    if (num_frags * (22 + dl) + nchar > slot) {      // would not fit the caller's slot
+        lens[idx] = -1;
+        return;
+    }
+    int pos = 0, ch = 0;
+    for (int frag = 1; frag <= num_frags; frag++) {
+        if (frag > 1)
+            out[pos++] = '\n';
+        const int start = pos;
+        const char head[7] = {'!', 'A', 'I', 'V', 'D', 'M', ','};
+        for (int k = 0; k < 7; k++)
+            out[pos++] = head[k];
+        pos += put_int(out + pos, num_frags);
+        out[pos++] = ',';
+        pos += put_int(out + pos, frag);
+        out[pos++] = ',';
+        out[pos++] = ',';
+        for (int k = 0; k < dl; k++)
+            out[pos++] = des[k];
+        out[pos++] = ',';
+        const int fl = min(56, nchar - ch);
+        for (int k = 0; k < fl; k++, ch++) {
+            // unpack_bits :63-79: six bits MSB first starting at bit 6*ch
+            unsigned v = 0;
+            for (int b = 0; b < 6; b++) {
+                const int i = 6 * ch + b;
+                if (i < nbits)
+                    v |= ((fr->data[i >> 3] >> (7 - (i & 7))) & 1u) << (5 - b);
+            }
+            if (npad && ch == nbits / 6)
+                v = (v << npad) & 0xFFu; // :75-77 shifts the left-aligned group again (uint8_t)
+            // to_ascii :81-88 on (signed) char
+            int sc = (int)(signed char)v;
+            if (sc > 39)
+                sc = (int)(signed char)(sc + 8);
+            sc = (int)(signed char)(sc + 48);
+            out[pos++] = (char)sc;
+        }
+        out[pos++] = ',';
+        pos += put_int(out + pos, npad);
+        unsigned sum = 0; // get_checksum :90-96
+        for (int k = start + 1; k < pos; k++)
+            sum ^= (unsigned char)out[k];
+        const char hex[17] = "0123456789ABCDEF";
+        out[pos++] = '*';
+        out[pos++] = hex[(sum >> 4) & 15];
+        out[pos++] = hex[sum & 15];
+    }
+    if (pos < slot)
+        out[pos] = 0;
+    lens[idx] = pos;
+}
+
+} // namespace
+
+// =========================================================== hdlc_deframer_bp
+
+struct b200ais_hdlc {
+    int channels = 0, length_min = 0, length_max = 0;
+    cudaStream_t stream = nullptr;
+    HdlcState *d_state = nullptr;
+    int *d_status = nullptr;
+    DevBuf bits, nbits, frames, nframes;
+};
+
+extern "C" int b200ais_hdlc_create(b200ais_hdlc **out, int length_min, int length_max, int channels)
+{
+    if (!out || channels < 1 || length_min < 2 || length_max < length_min ||
+        length_max > B200AIS_FRAME_MAX - 2) {
+        set_error("hdlc_create: need channels >= 1 and 2 <= length_min <= length_max <= %d",
+                  B200AIS_FRAME_MAX - 2);
+        return B200AIS_E_INVALID;
+    }
+    b200ais_hdlc *h = new (std::nothrow) b200ais_hdlc;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->channels = channels;
+    h->length_min = length_min;
+    h->length_max = length_max;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_state, sizeof(HdlcState) * (size_t)channels);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&h->d_status, sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaMemset(h->d_state, 0, sizeof(HdlcState) * (size_t)channels);
+    if (e == cudaSuccess)
+        e = cudaMemset(h->d_status, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        b200ais_hdlc_destroy(h);
+        return cuda_fail(e, "hdlc_create", __FILE__, __LINE__);
+    }
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_hdlc_destroy(b200ais_hdlc *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    if (h->d_state)
+        cudaFree(h->d_state);
+    if (h->d_status)
+        cudaFree(h->d_status);
+    h->bits.release();
+    h->nbits.release();
+    h->frames.release();
+    h->nframes.release();
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_hdlc_reset(b200ais_hdlc *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    B200_CU(cudaDeviceSynchronize());
+    B200_CU(cudaMemset(h->d_state, 0, sizeof(HdlcState) * (size_t)h->channels));
+    B200_CU(cudaMemset(h->d_status, 0, sizeof(int)));
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_hdlc_work_dev(b200ais_hdlc *h, const uint8_t *bits, size_t bits_stride,
+                                     const int *nbits, int nbits_all, b200ais_frame *frames,
+                                     int max_frames, int *nframes, void *stream)
+{
+    if (!h || !bits || !frames || !nframes || max_frames < 1 || (!nbits && nbits_all < 0)) {
+        set_error("hdlc_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int threads = 64;
+    k_hdlc<<<(h->channels + threads - 1) / threads, threads, 0, s>>>(
+        bits, bits_stride, nbits, nbits_all, h->channels, h->d_state, h->length_min, h->length_max,
+        frames, max_frames, nframes, h->d_status);
+    B200_LAUNCH_CHECK("k_hdlc");
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_hdlc_status(b200ais_hdlc *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    int st = 0;
+    B200_CU(cudaMemcpy(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        B200_CU(cudaMemset(h->d_status, 0, sizeof(int)));
+        set_error("a channel produced more HDLC frames than max_frames");
+    }
+    return st;
+}
+
+extern "C" int b200ais_hdlc_work(b200ais_hdlc *h, const uint8_t *bits, size_t bits_stride,
+                                 const int *nbits, int nbits_all, b200ais_frame *frames,
+                                 int max_frames, int *nframes)
+{
+    if (!h || !bits || !frames || !nframes || max_frames < 1 || (!nbits && nbits_all < 0)) {
+        set_error("hdlc_work: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    const int C = h->channels;
+    int maxn = nbits_all;
+    if (nbits) {
+        maxn = 0;
+        for (int c = 0; c < C; c++) {
+            if (nbits[c] < 0 || (size_t)nbits[c] > bits_stride) {
+                set_error("hdlc_work: nbits[%d] outside the row", c);
+                return B200AIS_E_INVALID;
+            }
+            maxn = nbits[c] > maxn ? nbits[c] : maxn;
+        }
+    } else if ((size_t)nbits_all > bits_stride) {
+        set_error("hdlc_work: nbits_all outside the row");
+        return B200AIS_E_INVALID;
+    }
+    const size_t dstride = ((size_t)maxn + 15) / 16 * 16 + 16;
+    int rc;
+    if ((rc = h->bits.reserve(dstride * C)) || (rc = h->nbits.reserve(sizeof(int) * C)) ||
+        (rc = h->frames.reserve(sizeof(b200ais_frame) * (size_t)C * max_frames)) ||
+        (rc = h->nframes.reserve(sizeof(int) * C)))
+        return rc;
+    cudaStream_t s = h->stream;
+    if (maxn > 0)
+        B200_CU(cudaMemcpy2DAsync(h->bits.p, dstride, bits, bits_stride, (size_t)maxn, (size_t)C,
+                                  cudaMemcpyHostToDevice, s));
+    if (nbits)
+        B200_CU(cudaMemcpyAsync(h->nbits.p, nbits, sizeof(int) * C, cudaMemcpyHostToDevice, s));
+    rc = b200ais_hdlc_work_dev(h, h->bits.as<uint8_t>(), dstride, nbits ? h->nbits.as<int>() : nullptr,
+                               nbits_all, h->frames.as<b200ais_frame>(), max_frames,
+                               h->nframes.as<int>(), s);
+    if (rc)
+        return rc;
+    B200_CU(cudaMemcpyAsync(nframes, h->nframes.p, sizeof(int) * C, cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaStreamSynchronize(s));
+    // copy only the frames that exist
+    for (int c = 0; c < C; c++)
+        if (nframes[c] > 0)
+            B200_CU(cudaMemcpyAsync(frames + (size_t)c * max_frames,
+                                    h->frames.as<b200ais_frame>() + (size_t)c * max_frames,
+                                    sizeof(b200ais_frame) * (size_t)nframes[c],
+                                    cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaStreamSynchronize(s));
+    return b200ais_hdlc_status(h);
+}
+
+// ================================================================ pdu_to_nmea
+
+extern "C" int b200ais_nmea_slot_bytes(int max_len, const char *designator)
+{
+    if (max_len < 1 || max_len > B200AIS_FRAME_MAX)
+        return B200AIS_E_INVALID;
+    const int dl = designator ? (int)strnlen(designator, 8) : 1;
+    const int nchar = (max_len * 8 + 5) / 6;
+    const int frags = 1 + (nchar - 1) / 56;
+    // "\n!AIVDM," + 2 x up to 2 digits + ",,," + designator + "," + npad + "*XX"
+    const int per = 1 + 7 + 2 + 1 + 2 + 2 + dl + 1 + 1 + 1 + 3;
+    return (frags * per + nchar + 1 + 15) / 16 * 16;
+}
+
+extern "C" int b200ais_nmea_format_dev(const b200ais_frame *frames, const int *nframes, int channels,
+                                       int max_frames, const char *designators, char *sentences,
+                                       int slot, int *lens, void *stream)
+{
+    if (!frames || !nframes || !sentences || !lens || channels < 1 || max_frames < 1 ||
+        slot < 32) {
+        set_error("nmea_format: bad arguments (slot: see b200ais_nmea_slot_bytes)");
+        return B200AIS_E_INVALID;
+    }
+    const long total = (long)channels * max_frames;
+    k_nmea<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        frames, nframes, channels, max_frames, designators, sentences, slot, lens);
+    B200_LAUNCH_CHECK("k_nmea");
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_nmea_format(const b200ais_frame *frames, const int *nframes, int channels,
+                                   int max_frames, const char *designators, char *sentences,
+                                   int slot, int *lens)
+{
+    if (!frames || !nframes || !sentences || !lens || channels < 1 || max_frames < 1) {
+        set_error("nmea_format: bad arguments");
+        return B200AIS_E_INVALID;
+    }
+    const size_t nf = (size_t)channels * max_frames;
+    void *d_frames = nullptr, *d_nframes = nullptr, *d_des = nullptr, *d_sent = nullptr,
+         *d_lens = nullptr;
+    int rc = B200AIS_OK;
+    cudaError_t e = cudaMalloc(&d_frames, nf * sizeof(b200ais_frame));
+    if (e == cudaSuccess) e = cudaMalloc(&d_nframes, sizeof(int) * channels);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sent, nf * (size_t)slot);
+    if (e == cudaSuccess) e = cudaMalloc(&d_lens, nf * sizeof(int));
+    if (e == cudaSuccess && designators) e = cudaMalloc(&d_des, (size_t)channels * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_frames, frames, nf * sizeof(b200ais_frame), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_nframes, nframes, sizeof(int) * channels, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && designators)
+        e = cudaMemcpy(d_des, designators, (size_t)channels * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = b200ais_nmea_format_dev((const b200ais_frame *)d_frames, (const int *)d_nframes, channels,
+                                     max_frames, (const char *)d_des, (char *)d_sent, slot,
+                                     (int *)d_lens, nullptr);
+        if (!rc) {
+            e = cudaMemcpy(sentences, d_sent, nf * (size_t)slot, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(lens, d_lens, nf * sizeof(int), cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(d_frames);
+    cudaFree(d_nframes);
+    cudaFree(d_des);
+    cudaFree(d_sent);
+    cudaFree(d_lens);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "nmea_format", __FILE__, __LINE__);
+    return rc;
+}

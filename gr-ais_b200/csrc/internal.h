@@ -31,6 +31,32 @@ void count_launch(int n = 1);
             return ::b200ais::cuda_fail(e__, name, __FILE__, __LINE__);         \
     } while (0)
 
+// ---- small device-buffer helper: grow-only scratch owned by a handle ----
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap)
+            return B200AIS_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        B200_CU(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return B200AIS_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
 // Regenerated GNU Radio data tables, resident in global memory of the current device.
 struct Tables {
     const float *mmse; // [129][8]  mmse_fir_interpolator taps

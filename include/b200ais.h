@@ -19,6 +19,14 @@
  *   b200ais_demod_*      ais_demod hier-block            python/ais_demod.py:21-56 with
  *                        + square_and_fft_sync_cc        python/gmsk_sync.py:14-37 fused in
  *
+ * and, either side of that path inside the reference's ais_rx receiver (python/radio.py:39-72):
+ *
+ *   b200ais_firdes_low_pass  filter.firdes.low_pass      python/radio.py:49
+ *   b200ais_xlat_*       filter.freq_xlating_fir_filter_ccf  python/radio.py:51-54
+ *   b200ais_hdlc_*       digital.hdlc_deframer_bp(11,64) python/radio.py:64
+ *   b200ais_nmea_*       gr::ais::pdu_to_nmea            include/ais/pdu_to_nmea.h:37-54,
+ *                                                        lib/pdu_to_nmea_impl.cc:63-131
+ *
  * The *_work functions mirror one GNU Radio work()/general_work() call, batched
  * over `channels` independent streams (the GR adapter calls with channels = 1).
  * Host-pointer variants copy to/from the device inside the call; *_dev variants
@@ -57,7 +65,8 @@ enum {
     B200AIS_E_NOMEM = -4,
     B200AIS_E_TAG_OVERFLOW = -5, /* more tags than max_tags on some channel */
     B200AIS_E_INTERP = -6,       /* mmse interpolator index out of [0,128] (reference: runtime_error) */
-    B200AIS_E_OUT_OVERFLOW = -7  /* an output row was too small */
+    B200AIS_E_OUT_OVERFLOW = -7, /* an output row was too small */
+    B200AIS_E_FRAME_OVERFLOW = -8 /* more HDLC frames than max_frames on some channel */
 };
 
 /* stream-tag keys emitted by corr_est_cc (lib/corr_est_cc_impl.cc:213-256) */
@@ -288,6 +297,78 @@ B200AIS_API int b200ais_demod_enable_taps(b200ais_demod *h, int enable);
 B200AIS_API int b200ais_demod_tap(b200ais_demod *h, int which, void **dev_ptr, size_t *row_items);
 /* copy a tap to host: dst holds channels*row_items items of the tap's type */
 B200AIS_API int b200ais_demod_read_tap(b200ais_demod *h, int which, void *dst, size_t dst_bytes);
+
+/* ------------------- channeliser: firdes.low_pass + freq_xlating_fir_filter_ccf */
+/* firdes::low_pass(gain, sampling_freq, cutoff, transition_width) with the default Hamming
+ * window (python/radio.py:49); init-time, host.  taps == NULL returns the tap count in *ntaps. */
+B200AIS_API int b200ais_firdes_low_pass(double gain, double sampling_freq, double cutoff_freq,
+                                        double transition_width, float *taps, int cap, int *ntaps);
+
+typedef struct b200ais_xlat b200ais_xlat;
+/* `nfreqs` freq_xlating_fir_filter_ccf(decimation, taps, center_freqs[k], sampling_freq) blocks
+ * fed by the same input (python/radio.py:86-91: the A and B rx paths share one source), for
+ * `sources` independent wideband inputs.  Output channel s*nfreqs + k is source s translated
+ * by center_freqs[k]. */
+B200AIS_API int b200ais_xlat_create(b200ais_xlat **h, int decimation, const float *taps, int ntaps,
+                                    const double *center_freqs, int nfreqs, double sampling_freq,
+                                    int sources);
+B200AIS_API int b200ais_xlat_destroy(b200ais_xlat *h);
+B200AIS_API int b200ais_xlat_history(const b200ais_xlat *h);    /* ntaps */
+B200AIS_API int b200ais_xlat_decimation(const b200ais_xlat *h);
+B200AIS_API int b200ais_xlat_set_center_freq(b200ais_xlat *h, int k, double center_freq);
+B200AIS_API int b200ais_xlat_set_taps(b200ais_xlat *h, const float *taps, int ntaps);
+/* back to freshly constructed rotators (phase 1, counter 0) */
+B200AIS_API int b200ais_xlat_reset(b200ais_xlat *h);
+/* One work() call.  in: [sources][in_stride] complex, each row ntaps-1 history items followed
+ * by noutput_items*decimation new ones (what GNU Radio hands work()); out:
+ * [sources*nfreqs][out_stride] complex, noutput_items per row.  The rotators advance. */
+B200AIS_API int b200ais_xlat_work(b200ais_xlat *h, int noutput_items, const float *in,
+                                  size_t in_stride, float *out, size_t out_stride);
+B200AIS_API int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const float *in,
+                                      size_t in_stride, float *out, size_t out_stride,
+                                      void *stream);
+
+/* -------------------------------------------------- hdlc_deframer_bp + CRC */
+#define B200AIS_FRAME_MAX 248
+/* one PDU published by hdlc_deframer_bp: pmt::cons(PMT_NIL, blob(data, len)) */
+typedef struct b200ais_frame {
+    uint64_t end_bit; /* absolute index, in the channel's bit stream, of the bit that completed
+                         the closing flag */
+    int32_t len;      /* payload bytes, CRC removed */
+    int32_t channel;  /* row of the bit stream it came from */
+    uint8_t data[B200AIS_FRAME_MAX];
+} b200ais_frame;
+
+typedef struct b200ais_hdlc b200ais_hdlc;
+/* hdlc_deframer_bp(length_min, length_max) for `channels` bit streams (python/radio.py:64) */
+B200AIS_API int b200ais_hdlc_create(b200ais_hdlc **h, int length_min, int length_max, int channels);
+B200AIS_API int b200ais_hdlc_destroy(b200ais_hdlc *h);
+B200AIS_API int b200ais_hdlc_reset(b200ais_hdlc *h);
+/* One work() call.  bits: [channels][bits_stride] unpacked 0/1 bytes, nbits[c] valid items in
+ * row c (nbits == NULL: nbits_all on every row); frames: [channels][max_frames]; nframes:
+ * [channels].  The deframer state (run of ones, partial frame) carries to the next call. */
+B200AIS_API int b200ais_hdlc_work(b200ais_hdlc *h, const uint8_t *bits, size_t bits_stride,
+                                  const int *nbits, int nbits_all, b200ais_frame *frames,
+                                  int max_frames, int *nframes);
+B200AIS_API int b200ais_hdlc_work_dev(b200ais_hdlc *h, const uint8_t *bits, size_t bits_stride,
+                                      const int *nbits, int nbits_all, b200ais_frame *frames,
+                                      int max_frames, int *nframes, void *stream);
+/* after a *_dev call has completed: 0 or B200AIS_E_FRAME_OVERFLOW */
+B200AIS_API int b200ais_hdlc_status(b200ais_hdlc *h);
+
+/* ------------------------------------------------------------ pdu_to_nmea */
+/* bytes one frame's sentence(s) can take for payloads up to max_len bytes and this designator */
+B200AIS_API int b200ais_nmea_slot_bytes(int max_len, const char *designator);
+/* pdu_to_nmea::msg_to_sentence (lib/pdu_to_nmea_impl.cc:127-131) for every frame:
+ * frames [channels][max_frames], nframes [channels]; designators: [channels][8] NUL-padded
+ * strings (NULL: "A" everywhere); sentences: [channels][max_frames][slot] characters (fragments
+ * joined by '\n', NUL-terminated when room), lens: [channels][max_frames]. */
+B200AIS_API int b200ais_nmea_format(const b200ais_frame *frames, const int *nframes, int channels,
+                                    int max_frames, const char *designators, char *sentences,
+                                    int slot, int *lens);
+B200AIS_API int b200ais_nmea_format_dev(const b200ais_frame *frames, const int *nframes,
+                                        int channels, int max_frames, const char *designators,
+                                        char *sentences, int slot, int *lens, void *stream);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@
 #ifndef AIS_ORACLE_H
 #define AIS_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -225,6 +226,46 @@ int ao_stream_set_symbols(ao_stream *s, const float *symbols, int L);
 /* bits/tags of this call only; returns 0 or a negative status */
 int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_bits, int *nbits,
                    ao_tag *tags_out, int max_tags, int *ntags_out);
+
+/* ======== the blocks either side of the path (python/radio.py:39-72), ais_oracle_rx.c ======== */
+
+/* ---- digital.hdlc_deframer_bp [G] ---- */
+#define AO_FRAME_MAX 248
+typedef struct ao_frame {
+    uint64_t end_bit; /* absolute index of the bit that completed the closing flag */
+    int32_t len;      /* payload bytes (CRC removed) */
+    int32_t channel;  /* unused by the single-stream oracle (0) */
+    uint8_t data[AO_FRAME_MAX];
+} ao_frame;
+typedef struct ao_hdlc {
+    int length_min, length_max;
+    int ones, bitctr, bytectr, pad;
+    uint64_t nitems_read;
+    uint8_t pktbuf[AO_FRAME_MAX + 8];
+} ao_hdlc;
+unsigned ao_crc_ccitt(const uint8_t *data, size_t len);
+void ao_hdlc_init(ao_hdlc *h, int length_min, int length_max);
+int ao_hdlc_work(ao_hdlc *h, const uint8_t *bits, int n, ao_frame *frames, int max_frames,
+                 int *dropped);
+
+/* ---- gr::ais::pdu_to_nmea (lib/pdu_to_nmea_impl.cc:63-131) [R] ---- */
+int ao_pdu_to_nmea(const char *designator, const uint8_t *data, int len, char *out, int cap);
+
+/* ---- firdes.low_pass + freq_xlating_fir_filter_ccf (python/radio.py:49-54) [G] ---- */
+int ao_firdes_low_pass(double gain, double fs, double cutoff, double tw, float *taps, int cap);
+typedef struct ao_xlat {
+    int decim, ntaps;
+    float *ctaps; /* [ntaps] complex band-pass taps */
+    float incr_re, incr_im, phase_re, phase_im;
+    unsigned counter;
+} ao_xlat;
+int ao_xlat_init(ao_xlat *x, int decimation, const float *taps, int ntaps, double center_freq,
+                 double sampling_freq);
+void ao_xlat_free(ao_xlat *x);
+int ao_xlat_work(ao_xlat *x, int noutput, const float *in, float *out, float *fir_out);
+void ao_xlat_f64(int decimation, const float *taps, int ntaps, double center_freq,
+                 double sampling_freq, uint64_t first_output, int noutput, const float *in,
+                 double *out);
 
 #ifdef __cplusplus
 }

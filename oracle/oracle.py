@@ -63,7 +63,7 @@ class ChainOut(C.Structure):
 
 def build(force=False):
     """Compile the oracle with oracle/Makefile (gcc only; seconds)."""
-    src = [os.path.join(_HERE, f) for f in ("ais_oracle.c", "ais_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("ais_oracle.c", "ais_oracle_rx.c", "ais_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return _LIB_PATH
@@ -501,3 +501,123 @@ def demod_chain_batch(x, symbols, cfg=None, max_tags=256, nthreads=0):
     if rc:
         raise RuntimeError("ao_demod_chain_batch failed: %d" % rc)
     return bits, nbits, tags, ntags
+
+
+# ------------------------------------------- rx rows (ais_oracle_rx.c)
+
+FRAME_MAX = 248
+FRAME_DTYPE = np.dtype([("end_bit", "<u8"), ("len", "<i4"), ("channel", "<i4"),
+                        ("data", "u1", (FRAME_MAX,))])
+
+
+class Hdlc(C.Structure):
+    _fields_ = [("length_min", C.c_int), ("length_max", C.c_int), ("ones", C.c_int),
+                ("bitctr", C.c_int), ("bytectr", C.c_int), ("pad", C.c_int),
+                ("nitems_read", C.c_uint64), ("pktbuf", C.c_uint8 * (FRAME_MAX + 8))]
+
+
+class Xlat(C.Structure):
+    _fields_ = [("decim", C.c_int), ("ntaps", C.c_int), ("ctaps", C.POINTER(C.c_float)),
+                ("incr_re", C.c_float), ("incr_im", C.c_float), ("phase_re", C.c_float),
+                ("phase_im", C.c_float), ("counter", C.c_uint)]
+
+
+def crc_ccitt(data: bytes) -> int:
+    L = lib()
+    L.ao_crc_ccitt.restype = C.c_uint
+    L.ao_crc_ccitt.argtypes = [C.c_char_p, C.c_size_t]
+    return int(L.ao_crc_ccitt(bytes(data), len(data)))
+
+
+class HdlcDeframer:
+    """digital.hdlc_deframer_bp(length_min, length_max) [G], streaming."""
+
+    def __init__(self, length_min=11, length_max=64):
+        self._h = Hdlc()
+        lib().ao_hdlc_init(C.byref(self._h), int(length_min), int(length_max))
+
+    def work(self, bits, max_frames=256):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        frames = np.zeros(max_frames, dtype=FRAME_DTYPE)
+        dropped = C.c_int(0)
+        L = lib()
+        L.ao_hdlc_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p]
+        n = L.ao_hdlc_work(C.byref(self._h), _fp(bits), len(bits), _fp(frames), max_frames,
+                           C.byref(dropped))
+        if dropped.value:
+            raise OverflowError("more than max_frames frames")
+        return frames[:n]
+
+
+def frames_payloads(frames):
+    return [bytes(f["data"][:f["len"]]) for f in frames]
+
+
+def pdu_to_nmea(data: bytes, designator="A") -> str:
+    L = lib()
+    L.ao_pdu_to_nmea.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    buf = C.create_string_buffer(4096)
+    n = L.ao_pdu_to_nmea(designator.encode(), bytes(data), len(data), buf, 4096)
+    if n < 0:
+        raise ValueError("pdu_to_nmea: bad length")
+    return buf.raw[:n].decode("latin-1")
+
+
+def firdes_low_pass(gain, fs, cutoff, tw):
+    L = lib()
+    L.ao_firdes_low_pass.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                     C.c_int]
+    n = L.ao_firdes_low_pass(gain, fs, cutoff, tw, None, 0)
+    taps = np.zeros(n, dtype=np.float32)
+    assert L.ao_firdes_low_pass(gain, fs, cutoff, tw, _fp(taps), n) == n
+    return taps
+
+
+class FreqXlatingFir:
+    """filter.freq_xlating_fir_filter_ccf(decimation, taps, center_freq, sampling_freq) [G]."""
+
+    def __init__(self, decimation, taps, center_freq, sampling_freq):
+        self.taps = np.ascontiguousarray(taps, dtype=np.float32)
+        self.decim = int(decimation)
+        self.center_freq, self.sampling_freq = float(center_freq), float(sampling_freq)
+        self._x = Xlat()
+        L = lib()
+        L.ao_xlat_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        if L.ao_xlat_init(C.byref(self._x), self.decim, _fp(self.taps), len(self.taps),
+                          self.center_freq, self.sampling_freq):
+            raise ValueError("xlat_init")
+        self.nout = 0
+
+    def __del__(self):
+        try:
+            lib().ao_xlat_free(C.byref(self._x))
+        except Exception:
+            pass
+
+    @property
+    def ctaps(self):
+        return np.ctypeslib.as_array(self._x.ctaps, shape=(2 * len(self.taps),)).copy().view(np.complex64)
+
+    def work(self, inbuf, fir=False):
+        """inbuf: ntaps-1 history items followed by noutput*decim new items."""
+        inbuf = _c64(inbuf)
+        n = (len(inbuf) - (len(self.taps) - 1)) // self.decim
+        out = np.zeros(n, dtype=np.complex64)
+        fo = np.zeros(n, dtype=np.complex64) if fir else None
+        L = lib()
+        L.ao_xlat_work.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ao_xlat_work(C.byref(self._x), n, _fp(inbuf), _fp(out), _fp(fo) if fir else None)
+        self.nout += n
+        return (out, fo) if fir else out
+
+    def f64(self, inbuf, first_output=0):
+        inbuf = _c64(inbuf)
+        n = (len(inbuf) - (len(self.taps) - 1)) // self.decim
+        out = np.zeros(2 * n, dtype=np.float64)
+        L = lib()
+        L.ao_xlat_f64.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_uint64,
+                                  C.c_int, C.c_void_p, C.c_void_p]
+        L.ao_xlat_f64(self.decim, _fp(self.taps), len(self.taps), self.center_freq,
+                      self.sampling_freq, int(first_output), n, _fp(inbuf), _fp(out))
+        return out.view(np.complex128)
