@@ -49,6 +49,10 @@ EXPORTS = [
     "b200ais_hdlc_create", "b200ais_hdlc_destroy", "b200ais_hdlc_reset", "b200ais_hdlc_work",
     "b200ais_hdlc_work_dev", "b200ais_hdlc_status",
     "b200ais_nmea_slot_bytes", "b200ais_nmea_format", "b200ais_nmea_format_dev",
+    "b200ais_demod_stream_stage", "b200ais_demod_stream_work_staged",
+    "b200ais_rx_default_config", "b200ais_rx_create", "b200ais_rx_destroy", "b200ais_rx_reset",
+    "b200ais_rx_decimation", "b200ais_rx_channels", "b200ais_rx_samples_per_symbol",
+    "b200ais_rx_sentence_slot", "b200ais_rx_work", "b200ais_rx_work_dev", "b200ais_rx_status",
 ]
 FRAME_MAX = 248
 FRAME_DTYPE = np.dtype([("end_bit", "<u8"), ("len", "<i4"), ("channel", "<i4"),
@@ -63,6 +67,15 @@ class DemodConfig(C.Structure):
                 ("mark_delay", C.c_uint), ("threshold", C.c_float), ("gain", C.c_float),
                 ("limit", C.c_float), ("osps", C.c_int), ("corr_chunk", C.c_int),
                 ("stages", C.c_int)]
+
+
+class RxConfig(C.Structure):
+    _fields_ = [("rate", C.c_double), ("nfreqs", C.c_int), ("freqs", C.c_double * 16),
+                ("designators", (C.c_char * 8) * 16), ("sources", C.c_int),
+                ("max_input_items", C.c_int), ("max_frames", C.c_int), ("bits_per_sec", C.c_float),
+                ("clockrec_gain", C.c_float), ("omega_relative_limit", C.c_float),
+                ("fftlen", C.c_int), ("lpf_cutoff", C.c_double), ("lpf_transition", C.c_double),
+                ("hdlc_length_min", C.c_int), ("hdlc_length_max", C.c_int)]
 
 
 class B200AisError(RuntimeError):
@@ -171,6 +184,17 @@ def lib():
     L.b200ais_nmea_slot_bytes.argtypes = [i, C.c_char_p]
     L.b200ais_nmea_format.argtypes = [vp, vp, i, i, vp, vp, i, vp]
     L.b200ais_nmea_format_dev.argtypes = [vp, vp, i, i, vp, vp, i, vp, vp]
+    L.b200ais_demod_stream_stage.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(sz), vp]
+    L.b200ais_demod_stream_work_staged.argtypes = [vp, i, vp, i, vp, vp, vp, vp]
+    L.b200ais_rx_default_config.argtypes = [C.POINTER(RxConfig)]
+    L.b200ais_rx_create.argtypes = [C.POINTER(vp), C.POINTER(RxConfig), vp, i]
+    for f in ("b200ais_rx_destroy", "b200ais_rx_reset", "b200ais_rx_decimation",
+              "b200ais_rx_channels", "b200ais_rx_samples_per_symbol", "b200ais_rx_sentence_slot",
+              "b200ais_rx_status"):
+        getattr(L, f).argtypes = [vp]
+    L.b200ais_rx_samples_per_symbol.restype = C.c_float
+    L.b200ais_rx_work.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, C.POINTER(i)]
+    L.b200ais_rx_work_dev.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, vp, vp]
     _lib = L
     return L
 

@@ -1621,6 +1621,43 @@ extern "C" int b200ais_demod_stream_work_dev(b200ais_demod *h, const float *iq, 
                       max_bits, nbits, tags, ntags, s);
 }
 
+extern "C" int b200ais_demod_stream_stage(b200ais_demod *h, int nsamples, int max_bits, float **dev_ptr,
+                                          size_t *stride, void *stream)
+{
+    if (!h || !dev_ptr || !stride) {
+        set_error("demod_stream_stage: null argument");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = stream_prepare(h, nsamples, max_bits, s);
+    if (rc)
+        return rc;
+    if ((rc = h->xs.reserve(h->xs_stride * (size_t)h->channels * sizeof(float2))))
+        return rc;
+    *dev_ptr = reinterpret_cast<float *>(h->xs.as<float2>() + h->st_nx);
+    *stride = h->xs_stride;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_demod_stream_work_staged(b200ais_demod *h, int nsamples, uint8_t *bits,
+                                                int max_bits, int *nbits, b200ais_tag *tags,
+                                                int *ntags, void *stream)
+{
+    if (!h || !bits || !nbits) {
+        set_error("demod_stream_work_staged: null argument");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = stream_prepare(h, nsamples, max_bits, s);
+    if (rc)
+        return rc;
+    if ((rc = h->xs.reserve(h->xs_stride * (size_t)h->channels * sizeof(float2))))
+        return rc;
+    B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
+    return stream_run(h, h->xs.as<float2>(), h->xs_stride, true, nsamples, bits, max_bits, nbits, tags,
+                      ntags, s);
+}
+
 extern "C" int b200ais_demod_stream_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
                                          int max_bits, int *nbits, b200ais_tag *tags, int *ntags)
 {

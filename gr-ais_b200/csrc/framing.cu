@@ -157,14 +157,14 @@ __device__ __forceinline__ int put_int(char *o, int v)
 // pdu_to_nmea_impl::msg_to_sentence (lib/pdu_to_nmea_impl.cc:63-131), one lane per frame.
 __global__ void __launch_bounds__(128)
 k_nmea(const b200ais_frame *__restrict__ frames, const int *__restrict__ nframes, int channels,
-       int max_frames, const char *__restrict__ designators, char *__restrict__ sentences, int slot,
-       int *__restrict__ lens)
+       int max_frames, const char *__restrict__ designators, int des_mod,
+       char *__restrict__ sentences, int slot, int *__restrict__ lens)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= channels * max_frames)
         return;
     const int c = idx / max_frames, f = idx - c * max_frames;
-    if (f >= nframes[c]) {
+    if (f >= min(nframes[c], max_frames)) {
         lens[idx] = 0;
         return;
     }
@@ -178,8 +178,9 @@ k_nmea(const b200ais_frame *__restrict__ frames, const int *__restrict__ nframes
     char des[8];
     int dl = 0;
     if (designators) {
-        for (; dl < 8 && designators[c * 8 + dl]; dl++)
-            des[dl] = designators[c * 8 + dl];
+        const int row = des_mod > 0 ? fr->channel % des_mod : c;
+        for (; dl < 8 && designators[row * 8 + dl]; dl++)
+            des[dl] = designators[row * 8 + dl];
     } else {
         des[0] = 'A';
         dl = 1;
@@ -420,10 +421,60 @@ extern "C" int b200ais_nmea_format_dev(const b200ais_frame *frames, const int *n
     }
     const long total = (long)channels * max_frames;
     k_nmea<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        frames, nframes, channels, max_frames, designators, sentences, slot, lens);
+        frames, nframes, channels, max_frames, designators, 0, sentences, slot, lens);
     B200_LAUNCH_CHECK("k_nmea");
     return B200AIS_OK;
 }
+
+namespace b200ais {
+
+// ais_rx (rx.cu): gather every channel's frames into one dense list (order of channels is
+// whatever the atomics give; a channel's own frames stay in order) ...
+__global__ void __launch_bounds__(128)
+k_gather_frames(const b200ais_frame *__restrict__ frames, const int *__restrict__ nframes,
+                int channels, int max_frames, b200ais_frame *__restrict__ dense, int max_msgs,
+                int *__restrict__ count, int *status)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels)
+        return;
+    const int nf = nframes[c];
+    if (nf <= 0)
+        return;
+    const int base = atomicAdd(count, nf);
+    if (base + nf > max_msgs) {
+        atomicExch(status, B200AIS_E_FRAME_OVERFLOW);
+        return;
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)c * max_frames);
+    uint4 *dst = reinterpret_cast<uint4 *>(dense + base);
+    const int words = nf * (int)(sizeof(b200ais_frame) / sizeof(uint4));
+    for (int k = 0; k < words; k++)
+        dst[k] = src[k];
+}
+
+int launch_gather_frames(const b200ais_frame *frames, const int *nframes, int channels,
+                         int max_frames, b200ais_frame *dense, int max_msgs, int *count,
+                         int *status, cudaStream_t s)
+{
+    k_gather_frames<<<(channels + 127) / 128, 128, 0, s>>>(frames, nframes, channels, max_frames,
+                                                           dense, max_msgs, count, status);
+    B200_LAUNCH_CHECK("k_gather_frames");
+    return B200AIS_OK;
+}
+
+// ... and format the dense list; designator row = frame.channel % des_mod
+int launch_nmea_dense(const b200ais_frame *dense, const int *count, int max_msgs,
+                      const char *designators, int des_mod, char *sentences, int slot, int *lens,
+                      cudaStream_t s)
+{
+    k_nmea<<<(max_msgs + 127) / 128, 128, 0, s>>>(dense, count, 1, max_msgs, designators, des_mod,
+                                                  sentences, slot, lens);
+    B200_LAUNCH_CHECK("k_nmea");
+    return B200AIS_OK;
+}
+
+} // namespace b200ais
 
 extern "C" int b200ais_nmea_format(const b200ais_frame *frames, const int *nframes, int channels,
                                    int max_frames, const char *designators, char *sentences,

@@ -155,6 +155,13 @@ int launch_roll_rows(float2 *rows, size_t stride, int channels, int from, int le
 int launch_msk_reset(MskState *state, int channels, float sps_half, cudaStream_t s);
 int launch_msk_set_omega(MskState *state, int channels, float omega, cudaStream_t s);
 int launch_invert(const uint8_t *in, uint8_t *out, size_t n, cudaStream_t s);
+// ais_rx output (framing.cu): dense message list + its sentences
+int launch_gather_frames(const b200ais_frame *frames, const int *nframes, int channels,
+                         int max_frames, b200ais_frame *dense, int max_msgs, int *count,
+                         int *status, cudaStream_t s);
+int launch_nmea_dense(const b200ais_frame *dense, const int *count, int max_msgs,
+                      const char *designators, int des_mod, char *sentences, int slot, int *lens,
+                      cudaStream_t s);
 int launch_copy_delay(const float2 *in, size_t in_stride, float2 *out, size_t out_stride,
                       int channels, int n, cudaStream_t s);
 

@@ -1,0 +1,296 @@
+// rx.cu -- the reference's ais_rx receiver (python/radio.py:39-72) for many wideband sources:
+//   freq_xlating_fir_filter_ccf -> ais_demod -> hdlc_deframer_bp(11, 64) -> pdu_to_nmea
+// composed from the C-ABI blocks of this library on one stream, every block keeping its
+// state from call to call (a capture is fed in pieces of any size).  The channeliser writes
+// straight into the demod chain's assembly rows; nothing between the wideband input and the
+// NMEA sentences leaves the device.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "internal.h"
+
+using namespace b200ais;
+
+struct b200ais_rx {
+    b200ais_rx_config cfg;
+    int D = 0, ntaps = 0, channels = 0, max_out = 0, max_bits = 0, slot = 0;
+    b200ais_xlat *xl = nullptr;
+    b200ais_demod *dm = nullptr;
+    b200ais_hdlc *hd = nullptr;
+    cudaStream_t stream = nullptr;
+    float2 *d_x = nullptr; // [sources][x_stride]: history + leftover + this call's items
+    size_t x_stride = 0;
+    int carry = 0; // items of every row kept from the last call
+    uint8_t *d_bits = nullptr;
+    int *d_nbits = nullptr, *d_nframes = nullptr, *d_count = nullptr, *d_status = nullptr;
+    b200ais_frame *d_frames = nullptr;
+    char *d_des = nullptr;
+    // device-side outputs of the host variant
+    b200ais_frame *d_msgs = nullptr;
+    char *d_sent = nullptr;
+    int *d_lens = nullptr;
+    int out_cap = 0;
+    uint64_t items_in = 0, items_out = 0;
+};
+
+extern "C" int b200ais_rx_default_config(b200ais_rx_config *c)
+{
+    if (!c)
+        return B200AIS_E_INVALID;
+    memset(c, 0, sizeof(*c));
+    c->rate = 250e3;                 // python/radio.py:120
+    c->nfreqs = 2;                   // python/radio.py:88-89
+    c->freqs[0] = 161.975e6 - 162.0e6;
+    c->freqs[1] = 162.025e6 - 162.0e6;
+    c->designators[0][0] = 'A';
+    c->designators[1][0] = 'B';
+    c->sources = 1;
+    c->max_input_items = 1 << 18;
+    c->max_frames = 64;
+    c->bits_per_sec = 9600.0f;       // python/radio.py:47
+    c->clockrec_gain = 0.04f;        // :58
+    c->omega_relative_limit = 0.01f; // :59
+    c->fftlen = 1024;                // :60
+    c->lpf_cutoff = 11000.0;         // :49
+    c->lpf_transition = 1000.0;
+    c->hdlc_length_min = 11;         // :64
+    c->hdlc_length_max = 64;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_rx_destroy(b200ais_rx *h)
+{
+    if (!h)
+        return B200AIS_OK;
+    b200ais_xlat_destroy(h->xl);
+    b200ais_demod_destroy(h->dm);
+    b200ais_hdlc_destroy(h->hd);
+    void *bufs[] = {h->d_x, h->d_bits, h->d_nbits, h->d_nframes, h->d_count, h->d_status,
+                    h->d_frames, h->d_des, h->d_msgs, h->d_sent, h->d_lens};
+    for (void *b : bufs)
+        if (b)
+            cudaFree(b);
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    delete h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_rx_decimation(const b200ais_rx *h) { return h ? h->D : 0; }
+extern "C" int b200ais_rx_channels(const b200ais_rx *h) { return h ? h->channels : 0; }
+extern "C" int b200ais_rx_sentence_slot(const b200ais_rx *h) { return h ? h->slot : 0; }
+extern "C" float b200ais_rx_samples_per_symbol(const b200ais_rx *h)
+{
+    return h ? (float)((h->cfg.rate / h->D) / h->cfg.bits_per_sec) : 0.0f;
+}
+
+extern "C" int b200ais_rx_create(b200ais_rx **out, const b200ais_rx_config *cfg,
+                                 const float *symbols_iq, int nsymbols)
+{
+    if (!out || !cfg || !symbols_iq || nsymbols < 1 || cfg->nfreqs < 1 || cfg->nfreqs > 16 ||
+        cfg->sources < 1 || cfg->max_input_items < 1 || cfg->max_frames < 1 || !(cfg->rate > 0) ||
+        !(cfg->bits_per_sec > 0)) {
+        set_error("rx_create: bad configuration");
+        return B200AIS_E_INVALID;
+    }
+    b200ais_rx *h = new (std::nothrow) b200ais_rx;
+    if (!h)
+        return B200AIS_E_NOMEM;
+    h->cfg = *cfg;
+    // python/radio.py:50: int(rate / (bits_per_sec * samples_per_symbol)), samples_per_symbol = 5
+    h->D = (int)(cfg->rate / ((double)cfg->bits_per_sec * 5.0));
+    if (h->D < 1) {
+        delete h;
+        set_error("rx_create: rate below one 48 ksps channel");
+        return B200AIS_E_INVALID;
+    }
+    int rc, nt = 0;
+    if ((rc = b200ais_firdes_low_pass(1.0, cfg->rate, cfg->lpf_cutoff, cfg->lpf_transition, nullptr, 0,
+                                      &nt))) {
+        delete h;
+        return rc;
+    }
+    std::vector<float> taps((size_t)nt);
+    rc = b200ais_firdes_low_pass(1.0, cfg->rate, cfg->lpf_cutoff, cfg->lpf_transition, taps.data(), nt, &nt);
+    h->ntaps = nt;
+    h->channels = cfg->sources * cfg->nfreqs;
+    h->max_out = (cfg->max_input_items + h->D - 1) / h->D + 1;
+    if (!rc)
+        rc = b200ais_xlat_create(&h->xl, h->D, taps.data(), nt, cfg->freqs, cfg->nfreqs, cfg->rate,
+                                 cfg->sources);
+    if (!rc) {
+        b200ais_demod_config dc;
+        b200ais_demod_default_config(&dc);
+        const float sps = b200ais_rx_samples_per_symbol(h); // python/radio.py:57
+        dc.sps = sps;
+        dc.data_rate = (int)cfg->bits_per_sec;
+        dc.sample_rate = sps * cfg->bits_per_sec;           // python/ais_demod.py:30
+        dc.fftlen = cfg->fftlen;
+        dc.gain = cfg->clockrec_gain;
+        dc.limit = cfg->omega_relative_limit;
+        rc = b200ais_demod_create(&h->dm, &dc, symbols_iq, nsymbols, h->channels, h->max_out, 256);
+    }
+    if (!rc)
+        rc = b200ais_hdlc_create(&h->hd, cfg->hdlc_length_min, cfg->hdlc_length_max, h->channels);
+    if (!rc) {
+        h->max_bits = b200ais_demod_stream_max_bits(h->dm, h->max_out);
+        h->max_bits = (h->max_bits + 15) / 16 * 16; // rows of 16-byte words for k_hdlc
+        h->slot = b200ais_nmea_slot_bytes(cfg->hdlc_length_max, "12345678");
+        h->x_stride = ((size_t)(nt - 1) + h->D + cfg->max_input_items + 3) / 2 * 2;
+        const size_t C = (size_t)h->channels;
+        cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_x, sizeof(float2) * h->x_stride * cfg->sources);
+        if (e == cudaSuccess) e = cudaMemset(h->d_x, 0, sizeof(float2) * h->x_stride * cfg->sources);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_bits, (size_t)h->max_bits * C);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_nbits, sizeof(int) * C);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_nframes, sizeof(int) * C);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_count, sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(h->d_status, 0, sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_frames, sizeof(b200ais_frame) * C * cfg->max_frames);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_des, 16 * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_des, cfg->designators, 16 * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess)
+            rc = cuda_fail(e, "rx_create", __FILE__, __LINE__);
+    }
+    if (rc) {
+        b200ais_rx_destroy(h);
+        return rc;
+    }
+    h->carry = nt - 1; // freq_xlating's history starts as zeros
+    *out = h;
+    return B200AIS_OK;
+}
+
+extern "C" int b200ais_rx_reset(b200ais_rx *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    B200_CU(cudaDeviceSynchronize());
+    B200_CU(cudaMemset(h->d_x, 0, sizeof(float2) * h->x_stride * h->cfg.sources));
+    h->carry = h->ntaps - 1;
+    h->items_in = h->items_out = 0;
+    int rc;
+    if ((rc = b200ais_xlat_reset(h->xl)) || (rc = b200ais_demod_stream_reset(h->dm, nullptr)) ||
+        (rc = b200ais_hdlc_reset(h->hd)))
+        return rc;
+    B200_CU(cudaDeviceSynchronize());
+    return B200AIS_OK;
+}
+
+// everything after this call's items are in d_x at [carry, carry + n)
+static int rx_run(b200ais_rx *h, int n, b200ais_frame *msgs, char *sentences, int slot, int *lens,
+                  int max_msgs, int *count, cudaStream_t s)
+{
+    const int S = h->cfg.sources;
+    const int avail = h->carry + n;
+    const int nout = avail >= h->ntaps - 1 + h->D ? (avail - (h->ntaps - 1)) / h->D : 0;
+    int rc;
+    float *stage = nullptr;
+    size_t sstride = 0;
+    if ((rc = b200ais_demod_stream_stage(h->dm, nout, h->max_bits, &stage, &sstride, s)))
+        return rc;
+    if (nout > 0) {
+        if ((rc = b200ais_xlat_work_dev(h->xl, nout, reinterpret_cast<const float *>(h->d_x), h->x_stride,
+                                        stage, sstride, s)))
+            return rc;
+        if ((rc = launch_roll_rows(h->d_x, h->x_stride, S, nout * h->D, avail - nout * h->D, s)))
+            return rc;
+    }
+    h->carry = avail - nout * h->D;
+    h->items_in += (uint64_t)n;
+    h->items_out += (uint64_t)nout;
+    if ((rc = b200ais_demod_stream_work_staged(h->dm, nout, h->d_bits, h->max_bits, h->d_nbits, nullptr,
+                                               nullptr, s)))
+        return rc;
+    if ((rc = b200ais_hdlc_work_dev(h->hd, h->d_bits, (size_t)h->max_bits, h->d_nbits, 0, h->d_frames,
+                                    h->cfg.max_frames, h->d_nframes, s)))
+        return rc;
+    B200_CU(cudaMemsetAsync(count, 0, sizeof(int), s));
+    if ((rc = launch_gather_frames(h->d_frames, h->d_nframes, h->channels, h->cfg.max_frames, msgs,
+                                   max_msgs, count, h->d_status, s)))
+        return rc;
+    return launch_nmea_dense(msgs, count, max_msgs, h->d_des, h->cfg.nfreqs, sentences, slot, lens, s);
+}
+
+extern "C" int b200ais_rx_work_dev(b200ais_rx *h, const float *iq, size_t iq_stride, int nitems,
+                                   b200ais_frame *msgs, char *sentences, int slot, int *lens,
+                                   int max_msgs, int *nmsgs, void *stream)
+{
+    if (!h || (!iq && nitems > 0) || !msgs || !sentences || !lens || !nmsgs || max_msgs < 1 ||
+        nitems < 0 || nitems > h->cfg.max_input_items || slot < h->slot) {
+        set_error("rx_work: bad arguments (nitems <= max_input_items, slot >= b200ais_rx_sentence_slot)");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (nitems > 0)
+        B200_CU(cudaMemcpy2DAsync(h->d_x + h->carry, h->x_stride * sizeof(float2), iq,
+                                  iq_stride * sizeof(float2), (size_t)nitems * sizeof(float2),
+                                  (size_t)h->cfg.sources, cudaMemcpyDeviceToDevice, s));
+    return rx_run(h, nitems, msgs, sentences, slot, lens, max_msgs, nmsgs, s);
+}
+
+extern "C" int b200ais_rx_status(b200ais_rx *h)
+{
+    if (!h)
+        return B200AIS_E_INVALID;
+    int st = 0;
+    B200_CU(cudaMemcpy(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        B200_CU(cudaMemset(h->d_status, 0, sizeof(int)));
+        set_error("rx: more messages than max_msgs in one call");
+        return st;
+    }
+    int rc = b200ais_hdlc_status(h->hd);
+    if (rc)
+        return rc;
+    return b200ais_demod_status(h->dm);
+}
+
+extern "C" int b200ais_rx_work(b200ais_rx *h, const float *iq, size_t iq_stride, int nitems,
+                               b200ais_frame *msgs, char *sentences, int slot, int *lens,
+                               int max_msgs, int *nmsgs)
+{
+    if (!h || (!iq && nitems > 0) || !msgs || !sentences || !lens || !nmsgs || max_msgs < 1 ||
+        nitems < 0 || nitems > h->cfg.max_input_items || slot < h->slot) {
+        set_error("rx_work: bad arguments (nitems <= max_input_items, slot >= b200ais_rx_sentence_slot)");
+        return B200AIS_E_INVALID;
+    }
+    cudaStream_t s = h->stream;
+    if (h->out_cap < max_msgs) {
+        if (h->d_msgs) cudaFree(h->d_msgs);
+        if (h->d_sent) cudaFree(h->d_sent);
+        if (h->d_lens) cudaFree(h->d_lens);
+        h->d_msgs = nullptr;
+        h->d_sent = nullptr;
+        h->d_lens = nullptr;
+        h->out_cap = 0;
+        B200_CU(cudaMalloc(&h->d_msgs, sizeof(b200ais_frame) * (size_t)max_msgs));
+        B200_CU(cudaMalloc(&h->d_sent, (size_t)h->slot * max_msgs));
+        B200_CU(cudaMalloc(&h->d_lens, sizeof(int) * (size_t)max_msgs));
+        h->out_cap = max_msgs;
+    }
+    if (nitems > 0)
+        B200_CU(cudaMemcpy2DAsync(h->d_x + h->carry, h->x_stride * sizeof(float2), iq,
+                                  iq_stride * sizeof(float2), (size_t)nitems * sizeof(float2),
+                                  (size_t)h->cfg.sources, cudaMemcpyHostToDevice, s));
+    int rc = rx_run(h, nitems, h->d_msgs, h->d_sent, h->slot, h->d_lens, max_msgs, h->d_count, s);
+    if (rc)
+        return rc;
+    int n = 0;
+    B200_CU(cudaMemcpyAsync(&n, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    B200_CU(cudaStreamSynchronize(s));
+    if ((rc = b200ais_rx_status(h)))
+        return rc;
+    *nmsgs = n;
+    if (n > 0) {
+        B200_CU(cudaMemcpyAsync(msgs, h->d_msgs, sizeof(b200ais_frame) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        B200_CU(cudaMemcpyAsync(lens, h->d_lens, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+        B200_CU(cudaMemcpy2DAsync(sentences, (size_t)slot, h->d_sent, (size_t)h->slot, (size_t)h->slot,
+                                  (size_t)n, cudaMemcpyDeviceToHost, s));
+        B200_CU(cudaStreamSynchronize(s));
+    }
+    return B200AIS_OK;
+}

@@ -200,3 +200,53 @@ def hdlc_deframe(bits, min_bytes: int = 11, max_bytes: int = 64):
 def payloads_found(bits, truth):
     found = hdlc_deframe(bits)
     return [t["payload"] in found for t in truth]
+
+
+# ------------------------------------------------------- wideband captures
+
+def make_wideband(source: int = 0, rate: float = 250e3, n: int = 250000, nbursts: int = 3,
+                  snr_db: float = 25.0, freqs=(-25e3, 25e3), seed: int = SEED):
+    """One wideband capture as the reference's ais_rx sees it (python/radio.py:86-91): AIS
+    channel k sits at freqs[k] Hz from the centre.  Bursts are GMSK at 9600 baud generated
+    directly at `rate` (float64), with AWGN of per-sample variance rate/9600 / 10^(snr/10)
+    (Es/N0 in the symbol bandwidth).  Returns (iq complex64 [n], truth list of
+    dict(channel, start, payload))."""
+    rng = rng_for(1000003 + source, seed)
+    sps = rate / SYMBOL_RATE
+    sigma2 = sps / (10.0 ** (snr_db / 10.0))
+    x = np.sqrt(sigma2 / 2) * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    truth = []
+    slot = int(round(256 * sps))
+    first_slot = 3
+    nslots = (n - int(300 * sps)) // slot - first_slot
+    t = np.arange(n, dtype=np.float64)
+    for k, f in enumerate(freqs):
+        if nslots < nbursts or nbursts <= 0:
+            continue
+        slots = np.sort(rng.choice(nslots, size=nbursts, replace=False)) + first_slot
+        for s in slots:
+            payload = random_payload(rng)
+            bits = frame_bits(payload)
+            levels = nrzi_encode(bits, nrzi_level_for_training())
+            b = gmsk_modulate_rate(levels, sps)
+            start = int(s) * slot + int(rng.integers(0, 64))
+            m = min(len(b), n - start)
+            x[start:start + m] += b[:m] * np.exp(2j * np.pi * f * t[start:start + m] / rate)
+            truth.append(dict(channel=k, start=start, payload=payload))
+    return x.astype(np.complex64), truth
+
+
+def gmsk_modulate_rate(levels, sps: float, bt: float = 0.4) -> np.ndarray:
+    """float64 GMSK (h = 0.5) at a non-integer number of samples per symbol: the phase is
+    built at 8 samples per symbol and interpolated linearly onto the output grid."""
+    fine = gmsk_phase(levels, 8, bt)
+    nout = int(len(levels) * sps)
+    pos = np.arange(nout) * (8.0 / sps)
+    return np.exp(1j * np.interp(pos, np.arange(len(fine)), fine))
+
+
+def gmsk_phase(levels, sps: int, bt: float = 0.4) -> np.ndarray:
+    nrz = 2.0 * np.asarray(levels, dtype=np.float64) - 1.0
+    up = np.zeros(len(nrz) * sps)
+    up[::sps] = nrz
+    return (np.pi / 2) * np.cumsum(np.convolve(up, gaussian_pulse(bt, sps)))

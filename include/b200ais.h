@@ -26,6 +26,7 @@
  *   b200ais_hdlc_*       digital.hdlc_deframer_bp(11,64) python/radio.py:64
  *   b200ais_nmea_*       gr::ais::pdu_to_nmea            include/ais/pdu_to_nmea.h:37-54,
  *                                                        lib/pdu_to_nmea_impl.cc:63-131
+ *   b200ais_rx_*         ais_rx hier-block (all of the above chained)  python/radio.py:39-72
  *
  * The *_work functions mirror one GNU Radio work()/general_work() call, batched
  * over `channels` independent streams (the GR adapter calls with channels = 1).
@@ -256,6 +257,15 @@ B200AIS_API int b200ais_demod_stream_work(b200ais_demod *h, const float *iq, int
 B200AIS_API int b200ais_demod_stream_work_dev(b200ais_demod *h, const float *iq, int nsamples,
                                               uint8_t *bits, int max_bits, int *nbits,
                                               b200ais_tag *tags, int *ntags, void *stream);
+/* The same pass with the input produced on the device by the caller (the channeliser writes
+ * straight into the chain's assembly rows): stage() returns where this call's `nsamples` new
+ * items of channel c go (*dev_ptr + c * *stride complex items); work_staged() then runs the
+ * pass.  Nothing else may touch the handle between the two calls. */
+B200AIS_API int b200ais_demod_stream_stage(b200ais_demod *h, int nsamples, int max_bits,
+                                           float **dev_ptr, size_t *stride, void *stream);
+B200AIS_API int b200ais_demod_stream_work_staged(b200ais_demod *h, int nsamples, uint8_t *bits,
+                                                 int max_bits, int *nbits, b200ais_tag *tags,
+                                                 int *ntags, void *stream);
 /* items waiting inside the stream (all nullable): input items short of an FFT vector, AGC
  * outputs short of a corr_est output multiple, corr_est's nitems_written */
 B200AIS_API int b200ais_demod_stream_pending(const b200ais_demod *h, int *input_items,
@@ -369,6 +379,55 @@ B200AIS_API int b200ais_nmea_format(const b200ais_frame *frames, const int *nfra
 B200AIS_API int b200ais_nmea_format_dev(const b200ais_frame *frames, const int *nframes,
                                         int channels, int max_frames, const char *designators,
                                         char *sentences, int slot, int *lens, void *stream);
+
+/* ------------------------------------------- ais_rx: the whole receiver path */
+/* python/radio.py:39-72 for `sources` wideband inputs:
+ *   freq_xlating_fir_filter_ccf(int(rate/48000), firdes.low_pass(1, rate, 11000, 1000), freq, rate)
+ *   -> ais_demod(options) -> hdlc_deframer_bp(11, 64) -> pdu_to_nmea(designator),
+ * one such path per entry of `freqs` sharing each source (python/radio.py:86-91).  Channel
+ * s*nfreqs + k is source s at freqs[k].  A capture is fed in pieces; every block keeps its state. */
+typedef struct b200ais_rx_config {
+    double rate;               /* options.rate (python/radio.py:120), default 250e3 */
+    int nfreqs;                /* 1..16 */
+    double freqs[16];          /* offsets from the tuned centre (python/radio.py:88-89) */
+    char designators[16][8];   /* NUL-padded, "A"/"B" */
+    int sources;
+    int max_input_items;       /* per source per call */
+    int max_frames;            /* per channel per call */
+    float bits_per_sec;        /* 9600 */
+    float clockrec_gain;       /* 0.04 */
+    float omega_relative_limit; /* 0.01 */
+    int fftlen;                /* 1024 */
+    double lpf_cutoff, lpf_transition; /* 11000, 1000 */
+    int hdlc_length_min, hdlc_length_max; /* 11, 64 */
+} b200ais_rx_config;
+
+typedef struct b200ais_rx b200ais_rx;
+B200AIS_API int b200ais_rx_default_config(b200ais_rx_config *cfg);
+/* symbols: the corr_est template, digital.gmsk_mod(samples_per_symbol, 0.4) of the preamble
+ * (python/ais_demod.py:36-38) at b200ais_rx_samples_per_symbol() */
+B200AIS_API int b200ais_rx_create(b200ais_rx **h, const b200ais_rx_config *cfg,
+                                  const float *symbols_iq, int nsymbols);
+B200AIS_API int b200ais_rx_destroy(b200ais_rx *h);
+B200AIS_API int b200ais_rx_reset(b200ais_rx *h);
+B200AIS_API int b200ais_rx_decimation(const b200ais_rx *h);
+B200AIS_API int b200ais_rx_channels(const b200ais_rx *h);
+B200AIS_API float b200ais_rx_samples_per_symbol(const b200ais_rx *h); /* python/radio.py:57 */
+B200AIS_API int b200ais_rx_sentence_slot(const b200ais_rx *h);
+/* Feed the next `nitems` wideband items of every source (iq: [sources][iq_stride] complex) and
+ * collect the messages completed in this call: msgs [max_msgs] (channel = s*nfreqs + k; end_bit
+ * = absolute position in that channel's bit stream), their NMEA sentence(s) in
+ * sentences [max_msgs][slot] with lens [max_msgs], *nmsgs of them.  Messages of one channel are
+ * in stream order; the order across channels is unspecified. */
+B200AIS_API int b200ais_rx_work(b200ais_rx *h, const float *iq, size_t iq_stride, int nitems,
+                                b200ais_frame *msgs, char *sentences, int slot, int *lens,
+                                int max_msgs, int *nmsgs);
+/* device pointers everywhere (nmsgs too), asynchronous on `stream`; b200ais_rx_status after it
+ * has completed */
+B200AIS_API int b200ais_rx_work_dev(b200ais_rx *h, const float *iq, size_t iq_stride, int nitems,
+                                    b200ais_frame *msgs, char *sentences, int slot, int *lens,
+                                    int max_msgs, int *nmsgs, void *stream);
+B200AIS_API int b200ais_rx_status(b200ais_rx *h);
 
 #ifdef __cplusplus
 }
