@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--template", default="north_star", choices=["north_star", "intended", "reference"])
     ap.add_argument("--snr-db", type=float, default=20.0)
     ap.add_argument("--cpu-channels", type=int, default=0,
-                    help="channels in the CPU sample (0 = 2 per host thread)")
+                    help="channels in the CPU sample (0 = about 12 s of CPU work, probed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap", type=int, default=1,
@@ -161,13 +161,23 @@ def cpu_sample(args, threads, sample_channels, n, steps, warmup):
     return sample_channels * (n / FS) / dt, dt
 
 
+def cpu_sample_size(args, threads, n, seconds=12.0):
+    """Channels that give about `seconds` of CPU work per pass (probed with 2 per thread)."""
+    if args.cpu_channels:
+        return args.cpu_channels
+    probe = 2 * threads
+    v, _ = cpu_sample(args, threads, probe, n, 1, 1)
+    want = int(v * seconds / (n / FS))
+    return max(probe, min(want // threads * threads, 16384))
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     n = int(round(args.seconds * FS))
-    sample = args.cpu_channels or 2 * threads
+    sample = cpu_sample_size(args, threads, n)
     warm = 1 if args.warmup > 0 else 0
     value, dt = cpu_sample(args, threads, sample, n, max(1, args.steps), warm)
     line = {
@@ -366,7 +376,7 @@ def run_b200(args):
         line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sample = args.cpu_channels or 2 * threads
+        sample = cpu_sample_size(args, threads, n)
         v, dt = cpu_sample(args, threads, sample, n, 1, 1)
         line["cpu_baseline"] = {"value": v, "unit": "channels/s", "cores": threads, "kind": "port",
                                 "sample": "%d channels x %d samples, one pass, OpenMP over %d host threads (%.1f s)" % (sample, n, threads, dt)}

@@ -18,6 +18,7 @@
 // Rows are padded by one item in eight so the 64-byte lane stride maps to distinct banks.
 // FP32-pipe bound: 4*ntaps/D fma per input item (482 at the reference's 250 ksps default).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -29,7 +30,6 @@ using namespace b200ais;
 
 namespace {
 
-constexpr int kR = 8;          // outputs per thread
 constexpr int kMaxFreqs = 16;
 constexpr int kFront = 2;      // slack items in front of every residue row (window prefetch)
 
@@ -38,7 +38,8 @@ struct RotState {
     unsigned counter;
 };
 
-__host__ __device__ __forceinline__ int pad8(int u) { return u + (u >> 3); }
+// rows are padded by one item per R so that a lane stride of R items maps to distinct banks
+template <int R> __host__ __device__ __forceinline__ int padr(int u) { return u + (int)((unsigned)u / (unsigned)R); }
 
 // gr::blocks::rotator [G]: table[j] = phase before item j; phase *= incr (std::complex product,
 // separate multiplies and adds); every 512th item phase /= |phase|.  One lane per frequency.
@@ -70,13 +71,13 @@ __global__ void k_rot_phase(RotState *__restrict__ st, int nfreqs, int n, float2
     st[k].counter = counter;
 }
 
-struct Acc {
-    float Pr[kR], Pi[kR], Qr[kR], Qi[kR];
+template <int R> struct Acc {
+    float Pr[R], Pi[R], Qr[R], Qi[R];
 };
 
-// eight taps of one polyphase branch; GUARD: stop at `left` taps (warp-uniform)
-template <bool GUARD>
-__device__ __forceinline__ void fir_steps(Acc &a, float2 (&W)[kR], float2 &nxt, float2 &c,
+// R taps of one polyphase branch; GUARD: stop at `left` taps (warp-uniform)
+template <int kR, bool GUARD>
+__device__ __forceinline__ void fir_steps(Acc<kR> &a, float2 (&W)[kR], float2 &nxt, float2 &c,
                                           const float2 *__restrict__ tp, const float2 *__restrict__ xp,
                                           int u_next, int left)
 {
@@ -95,11 +96,11 @@ __device__ __forceinline__ void fir_steps(Acc &a, float2 (&W)[kR], float2 &nxt, 
             a.Qi[r] = __fmaf_rn(cc.y, x.y, a.Qi[r]);
         }
         W[(kR - 1 - s) & (kR - 1)] = nxt;
-        nxt = xp[pad8(u_next - s)];
+        nxt = xp[padr<kR>(u_next - s)];
     }
 }
 
-template <int THREADS>
+template <int THREADS, int kR>
 __global__ void __launch_bounds__(THREADS)
 k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int ntaps,
            const float2 *__restrict__ taps_pm, const int *__restrict__ pass_a,
@@ -128,7 +129,7 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
         int a = tid % D, m = tid / D;
         const int da = THREADS % D, dm = THREADS / D;
         for (int t = tid; t < T; t += THREADS) {
-            xs[a * Mp + pad8(m + kFront)] = row[t];
+            xs[a * Mp + padr<kR>(m + kFront)] = row[t];
             a += da;
             m += dm;
             if (a >= D) {
@@ -139,7 +140,7 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     }
     __syncthreads();
 
-    Acc acc;
+    Acc<kR> acc;
 #pragma unroll
     for (int r = 0; r < kR; r++)
         acc.Pr[r] = acc.Pi[r] = acc.Qr[r] = acc.Qi[r] = 0.f;
@@ -155,14 +156,14 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
         float2 W[kR];
 #pragma unroll
         for (int i = 0; i < kR; i++)
-            W[i] = xp[pad8(u0 + i)];
-        float2 nxt = xp[pad8(u0 - 1)];
+            W[i] = xp[padr<kR>(u0 + i)];
+        float2 nxt = xp[padr<kR>(u0 - 1)];
         float2 c = tp[0];
         int q = 0;
         for (; q + kR <= Q; q += kR)
-            fir_steps<false>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, kR);
+            fir_steps<kR, false>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, kR);
         if (q < Q)
-            fir_steps<true>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, Q - q);
+            fir_steps<kR, true>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, Q - q);
         tp += Q;
     }
 
@@ -191,11 +192,11 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     }
 }
 
-size_t xlat_smem_bytes(int threads, int D, int ntaps, int *Mp_out)
+size_t xlat_smem_bytes(int threads, int R, int D, int ntaps, int *Mp_out)
 {
-    const int J = threads * kR;
+    const int J = threads * R;
     const int M = J + (ntaps + D - 1) / D + kFront + 1;
-    const int Mp = pad8(M) + 1;
+    const int Mp = M + M / R + 1;
     if (Mp_out)
         *Mp_out = Mp;
     return sizeof(float2) * ((size_t)ntaps + 1 + (size_t)D * Mp);
@@ -331,7 +332,7 @@ extern "C" int b200ais_xlat_create(b200ais_xlat **out, int decimation, const flo
         set_error("xlat_create: bad arguments (1 <= nfreqs <= %d)", kMaxFreqs);
         return B200AIS_E_INVALID;
     }
-    if (xlat_smem_bytes(32, decimation, ntaps, nullptr) > 227 * 1024) {
+    if (xlat_smem_bytes(32, 8, decimation, ntaps, nullptr) > 227 * 1024) {
         set_error("xlat_create: decimation %d x %d taps does not fit shared memory", decimation, ntaps);
         return B200AIS_E_INVALID;
     }
@@ -414,7 +415,7 @@ extern "C" int b200ais_xlat_set_center_freq(b200ais_xlat *h, int k, double cente
 
 extern "C" int b200ais_xlat_set_taps(b200ais_xlat *h, const float *taps, int ntaps)
 {
-    if (!h || !taps || ntaps < 1 || xlat_smem_bytes(32, h->D, ntaps, nullptr) > 227 * 1024) {
+    if (!h || !taps || ntaps < 1 || xlat_smem_bytes(32, 8, h->D, ntaps, nullptr) > 227 * 1024) {
         set_error("xlat_set_taps: bad arguments");
         return B200AIS_E_INVALID;
     }
@@ -445,30 +446,27 @@ extern "C" int b200ais_xlat_reset(b200ais_xlat *h)
     return B200AIS_OK;
 }
 
-template <int THREADS>
+template <int THREADS, int R>
 static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_stride, float2 *out,
-                       size_t out_stride, int Mp, size_t smem, cudaStream_t s)
+                       size_t out_stride, cudaStream_t s)
 {
-    static bool attr_set[8] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 8 && !attr_set[dev]) {
-        B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
-        attr_set[dev] = true;
-    } else if (dev >= 8) {
-        B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
-    }
-    const int J = THREADS * kR;
+    int Mp = 0;
+    const size_t smem = xlat_smem_bytes(THREADS, R, h->D, h->ntaps, &Mp);
+    B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 227 * 1024));
+    const int J = THREADS * R;
     dim3 grid((unsigned)((n + J - 1) / J), (unsigned)h->sources, (unsigned)h->npass);
-    k_xlat_fir<THREADS><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps, h->d_taps,
-                                                    h->d_pass, h->d_pass + kMaxFreqs, h->nfreqs,
-                                                    h->rottab.as<float2>(), (size_t)n, out,
-                                                    out_stride, Mp);
+    k_xlat_fir<THREADS, R><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps, h->d_taps,
+                                                       h->d_pass, h->d_pass + kMaxFreqs, h->nfreqs,
+                                                       h->rottab.as<float2>(), (size_t)n, out,
+                                                       out_stride, Mp);
     B200_LAUNCH_CHECK("k_xlat_fir");
     return B200AIS_OK;
 }
+
+// tile shapes, best first: {threads, outputs per thread}
+static const int kShapes[][2] = {{128, 16}, {64, 16}, {128, 8}, {64, 8}, {32, 8}};
+static int g_xlat_shape = -1; // B200AIS_XLAT_SHAPE=<index> pins one (profiling)
 
 extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const float *in,
                                      size_t in_stride, float *out, size_t out_stride, void *stream)
@@ -493,24 +491,32 @@ extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const f
     B200_LAUNCH_CHECK("k_rot_phase");
     const float2 *x = reinterpret_cast<const float2 *>(in);
     float2 *y = reinterpret_cast<float2 *>(out);
-    int Mp = 0;
-    // largest tile that leaves room for at least two CTAs per SM, else whatever fits
-    const int cand[3] = {128, 64, 32};
+    if (g_xlat_shape < 0) {
+        const char *e = getenv("B200AIS_XLAT_SHAPE");
+        g_xlat_shape = e ? atoi(e) : 99;
+    }
+    // first shape that leaves room for two CTAs per SM, else the first that fits at all
     int pick = -1;
-    for (int i = 0; i < 3 && pick < 0; i++)
-        if (xlat_smem_bytes(cand[i], h->D, h->ntaps, nullptr) <= 113 * 1024)
-            pick = cand[i];
-    for (int i = 0; i < 3 && pick < 0; i++)
-        if (xlat_smem_bytes(cand[i], h->D, h->ntaps, nullptr) <= 227 * 1024)
-            pick = cand[i];
-    const size_t smem = xlat_smem_bytes(pick, h->D, h->ntaps, &Mp);
+    if (g_xlat_shape < 5 && xlat_smem_bytes(kShapes[g_xlat_shape][0], kShapes[g_xlat_shape][1], h->D,
+                                            h->ntaps, nullptr) <= 227 * 1024)
+        pick = g_xlat_shape;
+    for (int i = 0; i < 5 && pick < 0; i++)
+        if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= 113 * 1024)
+            pick = i;
+    for (int i = 0; i < 5 && pick < 0; i++)
+        if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= 227 * 1024)
+            pick = i;
     switch (pick) {
-    case 128:
-        return xlat_launch<128>(h, n, x, in_stride, y, out_stride, Mp, smem, s);
-    case 64:
-        return xlat_launch<64>(h, n, x, in_stride, y, out_stride, Mp, smem, s);
+    case 0:
+        return xlat_launch<128, 16>(h, n, x, in_stride, y, out_stride, s);
+    case 1:
+        return xlat_launch<64, 16>(h, n, x, in_stride, y, out_stride, s);
+    case 2:
+        return xlat_launch<128, 8>(h, n, x, in_stride, y, out_stride, s);
+    case 3:
+        return xlat_launch<64, 8>(h, n, x, in_stride, y, out_stride, s);
     default:
-        return xlat_launch<32>(h, n, x, in_stride, y, out_stride, Mp, smem, s);
+        return xlat_launch<32, 8>(h, n, x, in_stride, y, out_stride, s);
     }
 }
 

@@ -1,0 +1,90 @@
+#!/usr/bin/env python3
+"""Whole-receiver timing (ais_rx: channeliser -> demod -> hdlc -> nmea) on one B200.
+
+    python tools/bench_rx.py [--sources 2048] [--rate 250e3] [--seconds 1.0] [--pieces 1]
+One JSON line: AIS channels (2 per source) received per second, device-resident and end to end
+(pinned host IQ in, host messages + sentences out), and the messages decoded per step."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gr_ais_b200 import binding as B  # noqa: E402
+from gr_ais_b200 import synth  # noqa: E402
+from gr_ais_b200.radio import ais_rx  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sources", type=int, default=2048)
+    ap.add_argument("--rate", type=float, default=250e3)
+    ap.add_argument("--seconds", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    B.set_device(0)
+    torch.cuda.set_device(0)
+    n = int(a.rate * a.seconds)
+    S = a.sources
+    base, truth = synth.make_wideband(0, a.rate, n, nbursts=max(1, int(4 * a.seconds)), snr_db=20.0)
+    rx = ais_rx([-25e3, 25e3], a.rate, ["A", "B"], sources=S, max_input_items=n, max_frames=16)
+    max_msgs = rx.channels * 8
+    xb = torch.from_numpy(base.view(np.float32).reshape(n, 2)).cuda()
+    x = torch.empty((S, n, 2), device="cuda", dtype=torch.float32)
+    for s in range(S):
+        x[s] = torch.roll(xb, shifts=64 * s, dims=0)
+    msgs = torch.zeros(max_msgs * B.FRAME_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    sent = torch.zeros(max_msgs * rx.slot, dtype=torch.uint8, device="cuda")
+    lens = torch.zeros(max_msgs, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        rx.work_dev(x.data_ptr(), n, n, msgs.data_ptr(), sent.data_ptr(), lens.data_ptr(), max_msgs,
+                    cnt.data_ptr(), st)
+
+    launches0 = B.launch_count()
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    rx.status()
+    launches1 = B.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    rx.status()
+    ms = e0.elapsed_time(e1) / a.steps
+    line = {"metric": "AIS channels received/sec (channeliser->demod->hdlc->nmea)",
+            "sources": S, "channels": rx.channels, "rate": a.rate, "items_per_source": n,
+            "ms_per_step": ms, "value": rx.channels * a.seconds / (ms * 1e-3), "unit": "channels/s",
+            "messages_per_step": int(cnt.item()), "bursts_sent_per_source": len(truth),
+            "gpu_launches_per_step": (launches1 - launches0) // max(a.warmup, 1),
+            "input_bytes_per_step": S * n * 8}
+    if not a.no_e2e:
+        pin = B.PinnedArray((S, n), np.complex64)
+        pin.array[:] = x.cpu().numpy().view(np.complex64).reshape(S, n)
+        rx.reset()
+        rx.work(pin.array, max_msgs=max_msgs)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            m, s_ = rx.work(pin.array, max_msgs=max_msgs)
+        dt = (time.perf_counter() - t0) / a.steps
+        line["e2e"] = {"value": rx.channels * a.seconds / dt, "unit": "channels/s",
+                       "ms_per_step": dt * 1e3, "h2d_bytes_per_step": S * n * 8,
+                       "messages": len(m), "example": s_[0] if s_ else None}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
