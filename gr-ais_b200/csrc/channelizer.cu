@@ -31,7 +31,6 @@ using namespace b200ais;
 namespace {
 
 constexpr int kMaxFreqs = 16;
-constexpr int kFront = 2;      // slack items in front of every residue row (window prefetch)
 
 struct RotState {
     float pr, pi, ir, ii;
@@ -75,16 +74,25 @@ template <int R> struct Acc {
     float Pr[R], Pi[R], Qr[R], Qi[R];
 };
 
-// R taps of one polyphase branch; GUARD: stop at `left` taps (warp-uniform)
-template <int kR, bool GUARD>
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// R taps of one polyphase branch (the branches are zero-padded to whole groups of R taps:
+// fma(0, x, acc) leaves acc as it is for every finite x)
+template <int kR>
 __device__ __forceinline__ void fir_steps(Acc<kR> &a, float2 (&W)[kR], float2 &nxt, float2 &c,
                                           const float2 *__restrict__ tp, const float2 *__restrict__ xp,
-                                          int u_next, int left)
+                                          int u_next)
 {
 #pragma unroll
     for (int s = 0; s < kR; s++) {
-        if (GUARD && s >= left)
-            break;
         const float2 cc = c;
         c = tp[s + 1]; // the tap array has one slack item behind it
 #pragma unroll
@@ -102,34 +110,39 @@ __device__ __forceinline__ void fir_steps(Acc<kR> &a, float2 (&W)[kR], float2 &n
 
 template <int THREADS, int kR>
 __global__ void __launch_bounds__(THREADS)
-k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int ntaps,
+k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int ntaps, int ntp,
            const float2 *__restrict__ taps_pm, const int *__restrict__ pass_a,
            const int *__restrict__ pass_b, int nfreqs, const float2 *__restrict__ rot,
            size_t rot_stride, float2 *__restrict__ out, size_t out_stride, int Mp)
 {
     extern __shared__ float2 smem[];
-    float2 *tps = smem;                // [ntaps + 1] this pass's taps, polyphase-major
-    float2 *xs = smem + ntaps + 1;     // [D][Mp] input tile by residue mod D
+    float2 *tps = smem;            // [ntp + 1] this pass's taps, polyphase-major, zero-padded
+    float2 *xs = smem + ntp + 1;   // [D][Mp] input tile by residue mod D
     constexpr int J = THREADS * kR;
+    constexpr int kFront = kR + 2; // zeroed items in front of every residue row: the window of
+                                   // the padded taps and its prefetch end up there
     const int tid = threadIdx.x;
     const int src = blockIdx.y, pass = blockIdx.z;
     const int jb = blockIdx.x * J;
     const int jt = min(J, n - jb);
 
-    const float2 *tp_g = taps_pm + (size_t)pass * ntaps;
-    for (int k = tid; k < ntaps; k += THREADS)
-        tps[k] = tp_g[k];
+    const float2 *tp_g = taps_pm + (size_t)pass * ntp;
+    for (int k = tid; k < ntp; k += THREADS)
+        cp_async8(tps + k, tp_g + k);
     if (tid == 0)
-        tps[ntaps] = make_float2(0.f, 0.f);
+        tps[ntp] = make_float2(0.f, 0.f);
+    for (int k = tid; k < D * kFront; k += THREADS)
+        xs[(k / kFront) * Mp + padr<kR>(k % kFront)] = make_float2(0.f, 0.f);
 
-    // stage items [jb*D, jb*D + (jt-1)*D + ntaps) of the row: item t -> xs[t % D][t / D + kFront]
+    // stage items [jb*D, jb*D + (jt-1)*D + ntaps) of the row: item t -> xs[t % D][t / D + kFront],
+    // asynchronously: every copy is in flight before the first one is waited for
     const float2 *row = in + (size_t)src * in_stride + (size_t)jb * D;
     const int T = (jt - 1) * D + ntaps;
     {
         int a = tid % D, m = tid / D;
         const int da = THREADS % D, dm = THREADS / D;
         for (int t = tid; t < T; t += THREADS) {
-            xs[a * Mp + padr<kR>(m + kFront)] = row[t];
+            cp_async8(xs + a * Mp + padr<kR>(m + kFront), row + t);
             a += da;
             m += dm;
             if (a >= D) {
@@ -138,6 +151,7 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     Acc<kR> acc;
@@ -150,21 +164,18 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     for (int p = 0; p < D; p++) {
         const int lag = ntaps - 1 - p;
         const int b_p = lag / D, a_p = lag - b_p * D;
-        const int Q = b_p + 1; // taps p, p+D, ... < ntaps
+        const int Qpad = (b_p + kR) / kR * kR; // b_p + 1 taps (p, p+D, ... < ntaps), padded
         const float2 *xp = xs + a_p * Mp;
-        const int u0 = r0 + b_p + kFront; // window at tap 0: items u0 .. u0+7
+        const int u0 = r0 + b_p + kFront; // window at tap 0: items u0 .. u0+R-1
         float2 W[kR];
 #pragma unroll
         for (int i = 0; i < kR; i++)
             W[i] = xp[padr<kR>(u0 + i)];
         float2 nxt = xp[padr<kR>(u0 - 1)];
         float2 c = tp[0];
-        int q = 0;
-        for (; q + kR <= Q; q += kR)
-            fir_steps<kR, false>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, kR);
-        if (q < Q)
-            fir_steps<kR, true>(acc, W, nxt, c, tp + q, xp, u0 - q - 2, Q - q);
-        tp += Q;
+        for (int q = 0; q < Qpad; q += kR)
+            fir_steps<kR>(acc, W, nxt, c, tp + q, xp, u0 - q - 2);
+        tp += Qpad;
     }
 
     const int ka = pass_a[pass], kb = pass_b[pass];
@@ -192,14 +203,23 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     }
 }
 
+// taps of one pass, polyphase-major, every branch zero-padded to a multiple of R
+int xlat_padded_taps(int R, int D, int ntaps)
+{
+    int n = 0;
+    for (int p = 0; p < D && p < ntaps; p++)
+        n += ((ntaps - 1 - p) / D + R) / R * R;
+    return n;
+}
+
 size_t xlat_smem_bytes(int threads, int R, int D, int ntaps, int *Mp_out)
 {
     const int J = threads * R;
-    const int M = J + (ntaps + D - 1) / D + kFront + 1;
+    const int M = J + (ntaps + D - 1) / D + (R + 2) + 1;
     const int Mp = M + M / R + 1;
     if (Mp_out)
         *Mp_out = Mp;
-    return sizeof(float2) * ((size_t)ntaps + 1 + (size_t)D * Mp);
+    return sizeof(float2) * ((size_t)xlat_padded_taps(R, D, ntaps) + 1 + (size_t)D * Mp);
 }
 
 } // namespace
@@ -253,7 +273,8 @@ struct b200ais_xlat {
     std::vector<double> freqs;
     std::vector<std::vector<float2>> ctaps; // [nfreqs][ntaps]
     cudaStream_t stream = nullptr;
-    float2 *d_taps = nullptr; // [npass][ntaps] polyphase-major
+    float2 *d_taps[2] = {nullptr, nullptr}; // [npass][ntp] polyphase-major, branches padded to 8 / 16
+    int ntp[2] = {0, 0};
     int *d_pass = nullptr;    // [2][kMaxFreqs]
     RotState *d_rot = nullptr;
     DevBuf rottab, in, out;
@@ -303,18 +324,27 @@ static int xlat_upload(b200ais_xlat *h)
         np++;
     }
     h->npass = np;
-    std::vector<float2> pm((size_t)np * nt);
-    for (int p = 0; p < np; p++) {
-        size_t o = (size_t)p * nt;
-        for (int ph = 0; ph < D; ph++)
-            for (int k = ph; k < nt; k += D)
-                pm[o++] = h->ctaps[pa[p]][k];
+    for (int v = 0; v < 2; v++) {
+        const int R = v ? 16 : 8;
+        const int ntp = xlat_padded_taps(R, D, nt);
+        std::vector<float2> pm((size_t)np * ntp, make_float2(0.f, 0.f));
+        for (int p = 0; p < np; p++) {
+            size_t o = (size_t)p * ntp;
+            for (int ph = 0; ph < D && ph < nt; ph++) {
+                const int Qpad = ((nt - 1 - ph) / D + R) / R * R;
+                int q = 0;
+                for (int k = ph; k < nt; k += D)
+                    pm[o + q++] = h->ctaps[pa[p]][k];
+                o += Qpad;
+            }
+        }
+        if (h->d_taps[v])
+            cudaFree(h->d_taps[v]);
+        h->d_taps[v] = nullptr;
+        h->ntp[v] = ntp;
+        B200_CU(cudaMalloc(&h->d_taps[v], sizeof(float2) * pm.size()));
+        B200_CU(cudaMemcpy(h->d_taps[v], pm.data(), sizeof(float2) * pm.size(), cudaMemcpyHostToDevice));
     }
-    if (h->d_taps)
-        cudaFree(h->d_taps);
-    h->d_taps = nullptr;
-    B200_CU(cudaMalloc(&h->d_taps, sizeof(float2) * pm.size()));
-    B200_CU(cudaMemcpy(h->d_taps, pm.data(), sizeof(float2) * pm.size(), cudaMemcpyHostToDevice));
     int both[2 * kMaxFreqs];
     memcpy(both, pa, sizeof(pa));
     memcpy(both + kMaxFreqs, pb, sizeof(pb));
@@ -380,8 +410,9 @@ extern "C" int b200ais_xlat_destroy(b200ais_xlat *h)
         return B200AIS_OK;
     if (h->stream)
         cudaStreamDestroy(h->stream);
-    if (h->d_taps)
-        cudaFree(h->d_taps);
+    for (int v = 0; v < 2; v++)
+        if (h->d_taps[v])
+            cudaFree(h->d_taps[v]);
     if (h->d_pass)
         cudaFree(h->d_pass);
     if (h->d_rot)
@@ -456,7 +487,8 @@ static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_strid
                                  227 * 1024));
     const int J = THREADS * R;
     dim3 grid((unsigned)((n + J - 1) / J), (unsigned)h->sources, (unsigned)h->npass);
-    k_xlat_fir<THREADS, R><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps, h->d_taps,
+    k_xlat_fir<THREADS, R><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps,
+                                                       h->ntp[R == 16], h->d_taps[R == 16],
                                                        h->d_pass, h->d_pass + kMaxFreqs, h->nfreqs,
                                                        h->rottab.as<float2>(), (size_t)n, out,
                                                        out_stride, Mp);

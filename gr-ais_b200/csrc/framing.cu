@@ -446,9 +446,10 @@ k_gather_frames(const b200ais_frame *__restrict__ frames, const int *__restrict_
         atomicExch(status, B200AIS_E_FRAME_OVERFLOW);
         return;
     }
-    const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)c * max_frames);
-    uint4 *dst = reinterpret_cast<uint4 *>(dense + base);
-    const int words = nf * (int)(sizeof(b200ais_frame) / sizeof(uint4));
+    static_assert(sizeof(b200ais_frame) % sizeof(uint2) == 0, "frames are copied as 8-byte words");
+    const uint2 *src = reinterpret_cast<const uint2 *>(frames + (size_t)c * max_frames);
+    uint2 *dst = reinterpret_cast<uint2 *>(dense + base);
+    const int words = nf * (int)(sizeof(b200ais_frame) / sizeof(uint2));
     for (int k = 0; k < words; k++)
         dst[k] = src[k];
 }

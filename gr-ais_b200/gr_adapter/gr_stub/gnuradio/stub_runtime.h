@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <complex>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -27,12 +28,15 @@ template <class T> using shared_ptr = std::shared_ptr<T>;
 }
 
 namespace pmt {
+struct pmt_base;
+typedef std::shared_ptr<pmt_base> pmt_t;
 struct pmt_base {
     bool is_symbol = false;
     std::string sym;
     double dbl = 0.0;
+    std::vector<uint8_t> blob; // blob / u8vector payload
+    pmt_t car, cdr;            // pair
 };
-typedef std::shared_ptr<pmt_base> pmt_t;
 inline pmt_t intern(const std::string &s)
 {
     static std::map<std::string, pmt_t> table;
@@ -56,6 +60,27 @@ inline pmt_t from_double(double v)
 inline double to_double(const pmt_t &p) { return p->dbl; }
 inline bool eqv(const pmt_t &a, const pmt_t &b) { return a == b; }
 inline std::string symbol_to_string(const pmt_t &p) { return p->sym; }
+// the PDU subset gr::ais::pdu_to_nmea uses (lib/pdu_to_nmea_impl.cc:64-65,139-140)
+static const pmt_t PMT_NIL = std::make_shared<pmt_base>();
+inline pmt_t mp(const std::string &s) { return intern(s); }
+inline pmt_t cons(const pmt_t &a, const pmt_t &b)
+{
+    pmt_t p = std::make_shared<pmt_base>();
+    p->car = a;
+    p->cdr = b;
+    return p;
+}
+inline pmt_t car(const pmt_t &p) { return p->car; }
+inline pmt_t cdr(const pmt_t &p) { return p->cdr; }
+inline pmt_t make_blob(const void *data, size_t len)
+{
+    pmt_t p = std::make_shared<pmt_base>();
+    p->blob.assign(static_cast<const uint8_t *>(data), static_cast<const uint8_t *>(data) + len);
+    return p;
+}
+inline pmt_t init_u8vector(size_t len, const uint8_t *data) { return make_blob(data, len); }
+inline const void *blob_data(const pmt_t &p) { return p->blob.data(); }
+inline size_t blob_length(const pmt_t &p) { return p->blob.size(); }
 } // namespace pmt
 
 namespace gr {
@@ -112,6 +137,24 @@ protected:
     }
     std::string d_name;
     io_signature::sptr d_in, d_out;
+
+    // message ports: handlers run synchronously in post(); published messages are kept for
+    // the harness to read
+public:
+    typedef std::function<void(pmt::pmt_t)> msg_handler_t;
+    void message_port_register_in(pmt::pmt_t port) { d_handlers[pmt::symbol_to_string(port)]; }
+    void message_port_register_out(pmt::pmt_t port) { d_published[pmt::symbol_to_string(port)]; }
+    void set_msg_handler(pmt::pmt_t port, msg_handler_t h) { d_handlers[pmt::symbol_to_string(port)] = h; }
+    void message_port_pub(pmt::pmt_t port, pmt::pmt_t msg)
+    {
+        d_published[pmt::symbol_to_string(port)].push_back(msg);
+    }
+    void post(pmt::pmt_t port, pmt::pmt_t msg) { d_handlers.at(pmt::symbol_to_string(port))(msg); }
+    std::vector<pmt::pmt_t> &published(const std::string &port) { return d_published[port]; }
+
+private:
+    std::map<std::string, msg_handler_t> d_handlers;
+    std::map<std::string, std::vector<pmt::pmt_t>> d_published;
 };
 
 // gr::block: general_work() with forecast(); the harness sets the item counters and the

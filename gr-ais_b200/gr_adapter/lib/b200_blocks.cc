@@ -7,12 +7,14 @@
 //   msk_timing_recovery_cc_impl reference lib/msk_timing_recovery_cc_impl.cc:45-105, :107-206
 //   freqest_impl                reference lib/freqest_impl.cc:41-48, :57-88
 //   invert_impl                 reference lib/invert_impl.cc:41-68
+//   pdu_to_nmea_impl            reference lib/pdu_to_nmea_impl.cc:43-143
 // A failing C-ABI call becomes the exception the reference would have thrown
 // (std::out_of_range for argument ranges, std::runtime_error otherwise); there is no CPU path.
 #include <ais/corr_est_cc.h>
 #include <ais/freqest.h>
 #include <ais/invert.h>
 #include <ais/msk_timing_recovery_cc.h>
+#include <ais/pdu_to_nmea.h>
 
 #ifdef B200AIS_HAVE_GNURADIO
 #include <gnuradio/io_signature.h>
@@ -22,8 +24,11 @@
 #include <b200ais.h>
 
 #include <cmath>
+#include <cstring>
+#include <iostream>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace gr {
 namespace ais {
@@ -268,6 +273,71 @@ public:
 };
 
 invert::sptr invert::make() { return gnuradio::get_initial_sptr(new invert_impl()); }
+
+// ------------------------------------------------------------------ pdu_to_nmea
+
+class pdu_to_nmea_impl : public pdu_to_nmea
+{
+public:
+    explicit pdu_to_nmea_impl(std::string designator)
+        : gr::block("pdu_to_nmea", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)),
+          d_designator(designator)
+    {
+        if (designator.empty() || designator.size() > 8)
+            throw std::invalid_argument("pdu_to_nmea: designator must be 1..8 characters");
+        message_port_register_in(pmt::mp("print"));
+        set_msg_handler(pmt::mp("print"), [this](pmt::pmt_t m) { this->print(m); });
+        message_port_register_in(pmt::mp("to_nmea"));
+        set_msg_handler(pmt::mp("to_nmea"), [this](pmt::pmt_t m) { this->to_nmea(m); });
+        message_port_register_out(pmt::mp("out"));
+    }
+
+    // msg_to_sentence (reference lib/pdu_to_nmea_impl.cc:127-131) on the device
+    std::string msg_to_sentence(pmt::pmt_t msg)
+    {
+        const uint8_t *p = static_cast<const uint8_t *>(pmt::blob_data(pmt::cdr(msg)));
+        const size_t len = pmt::blob_length(pmt::cdr(msg));
+        if (len < 1 || len > B200AIS_FRAME_MAX)
+            throw std::runtime_error("pdu_to_nmea: PDU length outside [1, 248]");
+        b200ais_frame fr;
+        memset(&fr, 0, sizeof(fr));
+        fr.len = (int32_t)len;
+        memcpy(fr.data, p, len);
+        const int one = 1;
+        char des[8] = {0};
+        memcpy(des, d_designator.data(), d_designator.size());
+        const int slot = b200ais_nmea_slot_bytes((int)len, d_designator.c_str());
+        std::vector<char> out((size_t)slot);
+        int n = 0;
+        throw_on(b200ais_nmea_format(&fr, &one, 1, 1, des, out.data(), slot, &n));
+        if (n < 0)
+            throw std::runtime_error("pdu_to_nmea: sentence does not fit");
+        return std::string(out.data(), (size_t)n);
+    }
+
+    void print(pmt::pmt_t msg) override { std::cout << msg_to_sentence(msg) << std::endl; }
+
+    void to_nmea(pmt::pmt_t msg) override
+    {
+        std::string aivdm = msg_to_sentence(msg);
+        pmt::pmt_t pdu(pmt::cons(pmt::PMT_NIL,
+                                 pmt::init_u8vector(aivdm.length(), (const uint8_t *)aivdm.c_str())));
+        message_port_pub(pmt::mp("out"), pdu);
+    }
+
+    int general_work(int, gr_vector_int &, gr_vector_const_void_star &, gr_vector_void_star &) override
+    {
+        return 0; // message block: no streams
+    }
+
+private:
+    std::string d_designator;
+};
+
+pdu_to_nmea::sptr pdu_to_nmea::make(std::string designator)
+{
+    return gnuradio::get_initial_sptr(new pdu_to_nmea_impl(designator));
+}
 
 } // namespace ais
 } // namespace gr

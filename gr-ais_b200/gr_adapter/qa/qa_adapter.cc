@@ -9,6 +9,7 @@
 #include <ais/corr_est_cc.h>
 #include <ais/freqest.h>
 #include <ais/invert.h>
+#include <ais/pdu_to_nmea.h>
 #include <ais/msk_timing_recovery_cc.h>
 
 #include <cstdio>
@@ -140,6 +141,21 @@ int main(int argc, char **argv)
             threw |= 2;
         }
         put(fo, &threw, 4);
+
+        // pdu_to_nmea: a 21-byte PDU (bytes 7*i+1) and a 53-byte one posted to "to_nmea";
+        // the sentences come back as u8vector PDUs on "out"
+        gr::ais::pdu_to_nmea::sptr nm = gr::ais::pdu_to_nmea::make("B");
+        for (int len : { 21, 53 }) {
+            std::vector<uint8_t> pdu((size_t)len);
+            for (int i = 0; i < len; i++)
+                pdu[(size_t)i] = (uint8_t)(7 * i + 1);
+            nm->post(pmt::mp("to_nmea"), pmt::cons(pmt::PMT_NIL, pmt::make_blob(pdu.data(), pdu.size())));
+        }
+        for (auto &m : nm->published("out")) {
+            int32_t sl = (int32_t)pmt::blob_length(pmt::cdr(m));
+            put(fo, &sl, 4);
+            put(fo, pmt::blob_data(pmt::cdr(m)), (size_t)sl);
+        }
         fseek(fo, 0, SEEK_SET);
         put(fo, &total_tags, 4);
         put(fo, &total_sym, 4);

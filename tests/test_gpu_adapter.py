@@ -72,5 +72,11 @@ def test_cpp_adapter_chain_matches_oracle(oracle, templates, tmp_path):
     inv = np.frombuffer(buf, np.uint8, 1000, pos); pos += 1000
     src = ((np.arange(1000) * 7 + 3) & 0xFF).astype(np.uint8)
     assert np.array_equal(inv, oracle.invert(src))
-    (threw,) = struct.unpack_from("<i", buf, pos)
+    (threw,) = struct.unpack_from("<i", buf, pos); pos += 4
     assert threw == 3      # both constructor range errors surfaced as std::out_of_range
+    # gr::ais::pdu_to_nmea through its "to_nmea" message port
+    for n in (21, 53):
+        (sl,) = struct.unpack_from("<i", buf, pos); pos += 4
+        text = bytes(buf[pos:pos + sl]).decode("latin-1"); pos += sl
+        pdu = bytes((7 * i + 1) & 0xFF for i in range(n))
+        assert text == oracle.pdu_to_nmea(pdu, "B")
