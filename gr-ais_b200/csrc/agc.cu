@@ -26,7 +26,9 @@ k_mix_agc(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, i
           float2 *__restrict__ out, size_t out_stride)
 {
     extern __shared__ float2 ys[]; // [span] mixed samples, then env[span], then tmp[span]
-    const int c = blockIdx.y;
+    const int c = channel_index();
+    if (c >= channels)
+        return;
     const int t0 = blockIdx.x * kAgcTile;
     const int tile = min(kAgcTile, n1 - t0);
     const bool do_mix = stages & B200AIS_STAGE_FREQSYNC;
@@ -188,7 +190,9 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     float *P = reinterpret_cast<float *>(ys + kFPad); // prefix maxima  [kFPad]
     float *S = P + kFPad;                             // suffix maxima  [kFPad]
     const int tid = threadIdx.x, lane = tid & 31;
-    const int c = blockIdx.y;
+    const int c = channel_index();
+    if (c >= channels)
+        return;
     const int t0 = blockIdx.x * kFOut;
     const int n0 = t0 - kFHalo + 16 * tid; // absolute index of this thread's first sample
     const float2 *xc = x + (size_t)c * x_stride;
@@ -332,7 +336,7 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
     if ((stages & B200AIS_STAGE_AGC) && agc_nsamples == 512 && seg == 16 &&
         (!(stages & B200AIS_STAGE_FREQSYNC) || (fftlen % 16 == 0 && n1 % fftlen == 0))) {
         const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float));
-        dim3 grid512((n1 + kFOut - 1) / kFOut, channels);
+        dim3 grid512 = channel_grid((n1 + kFOut - 1) / kFOut, channels);
         const int do_mix = (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0;
         const float2 *sine = reinterpret_cast<const float2 *>(tb.sine);
         if (hist_in || hist_out) {
@@ -363,7 +367,7 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
     size_t smem = (size_t)(kAgcTile + halo) * (sizeof(float2) + 2 * sizeof(float));
     B200_CU(cudaFuncSetAttribute(k_mix_agc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((kAgcTile + 2047) * (sizeof(float2) + 2 * sizeof(float)))));
-    dim3 grid((n1 + kAgcTile - 1) / kAgcTile, channels);
+    dim3 grid = channel_grid((n1 + kAgcTile - 1) / kAgcTile, channels);
     k_mix_agc<<<grid, kAgcThreads, smem, s>>>(x, x_stride, channels, n1, fftlen, fhat, vstride, ckpt, seg,
                                               sens, stages, agc_nsamples, agc_reference,
                                               reinterpret_cast<const float2 *>(tb.sine), out,

@@ -52,11 +52,22 @@ __global__ void k_rot_phase(RotState *__restrict__ st, int nfreqs, int n, float2
     const float ir = st[k].ir, ii = st[k].ii;
     unsigned counter = st[k].counter;
     float2 *t = tab + (size_t)k * tab_stride;
-    for (int j = 0; j < n; j++) {
-        t[j] = make_float2(pr, pi);
-        counter++;
+    // runs that end on a multiple of 512 items (or at n): only a run's last step can normalise,
+    // so the others are a bare two-deep multiply-add chain
+    for (int j = 0; j < n;) {
+        const int run = min(n - j, 512 - (int)(counter & 511u));
+#pragma unroll 8
+        for (int q = 0; q < run - 1; q++) {
+            t[j + q] = make_float2(pr, pi);
+            const float nr = pr * ir - pi * ii;
+            const float ni = pr * ii + pi * ir;
+            pr = nr;
+            pi = ni;
+        }
+        t[j + run - 1] = make_float2(pr, pi);
         float nr = pr * ir - pi * ii;
         float ni = pr * ii + pi * ir;
+        counter += (unsigned)run;
         if ((counter & 511u) == 0) {
             const float a = hypot_canon(nr, ni);
             nr = nr / a;
@@ -64,6 +75,7 @@ __global__ void k_rot_phase(RotState *__restrict__ st, int nfreqs, int n, float2
         }
         pr = nr;
         pi = ni;
+        j += run;
     }
     st[k].pr = pr;
     st[k].pi = pi;

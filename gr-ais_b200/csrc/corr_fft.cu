@@ -205,9 +205,11 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
            const float2 *__restrict__ tw, const float2 *__restrict__ hbr, float thresh,
            const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
            uint32_t *__restrict__ mask, size_t mask_stride_words, float2 *__restrict__ corr_out,
-           size_t corr_stride)
+           size_t corr_stride, int channels)
 {
     using P = Plan<LOGF>;
+    if (channel_index() >= channels)
+        return;
     constexpr int F = P::F, NT = P::NT, GROUPS = P::GROUPS;
     extern __shared__ float4 smem_raw[];
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);     // [F/2]
@@ -218,7 +220,7 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_tail + 3 * GROUPS * (L > 1 ? L - 1 : 1));
 
     const int ns = F - L + 1, tl = L - 1;
-    const int c = blockIdx.y;
+    const int c = channel_index();
     const int b0 = blockIdx.x * nb_per_cta;
     const int g = threadIdx.x / NT, t = threadIdx.x % NT;
     const int nwords = (nb_per_cta * ns) >> 5;
@@ -328,10 +330,10 @@ int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, in
     }
     B200_CU(cudaFuncSetAttribute(k_corr_fft<LOGF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    dim3 grid((nblocks + nb - 1) / nb, channels);
+    dim3 grid = channel_grid((nblocks + nb - 1) / nb, channels);
     k_corr_fft<LOGF><<<grid, P::THREADS, smem, s>>>(in, in_stride, nblocks, L, nb, tw, hbr, thresh,
                                                     tail_in, tail_out, mask, msw, corr_out,
-                                                    corr_stride);
+                                                    corr_stride, channels);
     B200_LAUNCH_CHECK("k_corr_fft");
     return B200AIS_OK;
 }

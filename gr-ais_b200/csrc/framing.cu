@@ -35,6 +35,7 @@ __device__ __forceinline__ unsigned crc_ccitt(const unsigned char *d, int len)
 
 struct Deframer {
     int ones, bitctr, bytectr;
+    unsigned cur; // the byte being assembled (d_pktbuf[d_bytectr] of the reference block)
     int length_min, length_max;
     unsigned char buf[B200AIS_FRAME_MAX + 8];
     b200ais_frame *frames;
@@ -42,52 +43,69 @@ struct Deframer {
     unsigned long long base;
     bool overflow;
 
-    // hdlc_deframer_bp_impl::work [G], one bit
+    __device__ __noinline__ void delimiter(int i)
+    {
+        if (bytectr >= length_min) {
+            const int len = bytectr - 2;
+            const unsigned crc = crc_ccitt(buf, len);
+            const unsigned got = (unsigned)buf[len] | ((unsigned)buf[len + 1] << 8);
+            if (crc == got) {
+                if (nf < max_frames) {
+                    b200ais_frame *f = frames + nf;
+                    f->end_bit = base + (unsigned long long)i;
+                    f->len = len;
+                    f->channel = channel;
+                    for (int k = 0; k < len; k++)
+                        f->data[k] = buf[k];
+                    for (int k = len; k < B200AIS_FRAME_MAX; k++)
+                        f->data[k] = 0;
+                    nf++;
+                } else {
+                    overflow = true;
+                }
+            }
+        }
+        bitctr = 0;
+        bytectr = 0;
+    }
+
+    // hdlc_deframer_bp_impl::work [G], one bit.  The partial byte lives in a register: the
+    // reference shifts it in place in d_pktbuf, and stale high bits leave it the same way.
     __device__ __forceinline__ void step(unsigned bit, int i)
     {
         if (ones >= 5) {
-            if (bit) { // six ones: frame delimiter
-                if (bytectr >= length_min) {
-                    const int len = bytectr - 2;
-                    const unsigned crc = crc_ccitt(buf, len);
-                    const unsigned got = (unsigned)buf[len] | ((unsigned)buf[len + 1] << 8);
-                    if (crc == got) {
-                        if (nf < max_frames) {
-                            b200ais_frame *f = frames + nf;
-                            f->end_bit = base + (unsigned long long)i;
-                            f->len = len;
-                            f->channel = channel;
-                            for (int k = 0; k < len; k++)
-                                f->data[k] = buf[k];
-                            for (int k = len; k < B200AIS_FRAME_MAX; k++)
-                                f->data[k] = 0;
-                            nf++;
-                        } else {
-                            overflow = true;
-                        }
-                    }
-                }
-                bitctr = 0;
-                bytectr = 0;
-            } // else: stuffed zero, dropped
+            if (bit) // six ones: frame delimiter
+                delimiter(i);
+            // else: stuffed zero, dropped
         } else if (bytectr > length_max) {
             bytectr = 0;
             bitctr = 0;
         } else {
-            unsigned v = buf[bytectr] >> 1;
-            if (bit)
-                v |= 0x80u;
-            buf[bytectr] = (unsigned char)v;
+            cur = (cur >> 1) | (bit << 7);
             if (++bitctr == 8) {
+                buf[bytectr++] = (unsigned char)cur;
                 bitctr = 0;
-                bytectr++;
             }
         }
         ones = bit ? ones + 1 : 0;
     }
+
+    // sixteen unpacked bits held one per byte in w
+    __device__ __forceinline__ void step16(uint4 w, int i)
+    {
+        const unsigned m = (((w.x & 0x01010101u) * 0x01020408u) >> 24) |
+                           ((((w.y & 0x01010101u) * 0x01020408u) >> 24) << 4) |
+                           ((((w.z & 0x01010101u) * 0x01020408u) >> 24) << 8) |
+                           ((((w.w & 0x01010101u) * 0x01020408u) >> 24) << 12);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            step((m >> k) & 1u, i + k);
+    }
 };
 
-__global__ void __launch_bounds__(64)
+// One lane per channel.  Rows are read 16 bits (one 128-bit load) at a time, the next load
+// issued before the current bits are walked.
+__global__ void __launch_bounds__(32)
 k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restrict__ nbits,
        int nbits_all, int channels, HdlcState *__restrict__ state, int length_min, int length_max,
        b200ais_frame *__restrict__ frames, int max_frames, int *__restrict__ nframes, int *status)
@@ -108,22 +126,24 @@ k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restri
     d.channel = c;
     d.base = st->nitems_read;
     d.overflow = false;
-    for (int k = 0; k < B200AIS_FRAME_MAX + 8; k++)
+    for (int k = 0; k < d.bytectr; k++)
         d.buf[k] = st->pktbuf[k];
+    d.cur = st->pktbuf[d.bytectr];
 
     const int n = nbits ? nbits[c] : nbits_all;
     const uint8_t *row = bits + (size_t)c * bits_stride;
     int i = 0;
     while (i < n && ((reinterpret_cast<uintptr_t>(row + i)) & 15))
         d.step(row[i] & 1u, i), i++;
-    for (; i + 16 <= n; i += 16) {
-        const uint4 w = *reinterpret_cast<const uint4 *>(row + i);
-        const unsigned v[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-#pragma unroll
-            for (int b = 0; b < 4; b++)
-                d.step((v[q] >> (8 * b)) & 1u, i + 4 * q + b);
+    if (i + 16 <= n) {
+        uint4 w = *reinterpret_cast<const uint4 *>(row + i);
+        for (; i + 32 <= n; i += 16) {
+            const uint4 nx = *reinterpret_cast<const uint4 *>(row + i + 16);
+            d.step16(w, i);
+            w = nx;
+        }
+        d.step16(w, i);
+        i += 16;
     }
     for (; i < n; i++)
         d.step(row[i] & 1u, i);
@@ -132,8 +152,9 @@ k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restri
     st->bitctr = d.bitctr;
     st->bytectr = d.bytectr;
     st->nitems_read = d.base + (unsigned long long)(n > 0 ? n : 0);
-    for (int k = 0; k < B200AIS_FRAME_MAX + 8; k++)
+    for (int k = 0; k < d.bytectr; k++)
         st->pktbuf[k] = d.buf[k];
+    st->pktbuf[d.bytectr] = (unsigned char)d.cur;
     nframes[c] = d.nf;
     if (d.overflow)
         atomicExch(status, B200AIS_E_FRAME_OVERFLOW);
@@ -322,7 +343,7 @@ extern "C" int b200ais_hdlc_work_dev(b200ais_hdlc *h, const uint8_t *bits, size_
         return B200AIS_E_INVALID;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int threads = 64;
+    const int threads = 32;
     k_hdlc<<<(h->channels + threads - 1) / threads, threads, 0, s>>>(
         bits, bits_stride, nbits, nbits_all, h->channels, h->d_state, h->length_min, h->length_max,
         frames, max_frames, nframes, h->d_status);

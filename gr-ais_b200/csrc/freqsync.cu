@@ -62,12 +62,14 @@ __device__ __forceinline__ Best block_argmax(Best v, Best *sh)
 // |X| in fft-shifted order -> argmax_j |S[j]| + |S[j+offset]|.
 __global__ void __launch_bounds__(kFftThreads)
 k_sqfft_freqest(const float2 *__restrict__ x, size_t x_stride, int vstride, int n, int lg,
-                const float2 *__restrict__ tw, int offset, int *__restrict__ raw)
+                const float2 *__restrict__ tw, int offset, int *__restrict__ raw, int channels)
 {
+    if (channel_index() >= channels)
+        return;
     extern __shared__ float2 buf[];
     float *hs = reinterpret_cast<float *>(buf + n);
     __shared__ Best sh[kFftThreads / 32];
-    const int b = blockIdx.x, c = blockIdx.y;
+    const int b = blockIdx.x, c = channel_index();
     const float2 *src = x + (size_t)c * x_stride + (size_t)b * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         float2 v = src[i];
@@ -158,15 +160,17 @@ __device__ __forceinline__ void pass8(float2 (&u)[8], const float2 w1, const flo
 
 __global__ void __launch_bounds__(kFast)
 k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
-                     const float2 *__restrict__ tw, int offset, int *__restrict__ raw)
+                     const float2 *__restrict__ tw, int offset, int *__restrict__ raw, int channels)
 {
     constexpr int N = 1024;
+    if (channel_index() >= channels)
+        return;
     __shared__ float2 cx[N + N / 16];
     __shared__ float hs[N];
     __shared__ Best sh[kFast / 32];
     __shared__ float s_max[kFast / 32];
     const int tid = threadIdx.x;
-    const int b = blockIdx.x, c = blockIdx.y;
+    const int b = blockIdx.x, c = channel_index();
     const float2 *src = x + (size_t)c * x_stride + (size_t)b * N;
 
     // ---- pass A: stages 1-4 on elements e = 16*tid + q, loaded from x[bitrev10(e)] ----
@@ -283,10 +287,13 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
 
 // Stand-alone freqest on caller-supplied spectra (any fftlen).
 __global__ void __launch_bounds__(kFftThreads)
-k_freqest_spec(const float2 *__restrict__ spec, int nvec, int n, int offset, int *__restrict__ raw)
+k_freqest_spec(const float2 *__restrict__ spec, int nvec, int n, int offset, int *__restrict__ raw,
+               int channels)
 {
+    if (channel_index() >= channels)
+        return;
     __shared__ Best sh[kFftThreads / 32];
-    const int b = blockIdx.x, c = blockIdx.y;
+    const int b = blockIdx.x, c = channel_index();
     const float2 *in = spec + ((size_t)c * nvec + b) * (size_t)n;
     Best best;
     best.e = 0.0f;
@@ -398,14 +405,15 @@ int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nve
     if (rc)
         return rc;
     size_t smem = (size_t)fftlen * (sizeof(float2) + sizeof(float));
-    dim3 grid(nvec, channels);
+    dim3 grid = channel_grid(nvec, channels);
     if (fftlen == 1024) {
-        k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw);
+        k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw, channels);
     } else {
         if (smem > 40 * 1024) // static shared memory counts towards the 48 KB default limit
             B200_CU(cudaFuncSetAttribute(k_sqfft_freqest, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-        k_sqfft_freqest<<<grid, kFftThreads, smem, s>>>(x, x_stride, vstride, fftlen, lg, tw, offset, raw);
+        k_sqfft_freqest<<<grid, kFftThreads, smem, s>>>(x, x_stride, vstride, fftlen, lg, tw, offset, raw,
+                                                        channels);
     }
     B200_LAUNCH_CHECK("k_sqfft_freqest");
     return B200AIS_OK;
@@ -416,8 +424,8 @@ int launch_freqest_spec(const float2 *spec, int channels, int nvec, int fftlen, 
 {
     if (nvec <= 0 || channels <= 0)
         return B200AIS_OK;
-    dim3 grid(nvec, channels);
-    k_freqest_spec<<<grid, kFftThreads, 0, s>>>(spec, nvec, fftlen, offset, raw);
+    dim3 grid = channel_grid(nvec, channels);
+    k_freqest_spec<<<grid, kFftThreads, 0, s>>>(spec, nvec, fftlen, offset, raw, channels);
     B200_LAUNCH_CHECK("k_freqest_spec");
     return B200AIS_OK;
 }

@@ -57,6 +57,18 @@ struct DevBuf {
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
+// Channels ride on grid.y, and on grid.z beyond the 65535 limit of grid.y:
+// c = blockIdx.z * gridDim.y + blockIdx.y, CTAs with c >= channels return at once.
+inline dim3 channel_grid(unsigned x, int channels)
+{
+    const unsigned z = ((unsigned)channels + 65534u) / 65535u;
+    const unsigned y = ((unsigned)channels + z - 1) / z;
+    return dim3(x, y, z);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int channel_index() { return (int)(blockIdx.z * gridDim.y + blockIdx.y); }
+#endif
+
 // Regenerated GNU Radio data tables, resident in global memory of the current device.
 struct Tables {
     const float *mmse; // [129][8]  mmse_fir_interpolator taps

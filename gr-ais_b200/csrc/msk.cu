@@ -423,7 +423,9 @@ k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict_
     for (int i = threadIdx.x; i < 257; i += blockDim.x)
         s_atan[i] = g_atan[i];
     __syncthreads();
-    const int c = blockIdx.y;
+    const int c = channel_index();
+    if (c >= channels)
+        return;
     const int n = nsym[c];
     const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (k0 >= n)
@@ -585,7 +587,7 @@ int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int chann
     int rc = get_tables(&tb);
     if (rc)
         return rc;
-    dim3 grid((max_sym + 4 * 128 - 1) / (4 * 128), channels);
+    dim3 grid = channel_grid((max_sym + 4 * 128 - 1) / (4 * 128), channels);
     k_tail<<<grid, 128, 0, s>>>(sym, sym_stride, nsym, channels, tb.atan, bits, bits_stride, soft,
                                 carry);
     B200_LAUNCH_CHECK("k_tail");

@@ -1,0 +1,46 @@
+"""GPU path against the committed golden vectors (tests/golden/*.npz): bits, tags and NMEA
+sentences must equal the stored ones exactly.  Nothing here touches oracle/."""
+import os
+
+import numpy as np
+import pytest
+
+from gr_ais_b200 import binding as B
+from gr_ais_b200.ais_demod import ais_demod
+from gr_ais_b200.radio import ais_rx
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(name):
+    return np.load(os.path.join(HERE, "golden", name))
+
+
+def test_chain_equals_golden_vectors():
+    z = load("chain_kat.npz")
+    for name in ("l120", "l140"):
+        x = z[name + "_iq"]
+        d = ais_demod(channels=3, max_samples=len(x), template=z[name + "_template"])
+        bits, nbits, tags, ntags = d.work(np.stack([x, x, x]))
+        for c in range(3):
+            assert np.array_equal(bits[c, :nbits[c]], z[name + "_bits"])
+            for f in ("offset", "key", "port", "value"):
+                assert np.array_equal(tags[c, :ntags[c]][f], z[name + "_tags"][f]), f
+        d.close()
+
+
+def test_ais_rx_equals_golden_sentences():
+    z = load("rx_kat.npz")
+    x = z["iq"]
+    rx = ais_rx([-25e3, 25e3], float(z["rate"]), ["A", "B"], sources=2, max_input_items=len(x))
+    got = []
+    for a, b in ((0, 30001), (30001, len(x))):
+        msgs, sents = rx.work(np.stack([x[a:b], x[a:b]]))
+        got += list(zip(msgs["channel"].tolist(), msgs["end_bit"].tolist(), sents))
+    want = list(z["sentences"])
+    ends = list(z["end_bit0"]) + list(z["end_bit1"])
+    for s in range(2):
+        mine = sorted((c - 2 * s, e, t) for c, e, t in got if c // 2 == s)
+        assert [t for _, _, t in mine] == want
+        assert [e for _, e, _ in mine] == ends
