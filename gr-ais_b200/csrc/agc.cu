@@ -182,7 +182,7 @@ template <bool kHist> // kHist: stream mode, AGC history in / out
 __global__ void __launch_bounds__(256, 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
-             int do_mix, float reference, const float2 *__restrict__ sine,
+             int do_mix, float reference, const float4 *__restrict__ sine,
              float2 *__restrict__ out, size_t out_stride, const float2 *__restrict__ hist_in,
              float2 *__restrict__ hist_out)
 {
@@ -244,7 +244,7 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
             bad = bad || !(ph >= -1.5f * F_2PI && ph < F_PI);
             const float folded = (ph < -F_PI) ? ph + F_2PI : ph;
             float sn, cs;
-            fxpt_sincos(float_to_fixed_inrange(folded), sine, &sn, &cs);
+            fxpt_sincos4(float_to_fixed_inrange(folded), sine, &sn, &cs);
             v[k] = cmul_fma(v[k], make_float2(cs, sn));
         }
         if (bad) { // general path (fmod, fold, true division) from the raw samples still in ys
@@ -253,7 +253,7 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
             for (int k = 0; k < 16; k++) {
                 ph = nco_step(ph, inc);
                 float sn, cs;
-                fxpt_sincos(float_to_fixed(ph), sine, &sn, &cs);
+                fxpt_sincos4(float_to_fixed(ph), sine, &sn, &cs);
                 v[k] = cmul_fma(ys[17 * tid + k], make_float2(cs, sn));
             }
         }
@@ -338,7 +338,7 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
         const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float));
         dim3 grid512 = channel_grid((n1 + kFOut - 1) / kFOut, channels);
         const int do_mix = (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0;
-        const float2 *sine = reinterpret_cast<const float2 *>(tb.sine);
+        const float4 *sine = reinterpret_cast<const float4 *>(tb.sine4);
         if (hist_in || hist_out) {
             if (!hist_in || !hist_out || hist_in == hist_out) {
                 set_error("mix_agc: stream mode needs distinct history buffers in and out");

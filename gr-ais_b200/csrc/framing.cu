@@ -33,75 +33,67 @@ __device__ __forceinline__ unsigned crc_ccitt(const unsigned char *d, int len)
     return (crc ^ 0xFFFFu) & 0xFFFFu;
 }
 
-struct Deframer {
-    int ones, bitctr, bytectr;
-    unsigned cur; // the byte being assembled (d_pktbuf[d_bytectr] of the reference block)
-    int length_min, length_max;
-    unsigned char buf[B200AIS_FRAME_MAX + 8];
-    b200ais_frame *frames;
-    int max_frames, nf, channel;
-    unsigned long long base;
-    bool overflow;
+// A delimiter closed a frame of `bytectr` bytes (CRC included): check it and publish it.
+// Out of line and by value, so the bit loop's state stays in registers.  Returns the new
+// frame count, or -1 when the row of frames is full.
+__device__ __noinline__ int hdlc_emit(const unsigned char *buf, int bytectr, b200ais_frame *frames,
+                                      int nf, int max_frames, int channel, unsigned long long end_bit)
+{
+    const int len = bytectr - 2;
+    const unsigned crc = crc_ccitt(buf, len);
+    const unsigned got = (unsigned)buf[len] | ((unsigned)buf[len + 1] << 8);
+    if (crc != got)
+        return nf;
+    if (nf >= max_frames)
+        return -1;
+    b200ais_frame *f = frames + nf;
+    f->end_bit = end_bit;
+    f->len = len;
+    f->channel = channel;
+    for (int k = 0; k < len; k++)
+        f->data[k] = buf[k];
+    for (int k = len; k < B200AIS_FRAME_MAX; k++)
+        f->data[k] = 0;
+    return nf + 1;
+}
 
-    __device__ __noinline__ void delimiter(int i)
-    {
-        if (bytectr >= length_min) {
-            const int len = bytectr - 2;
-            const unsigned crc = crc_ccitt(buf, len);
-            const unsigned got = (unsigned)buf[len] | ((unsigned)buf[len + 1] << 8);
-            if (crc == got) {
-                if (nf < max_frames) {
-                    b200ais_frame *f = frames + nf;
-                    f->end_bit = base + (unsigned long long)i;
-                    f->len = len;
-                    f->channel = channel;
-                    for (int k = 0; k < len; k++)
-                        f->data[k] = buf[k];
-                    for (int k = len; k < B200AIS_FRAME_MAX; k++)
-                        f->data[k] = 0;
-                    nf++;
-                } else {
-                    overflow = true;
-                }
-            }
-        }
-        bitctr = 0;
-        bytectr = 0;
-    }
+// hdlc_deframer_bp_impl::work [G], one bit.  The partial byte lives in a register (`cur`):
+// the reference shifts it in place in d_pktbuf, and stale high bits leave it the same way.
+#define HDLC_STEP(bit_, i_)                                                                  \
+    do {                                                                                     \
+        const unsigned b__ = (bit_);                                                         \
+        if (ones >= 5) {                                                                     \
+            if (b__) { /* six ones: frame delimiter */                                       \
+                if (bytectr >= length_min) {                                                 \
+                    const int r__ = hdlc_emit(buf, bytectr, myframes, nf, max_frames, c,     \
+                                              base + (unsigned long long)(i_));              \
+                    overflow |= r__ < 0;                                                     \
+                    nf = r__ < 0 ? nf : r__;                                                 \
+                }                                                                            \
+                bitctr = 0;                                                                  \
+                bytectr = 0;                                                                 \
+            } /* else: stuffed zero, dropped */                                              \
+        } else if (bytectr > length_max) {                                                   \
+            bytectr = 0;                                                                     \
+            bitctr = 0;                                                                      \
+        } else {                                                                             \
+            cur = (cur >> 1) | (b__ << 7);                                                   \
+            if (++bitctr == 8) {                                                             \
+                buf[bytectr++] = (unsigned char)cur;                                         \
+                bitctr = 0;                                                                  \
+            }                                                                                \
+        }                                                                                    \
+        ones = b__ ? ones + 1 : 0;                                                           \
+    } while (0)
 
-    // hdlc_deframer_bp_impl::work [G], one bit.  The partial byte lives in a register: the
-    // reference shifts it in place in d_pktbuf, and stale high bits leave it the same way.
-    __device__ __forceinline__ void step(unsigned bit, int i)
-    {
-        if (ones >= 5) {
-            if (bit) // six ones: frame delimiter
-                delimiter(i);
-            // else: stuffed zero, dropped
-        } else if (bytectr > length_max) {
-            bytectr = 0;
-            bitctr = 0;
-        } else {
-            cur = (cur >> 1) | (bit << 7);
-            if (++bitctr == 8) {
-                buf[bytectr++] = (unsigned char)cur;
-                bitctr = 0;
-            }
-        }
-        ones = bit ? ones + 1 : 0;
-    }
-
-    // sixteen unpacked bits held one per byte in w
-    __device__ __forceinline__ void step16(uint4 w, int i)
-    {
-        const unsigned m = (((w.x & 0x01010101u) * 0x01020408u) >> 24) |
-                           ((((w.y & 0x01010101u) * 0x01020408u) >> 24) << 4) |
-                           ((((w.z & 0x01010101u) * 0x01020408u) >> 24) << 8) |
-                           ((((w.w & 0x01010101u) * 0x01020408u) >> 24) << 12);
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            step((m >> k) & 1u, i + k);
-    }
-};
+// sixteen unpacked bits, one per byte of w, as a 16-bit mask (bit k = k-th bit of the stream)
+__device__ __forceinline__ unsigned pack16(uint4 w)
+{
+    return (((w.x & 0x01010101u) * 0x01020408u) >> 24) |
+           ((((w.y & 0x01010101u) * 0x01020408u) >> 24) << 4) |
+           ((((w.z & 0x01010101u) * 0x01020408u) >> 24) << 8) |
+           ((((w.w & 0x01010101u) * 0x01020408u) >> 24) << 12);
+}
 
 // One lane per channel.  Rows are read 16 bits (one 128-bit load) at a time, the next load
 // issued before the current bits are walked.
@@ -114,51 +106,54 @@ k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restri
     if (c >= channels)
         return;
     HdlcState *st = state + c;
-    Deframer d;
-    d.ones = st->ones;
-    d.bitctr = st->bitctr;
-    d.bytectr = st->bytectr;
-    d.length_min = length_min;
-    d.length_max = length_max;
-    d.frames = frames + (size_t)c * max_frames;
-    d.max_frames = max_frames;
-    d.nf = 0;
-    d.channel = c;
-    d.base = st->nitems_read;
-    d.overflow = false;
-    for (int k = 0; k < d.bytectr; k++)
-        d.buf[k] = st->pktbuf[k];
-    d.cur = st->pktbuf[d.bytectr];
+    unsigned char buf[B200AIS_FRAME_MAX + 8];
+    int ones = st->ones, bitctr = st->bitctr, bytectr = st->bytectr, nf = 0;
+    bool overflow = false;
+    const unsigned long long base = st->nitems_read;
+    b200ais_frame *myframes = frames + (size_t)c * max_frames;
+    for (int k = 0; k < bytectr; k++)
+        buf[k] = st->pktbuf[k];
+    unsigned cur = st->pktbuf[bytectr];
 
     const int n = nbits ? nbits[c] : nbits_all;
     const uint8_t *row = bits + (size_t)c * bits_stride;
     int i = 0;
-    while (i < n && ((reinterpret_cast<uintptr_t>(row + i)) & 15))
-        d.step(row[i] & 1u, i), i++;
+    while (i < n && ((reinterpret_cast<uintptr_t>(row + i)) & 15)) {
+        HDLC_STEP(row[i] & 1u, i);
+        i++;
+    }
     if (i + 16 <= n) {
         uint4 w = *reinterpret_cast<const uint4 *>(row + i);
         for (; i + 32 <= n; i += 16) {
             const uint4 nx = *reinterpret_cast<const uint4 *>(row + i + 16);
-            d.step16(w, i);
+            const unsigned m = pack16(w);
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                HDLC_STEP((m >> k) & 1u, i + k);
             w = nx;
         }
-        d.step16(w, i);
+        const unsigned m = pack16(w);
+#pragma unroll 1
+        for (int k = 0; k < 16; k++)
+            HDLC_STEP((m >> k) & 1u, i + k);
         i += 16;
     }
+#pragma unroll 1
     for (; i < n; i++)
-        d.step(row[i] & 1u, i);
+        HDLC_STEP(row[i] & 1u, i);
 
-    st->ones = d.ones;
-    st->bitctr = d.bitctr;
-    st->bytectr = d.bytectr;
-    st->nitems_read = d.base + (unsigned long long)(n > 0 ? n : 0);
-    for (int k = 0; k < d.bytectr; k++)
-        st->pktbuf[k] = d.buf[k];
-    st->pktbuf[d.bytectr] = (unsigned char)d.cur;
-    nframes[c] = d.nf;
-    if (d.overflow)
+    st->ones = ones;
+    st->bitctr = bitctr;
+    st->bytectr = bytectr;
+    st->nitems_read = base + (unsigned long long)(n > 0 ? n : 0);
+    for (int k = 0; k < bytectr; k++)
+        st->pktbuf[k] = buf[k];
+    st->pktbuf[bytectr] = (unsigned char)cur;
+    nframes[c] = nf;
+    if (overflow)
         atomicExch(status, B200AIS_E_FRAME_OVERFLOW);
 }
+#undef HDLC_STEP
 
 __device__ __forceinline__ int put_int(char *o, int v)
 {

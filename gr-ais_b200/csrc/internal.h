@@ -74,6 +74,8 @@ struct Tables {
     const float *mmse; // [129][8]  mmse_fir_interpolator taps
     const float *atan; // [257]     gr::fast_atan2f
     const float *sine; // [1024][2] gr::fxpt sine table {slope, intercept}
+    const float *sine4; // [1024][4] the same, entry i = {sine[i], sine[(i + 256) % 1024]}: the
+                        // sine and cosine segments of one angle in a single 16-byte load
 };
 int get_tables(Tables *t);
 // FFT twiddles for length n on the current device: n/2 complex, W[k] = exp(-2 pi i k/n)

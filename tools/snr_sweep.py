@@ -5,7 +5,8 @@ Per SNR point: `--channels` channels, independent noise per channel, random payl
 offset U(-500, 500) Hz, random phase, fractional delay U(0, 1) sample.
 Reports, for the GPU path and (on a subset of channels) the oracle:
   detect rate = bursts with a corr_start tag within +-sps of where the preamble correlates
-  crc rate    = bursts whose payload comes out of the CPU HDLC deframer with a good CRC
+  crc rate    = bursts whose payload comes out of hdlc_deframer_bp(11, 64) with a good CRC
+                (GPU path: b200ais_hdlc_work; oracle: its C restatement)
 and checks the two paths agree bit for bit on the oracle subset.
 
     python tools/snr_sweep.py --channels 16384 --snrs 0 2 4 6 8 10 12 14 16 18 20
@@ -28,11 +29,10 @@ def expected_tag_offset(start, L, agc_delay=511, pulse_delay=20, ramp=8 * 5, tem
     return start + ramp + pulse_delay + agc_delay + L - template_delay - 1
 
 
-def score(bits, nbits, tags, ntags, truth, L, sps=5):
-    from gr_ais_b200 import synth
+def score(pdus, tags, ntags, truth, L, sps=5):
     det = crc = tot = 0
     for c in range(len(truth)):
-        found = set(synth.hdlc_deframe(bits[c, :nbits[c]]))
+        found = set(pdus[c])
         cs = tags[c, :ntags[c]]
         cs = cs[cs["key"] == 0]["offset"].astype(np.int64)
         for t in truth[c]:
@@ -59,6 +59,8 @@ def main():
     tmpl = preamble_template("north_star")
     d = ais_demod(channels=args.channels, max_samples=n, template=tmpl, threshold=args.threshold,
                   max_tags=1024)
+    from gr_ais_b200 import blocks
+    deframer = blocks.hdlc_deframer_bp(11, 64, channels=args.channels)
     rows = []
     for snr in args.snrs:
         recs = [synth.make_record(c, n=n, nbursts=max(1, int(4 * args.seconds)), snr_db=snr,
@@ -67,7 +69,9 @@ def main():
         x = np.stack([r[0] for r in recs])
         truth = [r[1] for r in recs]
         bits, nbits, tags, ntags = d.work(x)
-        det, crc, tot = score(bits, nbits, tags, ntags, truth, len(tmpl))
+        deframer.reset()
+        frames, nframes = deframer.work(bits, nbits, max_frames=32)
+        det, crc, tot = score(deframer.pdus(frames, nframes), tags, ntags, truth, len(tmpl))
         k = min(args.oracle_channels, args.channels)
         ob, onb, ot, ont = O.demod_chain_batch(x[:k], tmpl, O.chain_cfg(threshold=args.threshold),
                                                max_tags=1024)
@@ -75,7 +79,9 @@ def main():
                    and ont[c] == ntags[c]
                    and np.array_equal(ot[c, :ont[c]]["offset"], tags[c, :ntags[c]]["offset"])
                    for c in range(k))
-        odet, ocrc, otot = score(ob, onb, ot.view(tags.dtype), ont, truth[:k], len(tmpl))
+        opdus = [O.frames_payloads(O.HdlcDeframer(11, 64).work(ob[c, :onb[c]])) for c in range(k)]
+        same = same and all(opdus[c] == deframer.pdus(frames, nframes)[c] for c in range(k))
+        odet, ocrc, otot = score(opdus, ot.view(tags.dtype), ont, truth[:k], len(tmpl))
         rows.append(dict(snr_db=snr, bursts=tot, gpu_detect=det / tot, gpu_crc=crc / tot,
                          oracle_bursts=otot, oracle_detect=odet / otot, oracle_crc=ocrc / otot,
                          gpu_equals_oracle_on_subset=bool(same)))
