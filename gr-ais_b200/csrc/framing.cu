@@ -15,35 +15,20 @@ using namespace b200ais;
 namespace {
 
 struct HdlcState {
-    int ones, bitctr, bytectr, pad;
+    int ones, bitctr, bytectr;
+    unsigned crcs; // running CRC register (low half) and its value at the last byte boundary
+                   // (high half), both ^ 0xFFFF so that a zeroed state means "fresh"
     unsigned long long nitems_read;
     unsigned char pktbuf[B200AIS_FRAME_MAX + 8];
 };
 
-// hdlc_deframer_bp_impl::crc_ccitt [G]: CRC-16/X.25
-__device__ __forceinline__ unsigned crc_ccitt(const unsigned char *d, int len)
-{
-    unsigned crc = 0xFFFFu;
-    for (int i = 0; i < len; i++) {
-        crc ^= d[i];
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            crc = (crc & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
-    }
-    return (crc ^ 0xFFFFu) & 0xFFFFu;
-}
-
-// A delimiter closed a frame of `bytectr` bytes (CRC included): check it and publish it.
-// Out of line and by value, so the bit loop's state stays in registers.  Returns the new
-// frame count, or -1 when the row of frames is full.
+// A delimiter closed a frame whose CRC is good: publish it.  Out of line and by value, so the
+// bit loop's state stays in registers.  Returns the new frame count, or -1 when the row of
+// frames is full.
 __device__ __noinline__ int hdlc_emit(const unsigned char *buf, int bytectr, b200ais_frame *frames,
                                       int nf, int max_frames, int channel, unsigned long long end_bit)
 {
     const int len = bytectr - 2;
-    const unsigned crc = crc_ccitt(buf, len);
-    const unsigned got = (unsigned)buf[len] | ((unsigned)buf[len + 1] << 8);
-    if (crc != got)
-        return nf;
     if (nf >= max_frames)
         return -1;
     b200ais_frame *f = frames + nf;
@@ -57,14 +42,22 @@ __device__ __noinline__ int hdlc_emit(const unsigned char *buf, int bytectr, b20
     return nf + 1;
 }
 
-// hdlc_deframer_bp_impl::work [G], one bit.  The partial byte lives in a register (`cur`):
-// the reference shifts it in place in d_pktbuf, and stale high bits leave it the same way.
+// hdlc_deframer_bp_impl::work [G], one bit.
+//  * The partial byte lives in a register (`cur`): the reference shifts it in place in
+//    d_pktbuf, and stale high bits leave it the same way.
+//  * The CRC runs with the bits instead of over the buffer at every delimiter (noise closes a
+//    "frame" every ~250 bits, and a lane walking 20-odd bytes stalls its whole warp): frame
+//    bits arrive LSB first, which is the reflected CRC's own bit order, so the register takes
+//    one shift/xor per stored bit; `crcb` is its value at the last byte boundary (the bits after
+//    it are the closing flag's).  crc_ccitt(data) == the two bytes that follow, the reference's
+//    test, holds exactly when the register over data + those two bytes is the CRC-16/X.25
+//    residue 0xF0B8 (for a given prefix the last 16 bits map one-to-one onto the register).
 #define HDLC_STEP(bit_, i_)                                                                  \
     do {                                                                                     \
         const unsigned b__ = (bit_);                                                         \
         if (ones >= 5) {                                                                     \
             if (b__) { /* six ones: frame delimiter */                                       \
-                if (bytectr >= length_min) {                                                 \
+                if (bytectr >= length_min && crcb == 0xF0B8u) {                              \
                     const int r__ = hdlc_emit(buf, bytectr, myframes, nf, max_frames, c,     \
                                               base + (unsigned long long)(i_));              \
                     overflow |= r__ < 0;                                                     \
@@ -72,15 +65,19 @@ __device__ __noinline__ int hdlc_emit(const unsigned char *buf, int bytectr, b20
                 }                                                                            \
                 bitctr = 0;                                                                  \
                 bytectr = 0;                                                                 \
+                crc = crcb = 0xFFFFu;                                                        \
             } /* else: stuffed zero, dropped */                                              \
         } else if (bytectr > length_max) {                                                   \
             bytectr = 0;                                                                     \
             bitctr = 0;                                                                      \
+            crc = crcb = 0xFFFFu;                                                            \
         } else {                                                                             \
             cur = (cur >> 1) | (b__ << 7);                                                   \
+            crc = (crc >> 1) ^ (((crc ^ b__) & 1u) ? 0x8408u : 0u);                          \
             if (++bitctr == 8) {                                                             \
                 buf[bytectr++] = (unsigned char)cur;                                         \
                 bitctr = 0;                                                                  \
+                crcb = crc;                                                                  \
             }                                                                                \
         }                                                                                    \
         ones = b__ ? ones + 1 : 0;                                                           \
@@ -114,6 +111,7 @@ k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restri
     for (int k = 0; k < bytectr; k++)
         buf[k] = st->pktbuf[k];
     unsigned cur = st->pktbuf[bytectr];
+    unsigned crc = (st->crcs & 0xFFFFu) ^ 0xFFFFu, crcb = (st->crcs >> 16) ^ 0xFFFFu;
 
     const int n = nbits ? nbits[c] : nbits_all;
     const uint8_t *row = bits + (size_t)c * bits_stride;
@@ -145,6 +143,7 @@ k_hdlc(const uint8_t *__restrict__ bits, size_t bits_stride, const int *__restri
     st->ones = ones;
     st->bitctr = bitctr;
     st->bytectr = bytectr;
+    st->crcs = ((crc ^ 0xFFFFu) & 0xFFFFu) | ((crcb ^ 0xFFFFu) << 16);
     st->nitems_read = base + (unsigned long long)(n > 0 ? n : 0);
     for (int k = 0; k < bytectr; k++)
         st->pktbuf[k] = buf[k];
