@@ -53,6 +53,7 @@ EXPORTS = [
     "b200ais_rx_default_config", "b200ais_rx_create", "b200ais_rx_destroy", "b200ais_rx_reset",
     "b200ais_rx_decimation", "b200ais_rx_channels", "b200ais_rx_samples_per_symbol",
     "b200ais_rx_sentence_slot", "b200ais_rx_work", "b200ais_rx_work_dev", "b200ais_rx_status",
+    "b200ais_rx_replay_file",
 ]
 FRAME_MAX = 248
 FRAME_DTYPE = np.dtype([("end_bit", "<u8"), ("len", "<i4"), ("channel", "<i4"),
@@ -76,6 +77,9 @@ class RxConfig(C.Structure):
                 ("clockrec_gain", C.c_float), ("omega_relative_limit", C.c_float),
                 ("fftlen", C.c_int), ("lpf_cutoff", C.c_double), ("lpf_transition", C.c_double),
                 ("hdlc_length_min", C.c_int), ("hdlc_length_max", C.c_int)]
+
+
+RX_SINK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int)
 
 
 class B200AisError(RuntimeError):
@@ -195,6 +199,7 @@ def lib():
     L.b200ais_rx_samples_per_symbol.restype = C.c_float
     L.b200ais_rx_work.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, C.POINTER(i)]
     L.b200ais_rx_work_dev.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, vp, vp]
+    L.b200ais_rx_replay_file.argtypes = [vp, C.c_char_p, i, i, RX_SINK, vp, C.POINTER(u64)]
     _lib = L
     return L
 

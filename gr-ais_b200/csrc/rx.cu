@@ -5,7 +5,9 @@
 // straight into the demod chain's assembly rows; nothing between the wideband input and the
 // NMEA sentences leaves the device.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
+#include <future>
 #include <new>
 #include <vector>
 
@@ -293,4 +295,121 @@ extern "C" int b200ais_rx_work(b200ais_rx *h, const float *iq, size_t iq_stride,
         B200_CU(cudaStreamSynchronize(s));
     }
     return B200AIS_OK;
+}
+
+// ------------------------------------------------------------ recorded-IQ replay
+
+namespace {
+
+// one capture to every source row: dst[s][i] = src[i]
+__global__ void __launch_bounds__(256)
+k_fanout(const float2 *__restrict__ src, int n, float2 *__restrict__ dst, size_t dst_stride, int sources)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float2 v = src[i];
+    for (int s = blockIdx.y; s < sources; s += gridDim.y)
+        dst[(size_t)s * dst_stride + i] = v;
+}
+
+size_t read_items(FILE *f, float2 *dst, size_t want)
+{
+    return fread(dst, sizeof(float2), want, f);
+}
+
+} // namespace
+
+// blocks.file_source(gr.sizeof_gr_complex, filename) (python/radio.py:204-207) feeding every
+// source of the receiver with the same recorded capture (replay fan-out): raw interleaved
+// float32 IQ, read in chunks through two pinned buffers -- the read of chunk k+1 runs on a
+// host thread while chunk k is copied and processed -- copied to the device once and
+// replicated there.
+extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk_items, int max_msgs,
+                                      b200ais_rx_sink sink, void *user, uint64_t *items_read)
+{
+    if (!h || !path || chunk_items < 1 || chunk_items > h->cfg.max_input_items || max_msgs < 1) {
+        set_error("rx_replay_file: bad arguments (chunk_items <= max_input_items)");
+        return B200AIS_E_INVALID;
+    }
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        set_error("rx_replay_file: cannot open %s", path);
+        return B200AIS_E_INVALID;
+    }
+    float2 *pin[2] = {nullptr, nullptr}, *d_stage = nullptr;
+    std::vector<b200ais_frame> msgs((size_t)max_msgs);
+    std::vector<char> sent((size_t)max_msgs * h->slot);
+    std::vector<int> lens((size_t)max_msgs);
+    int rc = B200AIS_OK;
+    uint64_t total = 0;
+    cudaError_t e = cudaMallocHost(&pin[0], sizeof(float2) * (size_t)chunk_items);
+    if (e == cudaSuccess) e = cudaMallocHost(&pin[1], sizeof(float2) * (size_t)chunk_items);
+    if (e == cudaSuccess) e = cudaMalloc(&d_stage, sizeof(float2) * (size_t)chunk_items);
+    if (e == cudaSuccess && h->out_cap < max_msgs) {
+        if (h->d_msgs) cudaFree(h->d_msgs);
+        if (h->d_sent) cudaFree(h->d_sent);
+        if (h->d_lens) cudaFree(h->d_lens);
+        h->d_msgs = nullptr;
+        h->d_sent = nullptr;
+        h->d_lens = nullptr;
+        h->out_cap = 0;
+        e = cudaMalloc(&h->d_msgs, sizeof(b200ais_frame) * (size_t)max_msgs);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_sent, (size_t)h->slot * max_msgs);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_lens, sizeof(int) * (size_t)max_msgs);
+        if (e == cudaSuccess) h->out_cap = max_msgs;
+    }
+    if (e != cudaSuccess)
+        rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+    cudaStream_t s = h->stream;
+    const int S = h->cfg.sources;
+    size_t have = rc ? 0 : read_items(f, pin[0], (size_t)chunk_items);
+    for (int k = 0; !rc && have > 0; k++) {
+        float2 *cur = pin[k & 1];
+        // next chunk from the file while this one is on the device
+        std::future<size_t> next = std::async(std::launch::async, read_items, f, pin[(k + 1) & 1],
+                                              (size_t)chunk_items);
+        const int n = (int)have;
+        e = cudaMemcpyAsync(d_stage, cur, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            dim3 grid((unsigned)((n + 255) / 256), (unsigned)std::min(S, 64));
+            k_fanout<<<grid, 256, 0, s>>>(d_stage, n, h->d_x + h->carry, h->x_stride, S);
+            count_launch();
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+        } else {
+            rc = rx_run(h, n, h->d_msgs, h->d_sent, h->slot, h->d_lens, max_msgs, h->d_count, s);
+        }
+        int cnt = 0;
+        if (!rc) {
+            e = cudaMemcpyAsync(&cnt, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess)
+                rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+        }
+        if (!rc)
+            rc = b200ais_rx_status(h);
+        if (!rc && cnt > 0) {
+            e = cudaMemcpy(msgs.data(), h->d_msgs, sizeof(b200ais_frame) * (size_t)cnt, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(lens.data(), h->d_lens, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(sent.data(), h->d_sent, (size_t)h->slot * cnt, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess)
+                rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+            else if (sink)
+                sink(user, msgs.data(), sent.data(), h->slot, lens.data(), cnt);
+        }
+        total += (uint64_t)n;
+        have = next.get(); // always joined, also on errors
+    }
+    if (items_read)
+        *items_read = total;
+    fclose(f);
+    if (pin[0]) cudaFreeHost(pin[0]);
+    if (pin[1]) cudaFreeHost(pin[1]);
+    if (d_stage) cudaFree(d_stage);
+    return rc;
 }

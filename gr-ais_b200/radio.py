@@ -10,6 +10,7 @@ source (python/radio.py:86-91); here one object carries every (source, frequency
 Fails loudly without the CUDA library or a device: there is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -101,6 +102,30 @@ class ais_rx:
         B.check(B.lib().b200ais_rx_work_dev(self._h, B.ptr(iq_ptr), int(iq_stride), int(nitems),
                                             B.ptr(msgs_ptr), B.ptr(sent_ptr), self.slot,
                                             B.ptr(lens_ptr), int(max_msgs), B.ptr(nmsgs_ptr), stream))
+
+    def replay_file(self, path, chunk_items=None, max_msgs=None):
+        """blocks.file_source(gr.sizeof_gr_complex, path) into every source (python/radio.py:
+        204-207): raw interleaved float32 IQ, double-buffered pinned reads.  Returns
+        (msgs, sentences, items_read) over the whole file, sorted by (channel, end_bit)."""
+        chunk_items = int(chunk_items or self.cfg.max_input_items)
+        max_msgs = int(max_msgs or self.channels * self.cfg.max_frames)
+        got_m, got_s = [], []
+
+        def sink(user, msgs, sent, slot, lens, n):
+            m = np.frombuffer((C.c_char * (n * B.FRAME_DTYPE.itemsize)).from_address(msgs),
+                              dtype=B.FRAME_DTYPE).copy()
+            ln = np.frombuffer((C.c_char * (4 * n)).from_address(lens), dtype=np.int32)
+            raw = np.frombuffer((C.c_char * (n * slot)).from_address(sent), dtype=np.uint8).reshape(n, slot)
+            got_m.append(m)
+            got_s.extend(bytes(raw[i, :ln[i]]).decode("latin-1") for i in range(n))
+
+        cb = B.RX_SINK(sink)
+        items = C.c_uint64(0)
+        B.check(B.lib().b200ais_rx_replay_file(self._h, os.fsencode(path), chunk_items, max_msgs, cb,
+                                               None, C.byref(items)))
+        msgs = np.concatenate(got_m) if got_m else np.zeros(0, dtype=B.FRAME_DTYPE)
+        order = np.lexsort((msgs["end_bit"], msgs["channel"]))
+        return msgs[order], [got_s[i] for i in order], items.value
 
     def status(self):
         B.check(B.lib().b200ais_rx_status(self._h))

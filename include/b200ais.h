@@ -428,6 +428,17 @@ B200AIS_API int b200ais_rx_work_dev(b200ais_rx *h, const float *iq, size_t iq_st
                                     b200ais_frame *msgs, char *sentences, int slot, int *lens,
                                     int max_msgs, int *nmsgs, void *stream);
 B200AIS_API int b200ais_rx_status(b200ais_rx *h);
+/* Recorded-IQ replay: blocks.file_source(gr.sizeof_gr_complex, path) (python/radio.py:204-207)
+ * feeding every source of the receiver with the same capture.  The file (raw interleaved
+ * float32 IQ) is read in chunks of chunk_items through two pinned buffers, the read of the next
+ * chunk overlapping the copy and the processing of the current one; each chunk crosses PCIe
+ * once and is replicated on the device.  sink (nullable) is called once per chunk that
+ * completed messages, on the calling thread. */
+typedef void (*b200ais_rx_sink)(void *user, const b200ais_frame *msgs, const char *sentences,
+                                int slot, const int *lens, int nmsgs);
+B200AIS_API int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk_items,
+                                       int max_msgs, b200ais_rx_sink sink, void *user,
+                                       uint64_t *items_read);
 
 #ifdef __cplusplus
 }
