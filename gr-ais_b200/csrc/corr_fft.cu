@@ -199,9 +199,11 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
     }
 }
 
-template <int LOGF>
+// LT: the tap count when it is known at compile time (0 = run-time L): with F = 256 and the
+// north-star's 120 taps every `element < ns` test on a slot other than q = 8 folds away.
+template <int LOGF, int LT>
 __global__ void __launch_bounds__(Plan<LOGF>::THREADS, (LOGF <= 8 ? 5 : (LOGF <= 10 ? 3 : 1)))
-k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, int nb_per_cta,
+k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_rt, int nb_per_cta,
            const float2 *__restrict__ tw, const float2 *__restrict__ hbr, float thresh,
            const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
            uint32_t *__restrict__ mask, size_t mask_stride_words, float2 *__restrict__ corr_out,
@@ -211,6 +213,7 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
     if (channel_index() >= channels)
         return;
     constexpr int F = P::F, NT = P::NT, GROUPS = P::GROUPS;
+    const int L = LT ? LT : L_rt;
     extern __shared__ float4 smem_raw[];
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);     // [F/2]
     float2 *s_h = s_tw + F / 2;                              // [F] as float4 pairs [8][NT]
@@ -313,7 +316,7 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L, 
         mrow[i] = s_mask[i];
 }
 
-template <int LOGF>
+template <int LOGF, int LT>
 int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, int L, int nb,
                const float2 *tw, const float2 *hbr, float thresh, const float2 *tail_in,
                float2 *tail_out, uint32_t *mask, size_t msw, float2 *corr_out, size_t corr_stride,
@@ -328,10 +331,10 @@ int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, in
         set_error("corr_est: %d taps need %zu bytes of shared memory", L, smem);
         return B200AIS_E_INVALID;
     }
-    B200_CU(cudaFuncSetAttribute(k_corr_fft<LOGF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CU(cudaFuncSetAttribute(k_corr_fft<LOGF, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     dim3 grid = channel_grid((nblocks + nb - 1) / nb, channels);
-    k_corr_fft<LOGF><<<grid, P::THREADS, smem, s>>>(in, in_stride, nblocks, L, nb, tw, hbr, thresh,
+    k_corr_fft<LOGF, LT><<<grid, P::THREADS, smem, s>>>(in, in_stride, nblocks, L, nb, tw, hbr, thresh,
                                                     tail_in, tail_out, mask, msw, corr_out,
                                                     corr_stride, channels);
     B200_LAUNCH_CHECK("k_corr_fft");
@@ -394,8 +397,11 @@ int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int
     const size_t msw = mask_stride / 4;
 #define B200_CASE(LG)                                                                             \
     case LG:                                                                                      \
-        return launch_one<LG>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh, tail_in,  \
-                              tail_out, m32, msw, corr_out, corr_stride, s);
+        return launch_one<LG, 0>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh,       \
+                                 tail_in, tail_out, m32, msw, corr_out, corr_stride, s);
+    if (L == 120) // the north-star template: tap count folded into the kernel
+        return launch_one<8, 120>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh, tail_in,
+                                  tail_out, m32, msw, corr_out, corr_stride, s);
     switch (lg) {
         B200_CASE(4)
         B200_CASE(5)
