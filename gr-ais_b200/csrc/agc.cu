@@ -8,6 +8,8 @@
 // mixed samples y[t-W+1 .. t] (W = agc window), so the block re-mixes a halo of W-1
 // samples in front of its tile from the phase checkpoints written by k_nco_phase; the
 // mixed stream itself never goes to HBM.
+#include <cstdlib>
+
 #include "device_math.cuh"
 #include "internal.h"
 
@@ -178,11 +180,13 @@ constexpr int kFHalo = 512;
 constexpr int kFOut = kFSpan - kFHalo;
 constexpr int kFPad = kFSpan + kFSpan / 16; // 1-in-16 padding: a thread's 16 items hit 16 banks
 
-template <bool kHist> // kHist: stream mode, AGC history in / out
-__global__ void __launch_bounds__(256, 3)
+// kHist: stream mode, AGC history in / out.  kTab: the paired sine table is copied to shared
+// memory (16 KB more per CTA: two CTAs per SM instead of three)
+template <bool kHist, bool kTab>
+__global__ void __launch_bounds__(256, kTab ? 2 : 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
-             int do_mix, float reference, const float4 *__restrict__ sine,
+             int do_mix, float reference, const float4 *sine,
              float2 *__restrict__ out, size_t out_stride, const float2 *__restrict__ hist_in,
              float2 *__restrict__ hist_out)
 {
@@ -190,6 +194,12 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     float *P = reinterpret_cast<float *>(ys + kFPad); // prefix maxima  [kFPad]
     float *S = P + kFPad;                             // suffix maxima  [kFPad]
     const int tid = threadIdx.x, lane = tid & 31;
+    if (kTab) {
+        float4 *st = reinterpret_cast<float4 *>(S + kFPad);
+        for (int i = tid; i < 1024; i += 256)
+            st[i] = sine[i];
+        sine = st; // published by the barrier below
+    }
     const int c = channel_index();
     if (c >= channels)
         return;
@@ -335,7 +345,13 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
         return rc;
     if ((stages & B200AIS_STAGE_AGC) && agc_nsamples == 512 && seg == 16 &&
         (!(stages & B200AIS_STAGE_FREQSYNC) || (fftlen % 16 == 0 && n1 % fftlen == 0))) {
-        const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float));
+        static int tab = -1; // B200AIS_MIX_SMEMTAB=1: sine table in shared memory (experiment)
+        if (tab < 0) {
+            const char *e = getenv("B200AIS_MIX_SMEMTAB");
+            tab = (e && atoi(e)) ? 1 : 0;
+        }
+        const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float)) +
+                               (tab ? 1024 * sizeof(float4) : 0);
         dim3 grid512 = channel_grid((n1 + kFOut - 1) / kFOut, channels);
         const int do_mix = (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0;
         const float4 *sine = reinterpret_cast<const float4 *>(tb.sine4);
@@ -344,18 +360,25 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
                 set_error("mix_agc: stream mode needs distinct history buffers in and out");
                 return B200AIS_E_INVALID;
             }
-            B200_CU(cudaFuncSetAttribute(k_mix_agc512<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem512));
-            k_mix_agc512<true><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,
-                                                             vstride, ckpt, sens, do_mix, agc_reference,
-                                                             sine, out, out_stride, hist_in, hist_out);
+#define B200_MIX(H, T, hi, ho)                                                                    \
+    do {                                                                                          \
+        B200_CU(cudaFuncSetAttribute(k_mix_agc512<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem512));                                              \
+        k_mix_agc512<H, T><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,  \
+                                                         vstride, ckpt, sens, do_mix, agc_reference, \
+                                                         sine, out, out_stride, hi, ho);          \
+    } while (0)
+            if (tab)
+                B200_MIX(true, true, hist_in, hist_out);
+            else
+                B200_MIX(true, false, hist_in, hist_out);
         } else {
-            B200_CU(cudaFuncSetAttribute(k_mix_agc512<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem512));
-            k_mix_agc512<false><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,
-                                                              vstride, ckpt, sens, do_mix, agc_reference,
-                                                              sine, out, out_stride, nullptr, nullptr);
+            if (tab)
+                B200_MIX(false, true, nullptr, nullptr);
+            else
+                B200_MIX(false, false, nullptr, nullptr);
         }
+#undef B200_MIX
         B200_LAUNCH_CHECK("k_mix_agc512");
         return B200AIS_OK;
     }

@@ -17,6 +17,8 @@
 // (NB * ns is a multiple of 32, so it owns whole words of the detector bitmask), GROUPS blocks at
 // a time, handing each block's tail to the next through shared memory; it recomputes the block
 // before its range only for that tail.
+#include <cstdlib>
+
 #include "device_math.cuh"
 #include "internal.h"
 
@@ -399,9 +401,20 @@ int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int
     case LG:                                                                                      \
         return launch_one<LG, 0>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh,       \
                                  tail_in, tail_out, m32, msw, corr_out, corr_stride, s);
-    if (L == 120) // the north-star template: tap count folded into the kernel
-        return launch_one<8, 120>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh, tail_in,
-                                  tail_out, m32, msw, corr_out, corr_stride, s);
+    // the three templates of python/ais_demod.py:36-38: tap count folded in
+    static int generic = -1; // B200AIS_CORR_GENERIC=1: run-time tap count everywhere (experiment)
+    if (generic < 0) {
+        const char *e = getenv("B200AIS_CORR_GENERIC");
+        generic = (e && atoi(e)) ? 1 : 0;
+    }
+#define B200_KNOWN(LG, LEN)                                                                       \
+    if (L == LEN && !generic)                                                                            \
+        return launch_one<LG, LEN>(in, in_stride, channels, nblocks, L, nb, tw, hbr, thresh,      \
+                                   tail_in, tail_out, m32, msw, corr_out, corr_stride, s);
+    B200_KNOWN(8, 120)
+    B200_KNOWN(9, 140)
+    B200_KNOWN(12, 1120)
+#undef B200_KNOWN
     switch (lg) {
         B200_CASE(4)
         B200_CASE(5)
