@@ -180,13 +180,13 @@ constexpr int kFHalo = 512;
 constexpr int kFOut = kFSpan - kFHalo;
 constexpr int kFPad = kFSpan + kFSpan / 16; // 1-in-16 padding: a thread's 16 items hit 16 banks
 
-// kHist: stream mode, AGC history in / out.  kTab: the paired sine table is copied to shared
-// memory (16 KB more per CTA: two CTAs per SM instead of three)
-template <bool kHist, bool kTab>
-__global__ void __launch_bounds__(256, kTab ? 2 : 3)
+// kHist: stream mode, AGC history in / out.  (The paired sine table stays in global memory / L1:
+// a copy in shared memory costs the third CTA per SM and measured 6 % slower.)
+template <bool kHist>
+__global__ void __launch_bounds__(256, 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
-             int do_mix, float reference, const float4 *sine,
+             int do_mix, float reference, const float4 *__restrict__ sine,
              float2 *__restrict__ out, size_t out_stride, const float2 *__restrict__ hist_in,
              float2 *__restrict__ hist_out)
 {
@@ -194,12 +194,6 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     float *P = reinterpret_cast<float *>(ys + kFPad); // prefix maxima  [kFPad]
     float *S = P + kFPad;                             // suffix maxima  [kFPad]
     const int tid = threadIdx.x, lane = tid & 31;
-    if (kTab) {
-        float4 *st = reinterpret_cast<float4 *>(S + kFPad);
-        for (int i = tid; i < 1024; i += 256)
-            st[i] = sine[i];
-        sine = st; // published by the barrier below
-    }
     const int c = channel_index();
     if (c >= channels)
         return;
@@ -345,13 +339,7 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
         return rc;
     if ((stages & B200AIS_STAGE_AGC) && agc_nsamples == 512 && seg == 16 &&
         (!(stages & B200AIS_STAGE_FREQSYNC) || (fftlen % 16 == 0 && n1 % fftlen == 0))) {
-        static int tab = -1; // B200AIS_MIX_SMEMTAB=1: sine table in shared memory (experiment)
-        if (tab < 0) {
-            const char *e = getenv("B200AIS_MIX_SMEMTAB");
-            tab = (e && atoi(e)) ? 1 : 0;
-        }
-        const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float)) +
-                               (tab ? 1024 * sizeof(float4) : 0);
+        const size_t smem512 = (size_t)kFPad * (sizeof(float2) + 2 * sizeof(float));
         dim3 grid512 = channel_grid((n1 + kFOut - 1) / kFOut, channels);
         const int do_mix = (stages & B200AIS_STAGE_FREQSYNC) ? 1 : 0;
         const float4 *sine = reinterpret_cast<const float4 *>(tb.sine4);
@@ -360,23 +348,17 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
                 set_error("mix_agc: stream mode needs distinct history buffers in and out");
                 return B200AIS_E_INVALID;
             }
-#define B200_MIX(H, T, hi, ho)                                                                    \
+#define B200_MIX(H, hi, ho)                                                                       \
     do {                                                                                          \
-        B200_CU(cudaFuncSetAttribute(k_mix_agc512<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        B200_CU(cudaFuncSetAttribute(k_mix_agc512<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem512));                                              \
-        k_mix_agc512<H, T><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,  \
+        k_mix_agc512<H><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,  \
                                                          vstride, ckpt, sens, do_mix, agc_reference, \
                                                          sine, out, out_stride, hi, ho);          \
     } while (0)
-            if (tab)
-                B200_MIX(true, true, hist_in, hist_out);
-            else
-                B200_MIX(true, false, hist_in, hist_out);
+            B200_MIX(true, hist_in, hist_out);
         } else {
-            if (tab)
-                B200_MIX(false, true, nullptr, nullptr);
-            else
-                B200_MIX(false, false, nullptr, nullptr);
+            B200_MIX(false, nullptr, nullptr);
         }
 #undef B200_MIX
         B200_LAUNCH_CHECK("k_mix_agc512");

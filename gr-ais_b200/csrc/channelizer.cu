@@ -120,16 +120,37 @@ __device__ __forceinline__ void fir_steps(Acc<kR> &a, float2 (&W)[kR], float2 &n
     }
 }
 
+// one polyphase branch p: a plain FIR over the residue row xp
+template <int kR>
+__device__ __forceinline__ void fir_branch(Acc<kR> &acc, const float2 *__restrict__ xp,
+                                           const float2 *__restrict__ tp, int r0, int b_p, int Qpad)
+{
+    constexpr int kFront = kR + 2;
+    const int u0 = r0 + b_p + kFront; // window at tap 0: items u0 .. u0+R-1
+    float2 W[kR];
+#pragma unroll
+    for (int i = 0; i < kR; i++)
+        W[i] = xp[padr<kR>(u0 + i)];
+    float2 nxt = xp[padr<kR>(u0 - 1)];
+    float2 c = tp[0];
+    for (int q = 0; q < Qpad; q += kR)
+        fir_steps<kR>(acc, W, nxt, c, tp + q, xp, u0 - q - 2);
+}
+
+// G: residue rows resident in shared memory at a time.  G >= D: the whole tile is staged once,
+// with coalesced reads (row = residue).  G < D (large decimations, e.g. 25 at 1.2 Msps): the
+// branches are walked in groups of G, each group's rows staged just before it (row = branch -
+// first branch of the group; a lane reads every D-th item).
 template <int THREADS, int kR>
 __global__ void __launch_bounds__(THREADS)
 k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int ntaps, int ntp,
            const float2 *__restrict__ taps_pm, const int *__restrict__ pass_a,
            const int *__restrict__ pass_b, int nfreqs, const float2 *__restrict__ rot,
-           size_t rot_stride, float2 *__restrict__ out, size_t out_stride, int Mp)
+           size_t rot_stride, float2 *__restrict__ out, size_t out_stride, int Mp, int G)
 {
     extern __shared__ float2 smem[];
     float2 *tps = smem;            // [ntp + 1] this pass's taps, polyphase-major, zero-padded
-    float2 *xs = smem + ntp + 1;   // [D][Mp] input tile by residue mod D
+    float2 *xs = smem + ntp + 1;   // [min(G, D)][Mp] input tile by residue mod D
     constexpr int J = THREADS * kR;
     constexpr int kFront = kR + 2; // zeroed items in front of every residue row: the window of
                                    // the padded taps and its prefetch end up there
@@ -137,20 +158,30 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     const int src = blockIdx.y, pass = blockIdx.z;
     const int jb = blockIdx.x * J;
     const int jt = min(J, n - jb);
+    const int rows = min(G, D);
 
     const float2 *tp_g = taps_pm + (size_t)pass * ntp;
     for (int k = tid; k < ntp; k += THREADS)
         cp_async8(tps + k, tp_g + k);
     if (tid == 0)
         tps[ntp] = make_float2(0.f, 0.f);
-    for (int k = tid; k < D * kFront; k += THREADS)
+    for (int k = tid; k < rows * kFront; k += THREADS)
         xs[(k / kFront) * Mp + padr<kR>(k % kFront)] = make_float2(0.f, 0.f);
 
-    // stage items [jb*D, jb*D + (jt-1)*D + ntaps) of the row: item t -> xs[t % D][t / D + kFront],
-    // asynchronously: every copy is in flight before the first one is waited for
+    // items [jb*D, jb*D + (jt-1)*D + ntaps) of the source row feed this tile:
+    // item t -> residue t % D, position t / D + kFront
     const float2 *row = in + (size_t)src * in_stride + (size_t)jb * D;
     const int T = (jt - 1) * D + ntaps;
-    {
+
+    Acc<kR> acc;
+#pragma unroll
+    for (int r = 0; r < kR; r++)
+        acc.Pr[r] = acc.Pi[r] = acc.Qr[r] = acc.Qi[r] = 0.f;
+    const int r0 = tid * kR;
+    const float2 *tp = tps;
+
+    if (G >= D) {
+        // asynchronously: every copy is in flight before the first one is waited for
         int a = tid % D, m = tid / D;
         const int da = THREADS % D, dm = THREADS / D;
         for (int t = tid; t < T; t += THREADS) {
@@ -162,32 +193,35 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
                 m++;
             }
         }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    Acc<kR> acc;
-#pragma unroll
-    for (int r = 0; r < kR; r++)
-        acc.Pr[r] = acc.Pi[r] = acc.Qr[r] = acc.Qi[r] = 0.f;
-
-    const int r0 = tid * kR;
-    const float2 *tp = tps;
-    for (int p = 0; p < D; p++) {
-        const int lag = ntaps - 1 - p;
-        const int b_p = lag / D, a_p = lag - b_p * D;
-        const int Qpad = (b_p + kR) / kR * kR; // b_p + 1 taps (p, p+D, ... < ntaps), padded
-        const float2 *xp = xs + a_p * Mp;
-        const int u0 = r0 + b_p + kFront; // window at tap 0: items u0 .. u0+R-1
-        float2 W[kR];
-#pragma unroll
-        for (int i = 0; i < kR; i++)
-            W[i] = xp[padr<kR>(u0 + i)];
-        float2 nxt = xp[padr<kR>(u0 - 1)];
-        float2 c = tp[0];
-        for (int q = 0; q < Qpad; q += kR)
-            fir_steps<kR>(acc, W, nxt, c, tp + q, xp, u0 - q - 2);
-        tp += Qpad;
+        cp_async_wait_all();
+        __syncthreads();
+        for (int p = 0; p < D; p++) {
+            const int lag = ntaps - 1 - p;
+            const int b_p = lag / D, a_p = lag - b_p * D;
+            const int Qpad = (b_p + kR) / kR * kR; // b_p + 1 taps (p, p+D, ... < ntaps), padded
+            fir_branch<kR>(acc, xs + a_p * Mp, tp, r0, b_p, Qpad);
+            tp += Qpad;
+        }
+    } else {
+        for (int p0 = 0; p0 < D; p0 += G) {
+            const int g = min(G, D - p0);
+            __syncthreads(); // the previous group's rows have been read
+            for (int r = 0; r < g; r++) {
+                const int a_p = (ntaps - 1 - (p0 + r)) % D;
+                float2 *xr = xs + r * Mp;
+                for (int m = tid; m * D + a_p < T; m += THREADS)
+                    cp_async8(xr + padr<kR>(m + kFront), row + (size_t)m * D + a_p);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            for (int r = 0; r < g; r++) {
+                const int lag = ntaps - 1 - (p0 + r);
+                const int b_p = lag / D;
+                const int Qpad = (b_p + kR) / kR * kR;
+                fir_branch<kR>(acc, xs + r * Mp, tp, r0, b_p, Qpad);
+                tp += Qpad;
+            }
+        }
     }
 
     const int ka = pass_a[pass], kb = pass_b[pass];
@@ -224,14 +258,16 @@ int xlat_padded_taps(int R, int D, int ntaps)
     return n;
 }
 
-size_t xlat_smem_bytes(int threads, int R, int D, int ntaps, int *Mp_out)
+size_t xlat_smem_bytes(int threads, int R, int D, int ntaps, int *Mp_out, int rows = 0)
 {
     const int J = threads * R;
     const int M = J + (ntaps + D - 1) / D + (R + 2) + 1;
     const int Mp = M + M / R + 1;
     if (Mp_out)
         *Mp_out = Mp;
-    return sizeof(float2) * ((size_t)xlat_padded_taps(R, D, ntaps) + 1 + (size_t)D * Mp);
+    if (rows <= 0 || rows > D)
+        rows = D;
+    return sizeof(float2) * ((size_t)xlat_padded_taps(R, D, ntaps) + 1 + (size_t)rows * Mp);
 }
 
 } // namespace
@@ -374,7 +410,7 @@ extern "C" int b200ais_xlat_create(b200ais_xlat **out, int decimation, const flo
         set_error("xlat_create: bad arguments (1 <= nfreqs <= %d)", kMaxFreqs);
         return B200AIS_E_INVALID;
     }
-    if (xlat_smem_bytes(32, 8, decimation, ntaps, nullptr) > 227 * 1024) {
+    if (xlat_smem_bytes(32, 8, decimation, ntaps, nullptr, 1) > 227 * 1024) {
         set_error("xlat_create: decimation %d x %d taps does not fit shared memory", decimation, ntaps);
         return B200AIS_E_INVALID;
     }
@@ -458,7 +494,7 @@ extern "C" int b200ais_xlat_set_center_freq(b200ais_xlat *h, int k, double cente
 
 extern "C" int b200ais_xlat_set_taps(b200ais_xlat *h, const float *taps, int ntaps)
 {
-    if (!h || !taps || ntaps < 1 || xlat_smem_bytes(32, 8, h->D, ntaps, nullptr) > 227 * 1024) {
+    if (!h || !taps || ntaps < 1 || xlat_smem_bytes(32, 8, h->D, ntaps, nullptr, 1) > 227 * 1024) {
         set_error("xlat_set_taps: bad arguments");
         return B200AIS_E_INVALID;
     }
@@ -491,10 +527,10 @@ extern "C" int b200ais_xlat_reset(b200ais_xlat *h)
 
 template <int THREADS, int R>
 static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_stride, float2 *out,
-                       size_t out_stride, cudaStream_t s)
+                       size_t out_stride, int G, cudaStream_t s)
 {
     int Mp = 0;
-    const size_t smem = xlat_smem_bytes(THREADS, R, h->D, h->ntaps, &Mp);
+    const size_t smem = xlat_smem_bytes(THREADS, R, h->D, h->ntaps, &Mp, G);
     B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
     const int J = THREADS * R;
@@ -503,7 +539,7 @@ static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_strid
                                                        h->ntp[R == 16], h->d_taps[R == 16],
                                                        h->d_pass, h->d_pass + kMaxFreqs, h->nfreqs,
                                                        h->rottab.as<float2>(), (size_t)n, out,
-                                                       out_stride, Mp);
+                                                       out_stride, Mp, G);
     B200_LAUNCH_CHECK("k_xlat_fir");
     return B200AIS_OK;
 }
@@ -539,28 +575,43 @@ extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const f
         const char *e = getenv("B200AIS_XLAT_SHAPE");
         g_xlat_shape = e ? atoi(e) : 99;
     }
-    // first shape that leaves room for two CTAs per SM, else the first that fits at all
-    int pick = -1;
+    // first shape whose whole tile (all D residue rows) leaves room for two CTAs per SM; else
+    // the 128 x 16 / 64 x 16 tile with as many rows at a time as fit beside a second CTA
+    const size_t half = 113 * 1024;
+    int pick = -1, G = h->D;
     if (g_xlat_shape < 5 && xlat_smem_bytes(kShapes[g_xlat_shape][0], kShapes[g_xlat_shape][1], h->D,
                                             h->ntaps, nullptr) <= 227 * 1024)
         pick = g_xlat_shape;
     for (int i = 0; i < 5 && pick < 0; i++)
-        if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= 113 * 1024)
+        if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= half)
             pick = i;
+    for (int i = 0; i < 2 && pick < 0; i++) {
+        int Mp = 0;
+        const size_t one = xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, &Mp, 1);
+        const size_t rowb = sizeof(float2) * (size_t)Mp;
+        if (one <= half) {
+            pick = i;
+            G = 1 + (int)((half - one) / rowb);
+        }
+    }
     for (int i = 0; i < 5 && pick < 0; i++)
         if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= 227 * 1024)
             pick = i;
+    if (pick < 0) {
+        set_error("xlat_work: %d taps at decimation %d do not fit shared memory", h->ntaps, h->D);
+        return B200AIS_E_INVALID;
+    }
     switch (pick) {
     case 0:
-        return xlat_launch<128, 16>(h, n, x, in_stride, y, out_stride, s);
+        return xlat_launch<128, 16>(h, n, x, in_stride, y, out_stride, G, s);
     case 1:
-        return xlat_launch<64, 16>(h, n, x, in_stride, y, out_stride, s);
+        return xlat_launch<64, 16>(h, n, x, in_stride, y, out_stride, G, s);
     case 2:
-        return xlat_launch<128, 8>(h, n, x, in_stride, y, out_stride, s);
+        return xlat_launch<128, 8>(h, n, x, in_stride, y, out_stride, G, s);
     case 3:
-        return xlat_launch<64, 8>(h, n, x, in_stride, y, out_stride, s);
+        return xlat_launch<64, 8>(h, n, x, in_stride, y, out_stride, G, s);
     default:
-        return xlat_launch<32, 8>(h, n, x, in_stride, y, out_stride, s);
+        return xlat_launch<32, 8>(h, n, x, in_stride, y, out_stride, G, s);
     }
 }
 
