@@ -575,25 +575,28 @@ extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const f
         const char *e = getenv("B200AIS_XLAT_SHAPE");
         g_xlat_shape = e ? atoi(e) : 99;
     }
-    // first shape whose whole tile (all D residue rows) leaves room for two CTAs per SM; else
-    // the 128 x 16 / 64 x 16 tile with as many rows at a time as fit beside a second CTA
+    // a 16-outputs-per-thread tile with two CTAs per SM: whole (all D residue rows resident) if
+    // it fits, else with as many rows at a time as fit; the small tiles are the last resort
     const size_t half = 113 * 1024;
     int pick = -1, G = h->D;
     if (g_xlat_shape < 5 && xlat_smem_bytes(kShapes[g_xlat_shape][0], kShapes[g_xlat_shape][1], h->D,
                                             h->ntaps, nullptr) <= 227 * 1024)
         pick = g_xlat_shape;
-    for (int i = 0; i < 5 && pick < 0; i++)
+    for (int i = 0; i < 2 && pick < 0; i++)
         if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= half)
             pick = i;
     for (int i = 0; i < 2 && pick < 0; i++) {
         int Mp = 0;
         const size_t one = xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, &Mp, 1);
         const size_t rowb = sizeof(float2) * (size_t)Mp;
-        if (one <= half) {
+        if (one + rowb <= half) { // at least two rows at a time
             pick = i;
             G = 1 + (int)((half - one) / rowb);
         }
     }
+    for (int i = 2; i < 5 && pick < 0; i++)
+        if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= half)
+            pick = i;
     for (int i = 0; i < 5 && pick < 0; i++)
         if (xlat_smem_bytes(kShapes[i][0], kShapes[i][1], h->D, h->ntaps, nullptr) <= 227 * 1024)
             pick = i;

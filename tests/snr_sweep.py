@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""BASELINE.json configs[4]: SNR sweep, packet-detect rate of the GPU path vs the CPU oracle.
+"""TEST INFRASTRUCTURE (it runs the CPU oracle beside the GPU path, so it lives under tests/).
+BASELINE.json configs[4]: SNR sweep, packet-detect rate of the GPU path vs the CPU oracle.
 
 Per SNR point: `--channels` channels, independent noise per channel, random payloads, carrier
 offset U(-500, 500) Hz, random phase, fractional delay U(0, 1) sample.
@@ -9,7 +10,7 @@ Reports, for the GPU path and (on a subset of channels) the oracle:
                 (GPU path: b200ais_hdlc_work; oracle: its C restatement)
 and checks the two paths agree bit for bit on the oracle subset.
 
-    python tools/snr_sweep.py --channels 16384 --snrs 0 2 4 6 8 10 12 14 16 18 20
+    python tests/snr_sweep.py --channels 16384 --snrs 0 2 4 6 8 10 12 14 16 18 20
 """
 import argparse
 import json

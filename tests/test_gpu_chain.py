@@ -118,7 +118,7 @@ def test_snr_sweep_gpu_equals_oracle():
     packet-detect rate rises with SNR"""
     import subprocess, sys, os, json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "snr_sweep.py"), "--channels", "48",
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "snr_sweep.py"), "--channels", "48",
                         "--oracle-channels", "48", "--seconds", "0.5", "--snrs", "0", "10", "20"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
