@@ -545,7 +545,7 @@ static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_strid
 }
 
 // tile shapes, best first: {threads, outputs per thread}
-static const int kShapes[][2] = {{128, 16}, {64, 16}, {128, 8}, {64, 8}, {32, 8}};
+static const int kShapes[][2] = {{64, 16}, {128, 16}, {128, 8}, {64, 8}, {32, 8}};
 static int g_xlat_shape = -1; // B200AIS_XLAT_SHAPE=<index> pins one (profiling)
 
 extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const float *in,
@@ -606,9 +606,9 @@ extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const f
     }
     switch (pick) {
     case 0:
-        return xlat_launch<128, 16>(h, n, x, in_stride, y, out_stride, G, s);
-    case 1:
         return xlat_launch<64, 16>(h, n, x, in_stride, y, out_stride, G, s);
+    case 1:
+        return xlat_launch<128, 16>(h, n, x, in_stride, y, out_stride, G, s);
     case 2:
         return xlat_launch<128, 8>(h, n, x, in_stride, y, out_stride, G, s);
     case 3:
