@@ -4,6 +4,12 @@
 // state from call to call (a capture is fed in pieces of any size).  The channeliser writes
 // straight into the demod chain's assembly rows; nothing between the wideband input and the
 // NMEA sentences leaves the device.
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <poll.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -313,10 +319,70 @@ k_fanout(const float2 *__restrict__ src, int n, float2 *__restrict__ dst, size_t
         dst[(size_t)s * dst_stride + i] = v;
 }
 
-size_t read_items(FILE *f, float2 *dst, size_t want)
-{
-    return fread(dst, sizeof(float2), want, f);
-}
+// a source of raw interleaved float32 IQ: fills dst with up to `want` items, returns how many it
+// got (0 = end of the capture)
+struct ItemReader {
+    virtual ~ItemReader() {}
+    virtual size_t read(float2 *dst, size_t want) = 0;
+};
+
+struct FileReader : ItemReader {
+    FILE *f = nullptr;
+    ~FileReader() override
+    {
+        if (f)
+            fclose(f);
+    }
+    size_t read(float2 *dst, size_t want) override { return fread(dst, sizeof(float2), want, f); }
+};
+
+// blocks.udp_source(gr.sizeof_gr_complex, ip, port, payload_size, eof) [G]: datagram payloads
+// are a byte stream of items; a zero-length datagram is the end-of-stream mark (eof = True);
+// idle_ms without traffic also ends the capture.  Bytes short of a whole item wait for the
+// next datagram.
+struct UdpReader : ItemReader {
+    int fd = -1;
+    int idle_ms = 1000;
+    bool eof = false;
+    std::vector<unsigned char> pend; // bytes beyond the items already handed out
+    ~UdpReader() override
+    {
+        if (fd >= 0)
+            close(fd);
+    }
+    size_t read(float2 *dst, size_t want) override
+    {
+        unsigned char *out = reinterpret_cast<unsigned char *>(dst);
+        const size_t want_b = want * sizeof(float2);
+        size_t have = std::min(pend.size(), want_b);
+        memcpy(out, pend.data(), have);
+        pend.erase(pend.begin(), pend.begin() + (long)have);
+        unsigned char dgram[65536];
+        while (have < want_b && !eof) {
+            pollfd pf = {fd, POLLIN, 0};
+            const int pr = poll(&pf, 1, idle_ms);
+            if (pr <= 0)
+                break; // idle (or error): the capture is over
+            const ssize_t n = recv(fd, dgram, sizeof(dgram), 0);
+            if (n < 0)
+                break;
+            if (n == 0) {
+                eof = true;
+                break;
+            }
+            const size_t take = std::min((size_t)n, want_b - have);
+            memcpy(out + have, dgram, take);
+            have += take;
+            pend.insert(pend.end(), dgram + take, dgram + n);
+        }
+        const size_t items = have / sizeof(float2), rem = have % sizeof(float2);
+        if (rem) // keep the split item for the next call
+            pend.insert(pend.begin(), out + items * sizeof(float2), out + have);
+        return items;
+    }
+};
+
+size_t reader_read(ItemReader *r, float2 *dst, size_t want) { return r->read(dst, want); }
 
 } // namespace
 
@@ -325,18 +391,11 @@ size_t read_items(FILE *f, float2 *dst, size_t want)
 // float32 IQ, read in chunks through two pinned buffers -- the read of chunk k+1 runs on a
 // host thread while chunk k is copied and processed -- copied to the device once and
 // replicated there.
-extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk_items, int max_msgs,
-                                      b200ais_rx_sink sink, void *user, uint64_t *items_read)
+// Chunks from `rd` through two pinned buffers: chunk k+1 is read on a host thread while chunk k
+// is copied (once) to the device, replicated to every source row and processed.
+static int rx_pump(b200ais_rx *h, ItemReader *rd, int chunk_items, int max_msgs, b200ais_rx_sink sink,
+                   void *user, uint64_t *items_read, uint64_t max_items)
 {
-    if (!h || !path || chunk_items < 1 || chunk_items > h->cfg.max_input_items || max_msgs < 1) {
-        set_error("rx_replay_file: bad arguments (chunk_items <= max_input_items)");
-        return B200AIS_E_INVALID;
-    }
-    FILE *f = fopen(path, "rb");
-    if (!f) {
-        set_error("rx_replay_file: cannot open %s", path);
-        return B200AIS_E_INVALID;
-    }
     float2 *pin[2] = {nullptr, nullptr}, *d_stage = nullptr;
     std::vector<b200ais_frame> msgs((size_t)max_msgs);
     std::vector<char> sent((size_t)max_msgs * h->slot);
@@ -360,15 +419,18 @@ extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk
         if (e == cudaSuccess) h->out_cap = max_msgs;
     }
     if (e != cudaSuccess)
-        rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+        rc = cuda_fail(e, "rx_pump", __FILE__, __LINE__);
     cudaStream_t s = h->stream;
     const int S = h->cfg.sources;
-    size_t have = rc ? 0 : read_items(f, pin[0], (size_t)chunk_items);
+    auto want = [&](uint64_t done) {
+        return (size_t)std::min<uint64_t>((uint64_t)chunk_items, max_items - done);
+    };
+    size_t have = rc ? 0 : rd->read(pin[0], want(0));
+    uint64_t asked = have;
     for (int k = 0; !rc && have > 0; k++) {
         float2 *cur = pin[k & 1];
-        // next chunk from the file while this one is on the device
-        std::future<size_t> next = std::async(std::launch::async, read_items, f, pin[(k + 1) & 1],
-                                              (size_t)chunk_items);
+        std::future<size_t> next = std::async(std::launch::async, reader_read, rd, pin[(k + 1) & 1],
+                                              want(asked));
         const int n = (int)have;
         e = cudaMemcpyAsync(d_stage, cur, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) {
@@ -378,7 +440,7 @@ extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk
             e = cudaGetLastError();
         }
         if (e != cudaSuccess) {
-            rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+            rc = cuda_fail(e, "rx_pump", __FILE__, __LINE__);
         } else {
             rc = rx_run(h, n, h->d_msgs, h->d_sent, h->slot, h->d_lens, max_msgs, h->d_count, s);
         }
@@ -387,7 +449,7 @@ extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk
             e = cudaMemcpyAsync(&cnt, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, s);
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
             if (e != cudaSuccess)
-                rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+                rc = cuda_fail(e, "rx_pump", __FILE__, __LINE__);
         }
         if (!rc)
             rc = b200ais_rx_status(h);
@@ -398,18 +460,63 @@ extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk
             if (e == cudaSuccess)
                 e = cudaMemcpy(sent.data(), h->d_sent, (size_t)h->slot * cnt, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess)
-                rc = cuda_fail(e, "rx_replay_file", __FILE__, __LINE__);
+                rc = cuda_fail(e, "rx_pump", __FILE__, __LINE__);
             else if (sink)
                 sink(user, msgs.data(), sent.data(), h->slot, lens.data(), cnt);
         }
         total += (uint64_t)n;
         have = next.get(); // always joined, also on errors
+        asked += have;
     }
     if (items_read)
         *items_read = total;
-    fclose(f);
     if (pin[0]) cudaFreeHost(pin[0]);
     if (pin[1]) cudaFreeHost(pin[1]);
     if (d_stage) cudaFree(d_stage);
     return rc;
+}
+
+extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk_items, int max_msgs,
+                                      b200ais_rx_sink sink, void *user, uint64_t *items_read)
+{
+    if (!h || !path || chunk_items < 1 || chunk_items > h->cfg.max_input_items || max_msgs < 1) {
+        set_error("rx_replay_file: bad arguments (chunk_items <= max_input_items)");
+        return B200AIS_E_INVALID;
+    }
+    FileReader rd;
+    rd.f = fopen(path, "rb");
+    if (!rd.f) {
+        set_error("rx_replay_file: cannot open %s", path);
+        return B200AIS_E_INVALID;
+    }
+    return rx_pump(h, &rd, chunk_items, max_msgs, sink, user, items_read, ~(uint64_t)0);
+}
+
+// blocks.udp_source(gr.sizeof_gr_complex, ip, port) (python/radio.py:209-213)
+extern "C" int b200ais_rx_serve_udp(b200ais_rx *h, const char *bind_ip, int port, int chunk_items,
+                                    int max_msgs, uint64_t max_items, int idle_ms,
+                                    b200ais_rx_sink sink, void *user, uint64_t *items_read)
+{
+    if (!h || !bind_ip || port < 1 || port > 65535 || chunk_items < 1 ||
+        chunk_items > h->cfg.max_input_items || max_msgs < 1 || idle_ms < 1) {
+        set_error("rx_serve_udp: bad arguments (chunk_items <= max_input_items)");
+        return B200AIS_E_INVALID;
+    }
+    UdpReader rd;
+    rd.idle_ms = idle_ms;
+    rd.fd = socket(AF_INET, SOCK_DGRAM, 0);
+    sockaddr_in addr;
+    memset(&addr, 0, sizeof(addr));
+    addr.sin_family = AF_INET;
+    addr.sin_port = htons((uint16_t)port);
+    const int buf = 8 << 20;
+    if (rd.fd >= 0)
+        setsockopt(rd.fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof(buf));
+    if (rd.fd < 0 || inet_pton(AF_INET, bind_ip, &addr.sin_addr) != 1 ||
+        bind(rd.fd, reinterpret_cast<sockaddr *>(&addr), sizeof(addr)) != 0) {
+        set_error("rx_serve_udp: cannot bind %s:%d", bind_ip, port);
+        return B200AIS_E_INVALID;
+    }
+    return rx_pump(h, &rd, chunk_items, max_msgs, sink, user, items_read,
+                   max_items ? max_items : ~(uint64_t)0);
 }

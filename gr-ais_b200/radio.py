@@ -107,6 +107,17 @@ class ais_rx:
         """blocks.file_source(gr.sizeof_gr_complex, path) into every source (python/radio.py:
         204-207): raw interleaved float32 IQ, double-buffered pinned reads.  Returns
         (msgs, sentences, items_read) over the whole file, sorted by (channel, end_bit)."""
+        return self._pump(lambda cb, items, chunk, mm: B.lib().b200ais_rx_replay_file(
+            self._h, os.fsencode(path), chunk, mm, cb, None, C.byref(items)), chunk_items, max_msgs)
+
+    def serve_udp(self, ip, port, chunk_items=None, max_msgs=None, max_items=0, idle_ms=1000):
+        """blocks.udp_source(gr.sizeof_gr_complex, ip, port) into every source (python/radio.py:
+        209-213).  Blocks until a zero-length datagram, max_items items or idle_ms of silence."""
+        return self._pump(lambda cb, items, chunk, mm: B.lib().b200ais_rx_serve_udp(
+            self._h, ip.encode(), int(port), chunk, mm, int(max_items), int(idle_ms), cb, None,
+            C.byref(items)), chunk_items, max_msgs)
+
+    def _pump(self, call, chunk_items, max_msgs):
         chunk_items = int(chunk_items or self.cfg.max_input_items)
         max_msgs = int(max_msgs or self.channels * self.cfg.max_frames)
         got_m, got_s = [], []
@@ -121,8 +132,7 @@ class ais_rx:
 
         cb = B.RX_SINK(sink)
         items = C.c_uint64(0)
-        B.check(B.lib().b200ais_rx_replay_file(self._h, os.fsencode(path), chunk_items, max_msgs, cb,
-                                               None, C.byref(items)))
+        B.check(call(cb, items, chunk_items, max_msgs))
         msgs = np.concatenate(got_m) if got_m else np.zeros(0, dtype=B.FRAME_DTYPE)
         order = np.lexsort((msgs["end_bit"], msgs["channel"]))
         return msgs[order], [got_s[i] for i in order], items.value

@@ -439,6 +439,13 @@ typedef void (*b200ais_rx_sink)(void *user, const b200ais_frame *msgs, const cha
 B200AIS_API int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk_items,
                                        int max_msgs, b200ais_rx_sink sink, void *user,
                                        uint64_t *items_read);
+/* The same pump fed by blocks.udp_source(gr.sizeof_gr_complex, ip, port) (python/radio.py:
+ * 209-213): datagram payloads are a byte stream of raw float32 IQ items.  Returns after a
+ * zero-length datagram (GNU Radio's end-of-stream mark), after max_items items (0 = no limit), or
+ * when no datagram arrives for idle_ms. */
+B200AIS_API int b200ais_rx_serve_udp(b200ais_rx *h, const char *bind_ip, int port, int chunk_items,
+                                     int max_msgs, uint64_t max_items, int idle_ms,
+                                     b200ais_rx_sink sink, void *user, uint64_t *items_read);
 
 #ifdef __cplusplus
 }

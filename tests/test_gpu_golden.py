@@ -62,3 +62,49 @@ def test_ais_rx_replays_a_recorded_file(tmp_path):
         assert mine == want
     with pytest.raises(B.B200AisError):
         rx.replay_file(str(tmp_path / "missing.cfile"))
+
+
+def test_ais_rx_serves_a_udp_stream():
+    """blocks.udp_source semantics (python/radio.py:209-213): datagram payloads are a byte stream
+    of raw float32 IQ items (split anywhere, also inside an item); a zero-length datagram ends
+    the stream.  Sentences equal the golden ones."""
+    import socket
+    import threading
+    import time
+    z = load("rx_kat.npz")
+    x = z["iq"]
+    rx = ais_rx([-25e3, 25e3], float(z["rate"]), ["A", "B"], sources=2, max_input_items=20000)
+    rx.work(np.zeros((2, 20000), np.complex64))     # load the kernels before datagrams queue up
+    rx.reset()
+    probe = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    try:
+        probe.bind(("127.0.0.1", 0))
+    except OSError:
+        pytest.skip("no UDP loopback in this sandbox")
+    port = probe.getsockname()[1]
+    probe.close()
+    raw = x.tobytes()
+
+    def send():
+        time.sleep(0.3)
+        tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        pos, k = 0, 0
+        while pos < len(raw):
+            n = 1472 if k % 3 else 1469          # payloads that split items
+            tx.sendto(raw[pos:pos + n], ("127.0.0.1", port))
+            pos += n
+            k += 1
+            if k % 4 == 0:
+                time.sleep(0.001)
+        for _ in range(3):
+            tx.sendto(b"", ("127.0.0.1", port))
+        tx.close()
+
+    th = threading.Thread(target=send)
+    th.start()
+    msgs, sents, items = rx.serve_udp("127.0.0.1", port, chunk_items=16384, idle_ms=3000)
+    th.join()
+    assert items == len(x)
+    want = list(z["sentences"])
+    for s in range(2):
+        assert [t for m, t in zip(msgs, sents) if m["channel"] // 2 == s] == want
