@@ -405,12 +405,11 @@ k_sqfft_freqest_1024w(const float2 *__restrict__ x, size_t x_stride, int vstride
         stage_b<9>(v, s_twB + lane);
         stage_b<10>(v, s_twB + lane);
         __syncwarp();
-        // spectrum (natural order, bin k = 32 q + lane) and float magnitudes back to shared memory
+        // float magnitudes (natural order, bin k = 32 q + lane) to shared memory; the spectrum
+        // itself stays in registers
 #pragma unroll
-        for (int q = 0; q < 32; q++) {
-            cx[32 * q + lane + q] = v[q]; // bin k at k + (k >> 5)
+        for (int q = 0; q < 32; q++)
             mag[32 * q + lane] = sqrtf(__fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y));
-        }
         __syncwarp();
         // ---- freqest: argmax_j |S[j]| + |S[j+offset]|, S[j] = X[(j + 512) mod 1024] ----
         // float estimates first (within 3e-7 of the canonical sums), then the canonical
@@ -423,18 +422,49 @@ k_sqfft_freqest_1024w(const float2 *__restrict__ x, size_t x_stride, int vstride
             m_est = fmaxf(m_est, __shfl_xor_sync(0xffffffffu, m_est, o));
         const bool exact_all = !(m_est > 1e-12f && m_est < 1e30f);
         const float cut = m_est * (1.0f - 2e-6f);
+        if (exact_all) { // an all-zero vector (a silent channel) has no maximum: skip the scan
+            unsigned any = 0;
+#pragma unroll
+            for (int q = 0; q < 32; q++)
+                any |= (__float_as_uint(v[q].x) | __float_as_uint(v[q].y)) << 1;
+            if (!__any_sync(0xffffffffu, any != 0)) {
+                if (lane == 0)
+                    raw[(size_t)c * vstride + b] = -1;
+                continue;
+            }
+        }
         Best best;
         best.e = 0.0f;
         best.j = 0x7fffffff;
-        for (int j = lane; j < N - offset; j += 32) {
+        // bin k lives in slot k >> 5 of lane k & 31: a candidate pair is fetched with two
+        // warp-wide picks (a select chain over the slots + a shuffle); candidates are few
+        for (int j0 = 0; j0 < N - offset; j0 += 32) {
+            const int j = j0 + lane;
             const int k1 = (j + N / 2) & (N - 1), k2 = (j + offset + N / 2) & (N - 1);
-            if (exact_all || mag[k1] + mag[k2] >= cut) {
-                const float2 p = cx[k1 + (k1 >> 5)];
-                const float2 q2 = cx[k2 + (k2 >> 5)];
-                const float e = hypot_canon(p.x, p.y) + hypot_canon(q2.x, q2.y);
-                if (e > best.e) {
-                    best.e = e;
-                    best.j = j;
+            const bool cand = j < N - offset && (exact_all || mag[k1] + mag[k2] >= cut);
+            unsigned todo = __ballot_sync(0xffffffffu, cand);
+            while (todo) {
+                const int ow = __ffs(todo) - 1; // owner lane of this candidate
+                todo &= todo - 1;
+                const int a1 = __shfl_sync(0xffffffffu, k1, ow), a2 = __shfl_sync(0xffffffffu, k2, ow);
+                float2 p = v[0], q2 = v[0];
+#pragma unroll
+                for (int q = 1; q < 32; q++) {
+                    if ((a1 >> 5) == q)
+                        p = v[q];
+                    if ((a2 >> 5) == q)
+                        q2 = v[q];
+                }
+                p.x = __shfl_sync(0xffffffffu, p.x, a1 & 31);
+                p.y = __shfl_sync(0xffffffffu, p.y, a1 & 31);
+                q2.x = __shfl_sync(0xffffffffu, q2.x, a2 & 31);
+                q2.y = __shfl_sync(0xffffffffu, q2.y, a2 & 31);
+                if (lane == ow) {
+                    const float e = hypot_canon(p.x, p.y) + hypot_canon(q2.x, q2.y);
+                    if (e > best.e) { // ascending j within a lane: strict '>' keeps the first
+                        best.e = e;
+                        best.j = j;
+                    }
                 }
             }
         }
