@@ -4,8 +4,6 @@
 //   python/gmsk_sync.py:22-24,30-31   multiply_cc(x,x) -> stream_to_vector -> fft_vcc(shift)
 //   lib/freqest_impl.cc:57-88         freqest_impl::work
 //   python/gmsk_sync.py:26-27         repeat -> frequency_modulator_fc (phase recurrence)
-#include <cstdlib>
-
 #include "device_math.cuh"
 #include "internal.h"
 
@@ -287,193 +285,6 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
         raw[(size_t)c * vstride + b] = (best.j == 0x7fffffff) ? -1 : best.j + offset / 2;
 }
 
-// ---- 1024-point warp path: one warp per vector, 32 values per thread, two register passes ----
-//
-// The same decimation-in-time graph again, cut in two: stages 1-5 touch index bits 0-4, stages
-// 6-10 bits 5-9.  Lane t first holds elements 32 t + q (q = 0..31: every combination of the low
-// five bits), runs five stages in registers, the warp transposes through shared memory, lane t
-// then holds elements 32 q + t and runs the other five.  One crossing instead of two, no block
-// barrier (a warp owns its vector from the load to the argmax), and the twiddles of the first
-// pass are the same sixteen for every lane (broadcast reads), those of the second are read from
-// a per-stage table laid out [entry][lane] (conflict-free).
-constexpr int kWarpsPerCta = 2;
-constexpr int kVecPerWarp = 4; // vectors a warp walks (amortises the twiddle staging)
-
-__device__ __forceinline__ Best warp_argmax(Best v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        Best w;
-        w.e = __shfl_xor_sync(0xffffffffu, v.e, o);
-        w.j = __shfl_xor_sync(0xffffffffu, v.j, o);
-        v = better(v, w);
-    }
-    return v;
-}
-
-// stage ST (1..5) of the graph on the 32 register values of pass A: pairs q, q + 2^(ST-1),
-// twiddle W[(q mod 2^(ST-1)) * 2^(10-ST)] = twA[(q mod 2^(ST-1)) << (5-ST)] (twA[k] = W[32 k])
-template <int ST>
-__device__ __forceinline__ void stage_a(float2 (&v)[32], const float2 *__restrict__ twA)
-{
-    constexpr int H = 1 << (ST - 1);
-#pragma unroll
-    for (int q = 0; q < 32; q++) {
-        if (q & H)
-            continue;
-        const int k = (q & (H - 1)) << (5 - ST); // W[32 k]
-        if (k == 0)
-            bf_one(v[q], v[q + H]);
-        else if (k == 8)
-            bf_mi(v[q], v[q + H]);
-        else
-            bf(v[q], v[q + H], twA[k]);
-    }
-}
-
-// stage ST (6..10) on pass B's values (element 32 q + t in slot q): pairs q, q + 2^(ST-6),
-// twiddle W[(32 (q mod 2^(ST-6)) + t) << (10-ST)] = twB[(2^(ST-6) - 1 + q mod 2^(ST-6)) * 32 + t]
-template <int ST>
-__device__ __forceinline__ void stage_b(float2 (&v)[32], const float2 *__restrict__ twB_lane)
-{
-    constexpr int H = 1 << (ST - 6);
-#pragma unroll
-    for (int qq = 0; qq < H; qq++) {
-        const float2 w = twB_lane[(H - 1 + qq) * 32];
-#pragma unroll
-        for (int q = qq; q < 32; q += 2 * H)
-            bf(v[q], v[q + H], w);
-    }
-}
-
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
-k_sqfft_freqest_1024w(const float2 *__restrict__ x, size_t x_stride, int vstride, int nvec,
-                      const float2 *__restrict__ tw, int offset, int *__restrict__ raw, int channels)
-{
-    constexpr int N = 1024;
-    if (channel_index() >= channels)
-        return;
-    __shared__ float2 s_twA[16];
-    __shared__ float2 s_twB[31 * 32];
-    __shared__ float2 s_cx[kWarpsPerCta][32 * 33];
-    __shared__ float s_mag[kWarpsPerCta][N];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = channel_index();
-    for (int i = threadIdx.x; i < 16; i += blockDim.x)
-        s_twA[i] = tw[32 * i];
-    for (int i = threadIdx.x; i < 31 * 32; i += blockDim.x) {
-        const int k1 = (i >> 5) + 1, t = i & 31; // k1 = 2^(ST-6) + qq
-        const int sh = 31 - __clz(k1), qq = k1 - (1 << sh); // sh = ST - 6
-        s_twB[i] = tw[(32 * qq + t) << (4 - sh)];
-    }
-    __syncthreads();
-    float2 *cx = s_cx[warp];
-    float *mag = s_mag[warp];
-    const int r5l = (int)(__brev((unsigned)lane) >> 27); // bitrev5(lane)
-
-#pragma unroll 1
-    for (int it = 0; it < kVecPerWarp; it++) {
-        const int b = (blockIdx.x * kWarpsPerCta + warp) * kVecPerWarp + it;
-        if (b >= nvec)
-            break; // warp-uniform
-        const float2 *src = x + (size_t)c * x_stride + (size_t)b * N;
-        float2 v[32];
-        // ---- pass A: stages 1-5 on elements e = 32 lane + q, loaded from x[bitrev10(e)] ----
-#pragma unroll
-        for (int q = 0; q < 32; q++) {
-            const int r5q = ((q & 1) << 4) | ((q & 2) << 2) | (q & 4) | ((q & 8) >> 2) | ((q & 16) >> 4);
-            const float2 in = src[r5q * 32 + r5l];
-            v[q] = cmul_fma(in, in); // blocks.multiply_cc(x, x)
-        }
-        stage_a<1>(v, s_twA);
-        stage_a<2>(v, s_twA);
-        stage_a<3>(v, s_twA);
-        stage_a<4>(v, s_twA);
-        stage_a<5>(v, s_twA);
-        __syncwarp(); // the previous vector's readers are done with cx / mag
-#pragma unroll
-        for (int q = 0; q < 32; q++)
-            cx[33 * lane + q] = v[q]; // element 32 lane + q
-        __syncwarp();
-        // ---- pass B: stages 6-10 on elements e = 32 q + lane ----
-#pragma unroll
-        for (int q = 0; q < 32; q++)
-            v[q] = cx[33 * q + lane];
-        stage_b<6>(v, s_twB + lane);
-        stage_b<7>(v, s_twB + lane);
-        stage_b<8>(v, s_twB + lane);
-        stage_b<9>(v, s_twB + lane);
-        stage_b<10>(v, s_twB + lane);
-        __syncwarp();
-        // float magnitudes (natural order, bin k = 32 q + lane) to shared memory; the spectrum
-        // itself stays in registers
-#pragma unroll
-        for (int q = 0; q < 32; q++)
-            mag[32 * q + lane] = sqrtf(__fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y));
-        __syncwarp();
-        // ---- freqest: argmax_j |S[j]| + |S[j+offset]|, S[j] = X[(j + 512) mod 1024] ----
-        // float estimates first (within 3e-7 of the canonical sums), then the canonical
-        // evaluation of the bins within 2e-6 of the estimated maximum (see the 64-thread kernel)
-        float m_est = 0.0f;
-        for (int j = lane; j < N - offset; j += 32)
-            m_est = fmaxf(m_est, mag[(j + N / 2) & (N - 1)] + mag[(j + offset + N / 2) & (N - 1)]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            m_est = fmaxf(m_est, __shfl_xor_sync(0xffffffffu, m_est, o));
-        const bool exact_all = !(m_est > 1e-12f && m_est < 1e30f);
-        const float cut = m_est * (1.0f - 2e-6f);
-        if (exact_all) { // an all-zero vector (a silent channel) has no maximum: skip the scan
-            unsigned any = 0;
-#pragma unroll
-            for (int q = 0; q < 32; q++)
-                any |= (__float_as_uint(v[q].x) | __float_as_uint(v[q].y)) << 1;
-            if (!__any_sync(0xffffffffu, any != 0)) {
-                if (lane == 0)
-                    raw[(size_t)c * vstride + b] = -1;
-                continue;
-            }
-        }
-        Best best;
-        best.e = 0.0f;
-        best.j = 0x7fffffff;
-        // bin k lives in slot k >> 5 of lane k & 31: a candidate pair is fetched with two
-        // warp-wide picks (a select chain over the slots + a shuffle); candidates are few
-        for (int j0 = 0; j0 < N - offset; j0 += 32) {
-            const int j = j0 + lane;
-            const int k1 = (j + N / 2) & (N - 1), k2 = (j + offset + N / 2) & (N - 1);
-            const bool cand = j < N - offset && (exact_all || mag[k1] + mag[k2] >= cut);
-            unsigned todo = __ballot_sync(0xffffffffu, cand);
-            while (todo) {
-                const int ow = __ffs(todo) - 1; // owner lane of this candidate
-                todo &= todo - 1;
-                const int a1 = __shfl_sync(0xffffffffu, k1, ow), a2 = __shfl_sync(0xffffffffu, k2, ow);
-                float2 p = v[0], q2 = v[0];
-#pragma unroll
-                for (int q = 1; q < 32; q++) {
-                    if ((a1 >> 5) == q)
-                        p = v[q];
-                    if ((a2 >> 5) == q)
-                        q2 = v[q];
-                }
-                p.x = __shfl_sync(0xffffffffu, p.x, a1 & 31);
-                p.y = __shfl_sync(0xffffffffu, p.y, a1 & 31);
-                q2.x = __shfl_sync(0xffffffffu, q2.x, a2 & 31);
-                q2.y = __shfl_sync(0xffffffffu, q2.y, a2 & 31);
-                if (lane == ow) {
-                    const float e = hypot_canon(p.x, p.y) + hypot_canon(q2.x, q2.y);
-                    if (e > best.e) { // ascending j within a lane: strict '>' keeps the first
-                        best.e = e;
-                        best.j = j;
-                    }
-                }
-            }
-        }
-        best = warp_argmax(best);
-        if (lane == 0)
-            raw[(size_t)c * vstride + b] = (best.j == 0x7fffffff) ? -1 : best.j + offset / 2;
-    }
-}
-
 // Stand-alone freqest on caller-supplied spectra (any fftlen).
 __global__ void __launch_bounds__(kFftThreads)
 k_freqest_spec(const float2 *__restrict__ spec, int nvec, int n, int offset, int *__restrict__ raw,
@@ -595,17 +406,7 @@ int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nve
         return rc;
     size_t smem = (size_t)fftlen * (sizeof(float2) + sizeof(float));
     dim3 grid = channel_grid(nvec, channels);
-    static int variant = -1; // B200AIS_SQFFT=64: the 64-thread kernel (default: warp per vector)
-    if (variant < 0) {
-        const char *e = getenv("B200AIS_SQFFT");
-        variant = (e && atoi(e) == 64) ? 64 : 32;
-    }
-    if (fftlen == 1024 && variant == 32) {
-        const int per_cta = kWarpsPerCta * kVecPerWarp;
-        dim3 gw = channel_grid((nvec + per_cta - 1) / per_cta, channels);
-        k_sqfft_freqest_1024w<<<gw, 32 * kWarpsPerCta, 0, s>>>(x, x_stride, vstride, nvec, tw, offset,
-                                                               raw, channels);
-    } else if (fftlen == 1024) {
+    if (fftlen == 1024) {
         k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw, channels);
     } else {
         if (smem > 40 * 1024) // static shared memory counts towards the 48 KB default limit
