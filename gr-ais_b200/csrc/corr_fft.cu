@@ -204,7 +204,7 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
 // LT: the tap count when it is known at compile time (0 = run-time L): with F = 256 and the
 // north-star's 120 taps every `element < ns` test on a slot other than q = 8 folds away.
 template <int LOGF, int LT>
-__global__ void __launch_bounds__(Plan<LOGF>::THREADS, (LOGF <= 8 ? 5 : (LOGF <= 10 ? 3 : 1)))
+__global__ void __launch_bounds__(Plan<LOGF>::THREADS, (LOGF <= 8 ? 4 : (LOGF <= 10 ? 3 : 1)))
 k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_rt, int nb_per_cta,
            const float2 *__restrict__ tw, const float2 *__restrict__ hbr, float thresh,
            const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
@@ -252,15 +252,27 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
     const int first = b0 > 0 ? b0 - 1 : 0;                   // lead block: only its tail is used
     const int last = min(b0 + nb_per_cta, nblocks);          // exclusive
     const int rounds = (last - first + GROUPS - 1) / GROUPS;
+    // the input block of round r+1 is requested before round r's transform, so that HBM latency
+    // runs under it (the slots at or beyond ns are zero padding and never loaded)
+    auto fetch = [&](float2 (&d)[16], int bb) {
+        const bool ok = bb < last;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int e = t + NT * q;
+            d[q] = (ok && e < ns) ? xc[(size_t)bb * ns + e] : make_float2(0.0f, 0.0f);
+        }
+    };
+    float2 vnext[16];
+    fetch(vnext, first + g);
     for (int r = 0; r < rounds; r++) {
         const int b = first + r * GROUPS + g;
         const bool valid = b < last;
         float2 v[16];
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int e = t + NT * q;
-            v[q] = (valid && e < ns) ? xc[(size_t)b * ns + e] : make_float2(0.0f, 0.0f);
-        }
+        for (int q = 0; q < 16; q++)
+            v[q] = vnext[q];
+        if (r + 1 < rounds)
+            fetch(vnext, b + GROUPS);
         block_filter<LOGF>(v, t, s_tw, s_twp, reinterpret_cast<const float4 *>(s_h), xb);
         // stash this block's tail (outputs ns .. F-1) for the next block
         float2 *my_tail = s_tail + ((r % 3) * GROUPS + g) * tl;
