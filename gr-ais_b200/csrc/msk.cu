@@ -411,6 +411,22 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         unconsumed[c] = navail - (L.iidx - mis);
 }
 
+// binary_slicer_fb(quadrature_demod_cf): (pi/2) * fast_atan2f(y, x) >= 0.  Only the sign reaches
+// the bit stream, and for finite arguments fast_atan2f's sign is y's -- its result is -base_angle,
+// base_angle - pi or -pi/2 +- base_angle (base_angle in [0, pi/4]) for y < 0 and non-negative for
+// y >= 0 (also -0 and (0, 0)) -- with one exception: y < 0 < x and |y| / |x| rounding to zero
+// gives -0, which passes `>= 0`.  That corner (|y| < |x| * 2^-100 is a superset of it) and
+// non-finite arguments take the table path.
+__device__ __forceinline__ unsigned slicer_bit(float y, float x, const float *__restrict__ tab)
+{
+    const float ya = fabsf(y), xa = fabsf(x);
+    const bool plain = xa <= 3.402823466e+38f && ya <= 3.402823466e+38f &&
+                       !(y < 0.0f && x > 0.0f && ya < xa * 7.8886090522101181e-31f);
+    if (plain)
+        return y >= 0.0f ? 1u : 0u;
+    return (1.57079632679489661923f * fast_atan2f_tab(y, x, tab)) >= 0 ? 1u : 0u;
+}
+
 // G4-G6 + A9 on the symbol stream: quadrature_demod_cf(pi/2) -> binary_slicer_fb ->
 // diff_decoder_bb(2) -> invert.  bit[k] depends on sym[k], sym[k-1], sym[k-2] only, so every
 // thread produces four consecutive bits (one 32-bit store) from six symbols.
@@ -419,10 +435,7 @@ k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict_
        int channels, const float *__restrict__ g_atan, uint8_t *__restrict__ bits,
        size_t bits_stride, float *__restrict__ soft_out, const TailCarry *__restrict__ carry)
 {
-    __shared__ float s_atan[257];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x)
-        s_atan[i] = g_atan[i];
-    __syncthreads();
+    const float *s_atan = g_atan; // read through L1: only the soft output and odd corners need it
     const int c = channel_index();
     if (c >= channels)
         return;
@@ -446,7 +459,7 @@ k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict_
     if (k0 >= 1) {
         const float re = __fmaf_rn(cur.x, prev.x, cur.y * prev.y);
         const float im = __fmaf_rn(cur.y, prev.x, -(cur.x * prev.y));
-        bprev = (qgain * fast_atan2f_tab(im, re, s_atan)) >= 0 ? 1u : 0u;
+        bprev = slicer_bit(im, re, s_atan);
     }
     unsigned pack = 0;
     const int kend = min(4, n - k0);
@@ -455,13 +468,17 @@ k_tail(const float2 *__restrict__ sym, size_t sym_stride, const int *__restrict_
         // quadrature_demod_cf: x[n]*conj(x[n-1]), VOLK multiply-conjugate FMA form
         const float re = __fmaf_rn(v.x, cur.x, v.y * cur.y);
         const float im = __fmaf_rn(v.y, cur.x, -(v.x * cur.y));
-        const float soft = qgain * fast_atan2f_tab(im, re, s_atan);
         cur = v;
-        const unsigned b = soft >= 0 ? 1u : 0u;     // binary_slicer_fb
+        unsigned b;                                 // binary_slicer_fb
+        if (soft_out) {
+            const float soft = qgain * fast_atan2f_tab(im, re, s_atan);
+            soft_out[(size_t)c * sym_stride + k0 + q] = soft;
+            b = soft >= 0 ? 1u : 0u;
+        } else {
+            b = slicer_bit(im, re, s_atan);
+        }
         const unsigned d = (b - bprev) % 2u;        // diff_decoder_bb(2)
         bprev = b;
-        if (soft_out)
-            soft_out[(size_t)c * sym_stride + k0 + q] = soft;
         pack |= ((d ^ 0x01u) & 0x01u) << (8 * q);   // lib/invert_impl.cc:63
     }
     uint8_t *ob = bits + (size_t)c * bits_stride + k0;
