@@ -200,15 +200,6 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
     const int t0 = blockIdx.x * kFOut;
     const int n0 = t0 - kFHalo + 16 * tid; // absolute index of this thread's first sample
     const float2 *xc = x + (size_t)c * x_stride;
-    // the NCO checkpoint and frequency of this thread's 16 samples: requested now, used after
-    // the staging barrier
-    const bool mixes = do_mix && n0 >= 0 && n0 < n1;
-    float ph0 = 0.0f, inc = 0.0f;
-    if (mixes) {
-        ph0 = ckpt[(size_t)(n0 >> 4) * channels + c];
-        inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
-    }
-
     // stage the block's 4096 input samples through shared memory with coalesced loads (lane i
     // reads sample i of each 256-sample row), then every thread picks up its own 16
     {
@@ -236,7 +227,9 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
 #pragma unroll
     for (int k = 0; k < 16; k++)
         v[k] = ys[17 * tid + k];
-    if (mixes) { // n1 is a multiple of fftlen (a multiple of 16): whole segments
+    if (do_mix && n0 >= 0 && n0 < n1) { // n1 is a multiple of fftlen (a multiple of 16): whole segments
+        const float ph0 = ckpt[(size_t)(n0 >> 4) * channels + c];
+        const float inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
         const float F_PI = 3.14159265358979323846f;
         // straight-line fast path.  frequency_modulator_fc leaves d_phase = fmod(u, 2 pi) - pi in
         // (-3 pi, pi): below -pi whenever the frequency is negative (fmod keeps the sign).  There
