@@ -240,11 +240,14 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
         // Anything else takes the general path below.
         const float F_2PI = 2.0f * F_PI;
         float ph = ph0;
-        bool bad = false;
+        // One test for the whole segment: with |inc| <= pi_f and ph in [-3 pi_f, pi_f) a step has
+        // u = (ph + inc) + pi_f in [-3 pi_f, 3 pi_f), the select fold of nco_step() is exact
+        // there, and ph' = r - pi_f lands in (-3 pi_f, pi_f) again (r in (-2 pi_f, 2 pi_f)).
+        // Anything else (also NaN) takes the general path.
+        const bool bad = !(fabsf(inc) <= F_PI && ph0 >= -1.5f * F_2PI && ph0 < F_PI);
 #pragma unroll
         for (int k = 0; k < 16; k++) {
-            ph = nco_step_nobranch(ph, inc, bad);
-            bad = bad || !(ph >= -1.5f * F_2PI && ph < F_PI);
+            ph = nco_step_inrange(ph, inc);
             const float folded = (ph < -F_PI) ? ph + F_2PI : ph;
             float sn, cs;
             fxpt_sincos4(float_to_fixed_inrange(folded), sine, &sn, &cs);
