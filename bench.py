@@ -208,6 +208,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     B.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from gr_ais_b200 import sharding
+    numa_cpus = sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     # rank 0 owns the preamble template; the other ranks receive it over NCCL (the only collective)
     from gr_ais_b200 import sharding
@@ -316,7 +318,8 @@ def run_b200(args):
         e2e = {"value": world * C * (n / FS) / dt_step, "unit": "channels/s",
                "h2d_bytes_per_step": int(C * n * 8),
                "d2h_bytes_per_step": int(C * mb + C * 4 + C * d.max_tags * B.TAG_DTYPE.itemsize + C * 4),
-               "ms_per_step": dt_step * 1e3, "host_memory": "pinned (b200ais_host_alloc)"}
+               "ms_per_step": dt_step * 1e3, "host_memory": "pinned (b200ais_host_alloc)" +
+               (", rank bound to the GPU's %d local CPUs" % len(numa_cpus) if numa_cpus else "")}
 
     # ---- roofline of the dominant kernel (corr_est correlator) ----
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"

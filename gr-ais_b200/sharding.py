@@ -53,3 +53,34 @@ def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs local to `device_index` (NVML's ideal affinity), so
+    that the pinned staging buffers it allocates next live on the GPU's own NUMA node: with
+    eight ranks streaming 6 GB per step each, buffers on the wrong socket halve the host-to-device
+    rate.  Returns the CPU set, or None when NVML is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = None
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(device_index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        except Exception:
+            bus = None
+        h = (pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()) if bus
+             else pynvml.nvmlDeviceGetHandleByIndex(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        return None
+    return None
