@@ -400,13 +400,21 @@ extern "C" int b200ais_hdlc_work(b200ais_hdlc *h, const uint8_t *bits, size_t bi
         return rc;
     B200_CU(cudaMemcpyAsync(nframes, h->nframes.p, sizeof(int) * C, cudaMemcpyDeviceToHost, s));
     B200_CU(cudaStreamSynchronize(s));
-    // copy only the frames that exist
+    // copy only the frames that exist (row by row while few rows have any, else all at once)
+    int busy = 0;
     for (int c = 0; c < C; c++)
-        if (nframes[c] > 0)
-            B200_CU(cudaMemcpyAsync(frames + (size_t)c * max_frames,
-                                    h->frames.as<b200ais_frame>() + (size_t)c * max_frames,
-                                    sizeof(b200ais_frame) * (size_t)nframes[c],
-                                    cudaMemcpyDeviceToHost, s));
+        busy += nframes[c] > 0;
+    if (busy > 64) {
+        B200_CU(cudaMemcpyAsync(frames, h->frames.p, sizeof(b200ais_frame) * (size_t)C * max_frames,
+                                cudaMemcpyDeviceToHost, s));
+    } else {
+        for (int c = 0; c < C; c++)
+            if (nframes[c] > 0)
+                B200_CU(cudaMemcpyAsync(frames + (size_t)c * max_frames,
+                                        h->frames.as<b200ais_frame>() + (size_t)c * max_frames,
+                                        sizeof(b200ais_frame) * (size_t)nframes[c],
+                                        cudaMemcpyDeviceToHost, s));
+    }
     B200_CU(cudaStreamSynchronize(s));
     return b200ais_hdlc_status(h);
 }

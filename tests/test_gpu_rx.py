@@ -100,7 +100,7 @@ def _bit_rows(rng, channels, n, pdus_per_row):
 
 def test_hdlc_matches_oracle_batched_ragged_and_streamed(oracle):
     rng = np.random.default_rng(31)
-    C, n = 37, 6000
+    C, n = 97, 6000    # more than 64 rows with frames: the all-at-once copy of the host path
     rows, nbits, sent = _bit_rows(rng, C, n, 8)
     blk = blocks.hdlc_deframer_bp(11, 64, channels=C)
     refs = [oracle.HdlcDeframer(11, 64) for _ in range(C)]
@@ -219,3 +219,55 @@ def test_ais_rx_end_to_end_matches_oracle_and_decodes_truth(oracle, rate, pieces
             (len(sent & found), len(sent))
         for c, _, p, text in want:
             assert text.startswith("!AIVDM,1,1,,%s," % des[c])
+
+
+def test_xlat_set_taps_and_argument_errors(oracle):
+    import ctypes as C
+    rate, D = 250e3, 5
+    taps = oracle.firdes_low_pass(1.0, rate, 11e3, 1e3)
+    short = oracle.firdes_low_pass(1.0, rate, 11e3, 2e3)    # 301 taps
+    assert len(short) == 301
+    rng = np.random.default_rng(29)
+    x = _noise(rng, (1, len(taps) - 1 + 900 * D))
+    blk = blocks.freq_xlating_fir_filter_ccf(D, taps, [25e3], rate)
+    ref = oracle.FreqXlatingFir(D, taps, 25e3, rate)
+    out = np.zeros((1, 400), np.complex64)
+    blk.work(400, [np.ascontiguousarray(x[:, :len(taps) - 1 + 400 * D])], [out])
+    assert np.array_equal(out[0], ref.work(x[0, :len(taps) - 1 + 400 * D]))
+    # set_taps keeps the rotator's phase and counter; history() follows the new length
+    blk.set_taps(short)
+    assert blk.history() == 301
+    ref2 = oracle.FreqXlatingFir(D, short, 25e3, rate)
+    ref2._x.phase_re, ref2._x.phase_im, ref2._x.counter = ref._x.phase_re, ref._x.phase_im, ref._x.counter
+    piece = x[:, 400 * D: 400 * D + 300 + 500 * D]
+    out = np.zeros((1, 500), np.complex64)
+    blk.work(500, [np.ascontiguousarray(piece)], [out])
+    assert np.array_equal(out[0], ref2.work(piece[0]))
+    # rows shorter than ntaps-1 + noutput*decimation are refused
+    with pytest.raises(ValueError):
+        blk.work(500, [np.ascontiguousarray(piece[:, :-1])], [out])
+    rc = B.lib().b200ais_xlat_work(blk._h, 10, B.ptr(piece), 20, B.ptr(out), 500)
+    assert rc == B.E_INVALID
+    h = C.c_void_p()
+    freqs = np.zeros(17, np.float64)
+    assert B.lib().b200ais_xlat_create(C.byref(h), D, B.ptr(taps), len(taps), B.ptr(freqs), 17, rate, 1) \
+        == B.E_INVALID
+
+
+def test_nmea_reports_a_slot_that_is_too_small():
+    frames = np.zeros((1, 1), dtype=B.FRAME_DTYPE)
+    frames[0, 0]["len"] = 64
+    nframes = np.ones(1, np.int32)
+    des = np.zeros((1, 8), np.uint8)
+    des[0, 0] = ord("A")
+    slot = 48                                   # 86 characters + two headers do not fit
+    sent = np.zeros((1, 1, slot), np.uint8)
+    lens = np.zeros((1, 1), np.int32)
+    B.check(B.lib().b200ais_nmea_format(B.ptr(frames), B.ptr(nframes), 1, 1, B.ptr(des), B.ptr(sent), slot,
+                                        B.ptr(lens)))
+    assert lens[0, 0] == -1 and not sent.any()
+    big = B.lib().b200ais_nmea_slot_bytes(64, b"A")
+    sent = np.zeros((1, 1, big), np.uint8)
+    B.check(B.lib().b200ais_nmea_format(B.ptr(frames), B.ptr(nframes), 1, 1, B.ptr(des), B.ptr(sent), big,
+                                        B.ptr(lens)))
+    assert 0 < lens[0, 0] <= big

@@ -168,3 +168,11 @@ def test_broadcast_template_single_process():
     t = np.arange(6).astype(np.complex64)
     assert np.array_equal(sharding.broadcast_template(t), t)
     assert sharding.max_over_ranks(1.5) == 1.5
+
+
+def test_numa_binding_is_a_no_op_without_nvml_devices():
+    import os
+    from gr_ais_b200 import sharding
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
