@@ -515,6 +515,7 @@ extern "C" int b200ais_nmea_format(const b200ais_frame *frames, const int *nfram
     cudaError_t e = cudaMalloc(&d_frames, nf * sizeof(b200ais_frame));
     if (e == cudaSuccess) e = cudaMalloc(&d_nframes, sizeof(int) * channels);
     if (e == cudaSuccess) e = cudaMalloc(&d_sent, nf * (size_t)slot);
+    if (e == cudaSuccess) e = cudaMemset(d_sent, 0, nf * (size_t)slot);
     if (e == cudaSuccess) e = cudaMalloc(&d_lens, nf * sizeof(int));
     if (e == cudaSuccess && designators) e = cudaMalloc(&d_des, (size_t)channels * 8);
     if (e == cudaSuccess) e = cudaMemcpy(d_frames, frames, nf * sizeof(b200ais_frame), cudaMemcpyHostToDevice);
