@@ -41,7 +41,7 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
 constexpr int kMskChunk = 32;   // samples per prefetch chunk
 constexpr int kMskRing = 128;   // ring samples per channel (4 chunks)
 constexpr int kMskMirror = 8;   // samples 0..7 repeated after the ring: 10-sample reads never wrap
-constexpr int kMskSlots = kMskRing + kMskMirror;       // 8-byte slots (one sample) per lane
+constexpr int kMskUnits = (kMskRing + kMskMirror) / 2; // 16-byte units (2 samples) per lane
 constexpr int kMskInner = 4;    // half-symbol steps per careful round
 constexpr int kMskFast = 8;     // half-symbol steps per straight-line round
 constexpr int kMskNeed = 32;    // samples past iidx a round may touch
@@ -51,6 +51,10 @@ constexpr int kMskTagCap = 32;  // time_est tags per channel staged in shared me
 __device__ __forceinline__ void cp_async_8(unsigned smem, const void *gmem, int src_bytes)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_16(unsigned smem, const void *gmem, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -67,22 +71,31 @@ struct MskLane {
 };
 
 // One half-symbol step from the row index imu (:170-201 without the tag test): interpolate,
-// error detector, loop filter on odd steps, output on even steps, advance.  ring2: this lane's
-// column of the ring (sample j of the lane at ring2[(j mod 128) * 32]).  Returns x = mu + omega
-// before the floor.
+// error detector, loop filter on odd steps, output on even steps, advance.  ring4: this lane's
+// column of the 16-byte-unit ring.  Returns x = mu + omega before the floor.
 template <bool kDebug>
-__device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float2 *__restrict__ ring2,
+__device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *__restrict__ ring4,
                                           const float *__restrict__ s_mmse, const MskParams &p,
                                           float *oe, float *om)
 {
     // mmse_fir_interpolator_cc::interpolate: in[0..7] . reversed row.  The 8 samples start at
-    // ring sample iidx: eight 8-byte loads at fixed offsets from one address (a warp's 32 lanes
-    // read 256 consecutive bytes whatever their sample indices are: conflict-free)
-    const float2 *sp = ring2 + (L.iidx & (kMskRing - 1)) * 32;
+    // ring sample iidx: five 16-byte units (conflict-free: the lane picks the banks), then the
+    // odd/even start is a select
+    const int k = L.iidx;
+    const int u0 = (k >> 1) & (kMskRing / 2 - 1);
+    const bool par = k & 1;
     const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8);
     const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8 + 4);
-    const float2 s0 = sp[0 * 32], s1 = sp[1 * 32], s2 = sp[2 * 32], s3 = sp[3 * 32];
-    const float2 s4 = sp[4 * 32], s5 = sp[5 * 32], s6 = sp[6 * 32], s7 = sp[7 * 32];
+    const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
+    const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
+    const float2 s0 = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
+    const float2 s1 = par ? make_float2(U1.x, U1.y) : make_float2(U0.z, U0.w);
+    const float2 s2 = par ? make_float2(U1.z, U1.w) : make_float2(U1.x, U1.y);
+    const float2 s3 = par ? make_float2(U2.x, U2.y) : make_float2(U1.z, U1.w);
+    const float2 s4 = par ? make_float2(U2.z, U2.w) : make_float2(U2.x, U2.y);
+    const float2 s5 = par ? make_float2(U3.x, U3.y) : make_float2(U2.z, U2.w);
+    const float2 s6 = par ? make_float2(U3.z, U3.w) : make_float2(U3.x, U3.y);
+    const float2 s7 = par ? make_float2(U4.x, U4.y) : make_float2(U3.z, U3.w);
     // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
     const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
     const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
@@ -131,10 +144,9 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float2 *_
 // (#half-symbols) x (latency of one step) however many channels run: the step is kept as
 // short as possible and everything off the recurrence (the bit tail) lives in k_tail.
 // Each lane streams its own channel through a private shared-memory ring (4 chunks of 32
-// samples; sample j of lane l sits at 8-byte slot (j mod 128) * 32 + l, so the 32 lanes of a
-// load always cover 256 consecutive bytes, whatever their sample indices, and the eight samples
-// of an interpolation are eight loads at fixed offsets from one address) with cp.async,
-// requesting a 32-sample chunk ~60 samples before it is needed, so no step waits on HBM.  The lane's time_est tags are staged in shared memory
+// samples, stored as 16-byte units interleaved across lanes so that a lane's reads never
+// meet another lane's banks) with cp.async, requesting a 256-byte chunk ~60 samples before it
+// is needed, so no step waits on HBM.  The lane's time_est tags are staged in shared memory
 // by a prologue (a tag fetched from HBM on the loop's critical path costs a DRAM round trip).
 template <bool kDebug>
 __global__ void __launch_bounds__(32)
@@ -147,7 +159,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
       int *__restrict__ unconsumed)
 {
     __shared__ __align__(16) float s_mmse[129 * 8];
-    __shared__ __align__(16) float2 ring[kMskSlots * 32];
+    __shared__ __align__(16) float4 ring[kMskUnits * 32];
     __shared__ int2 s_tags[kMskTagCap * 32];
     const int lane = threadIdx.x;
     for (int i = lane; i < 129 * 8; i += 32)
@@ -180,11 +192,12 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     const int ninp = ninp0 + mis;
 
     // ring preset: samples before 0 are zero, in[-1] is the item carried from the last call
-    float2 *ring2 = ring + lane;
-    for (int u = 0; u < kMskSlots; u++)
-        ring2[u * 32] = make_float2(0.0f, 0.0f);
-    ring2[(kMskRing - 1) * 32] = make_float2(st.prev_re, st.prev_im);
-    const unsigned my_s = (unsigned)__cvta_generic_to_shared(ring2);
+    float4 *ring4 = ring + lane;
+    for (int u = 0; u < kMskUnits; u++)
+        ring4[u * 32] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    ring4[(kMskRing / 2 - 1) * 32] = make_float4(0.0f, 0.0f, st.prev_re, st.prev_im);
+    const unsigned my_s = (unsigned)__cvta_generic_to_shared(ring4);
+    const bool row16 = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 
     // time_est tags inside [read, read+ninp), in offset order (:125-130): staged in shared
     // memory; a channel with more than kMskTagCap of them reads them from HBM as it goes
@@ -296,27 +309,25 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         if (any & 4u) {
             // (want implies room: the chunk being replaced ends at issue_end - 96 <= iidx - 33)
             if (want) {
-                // one 8-byte copy per sample into its own 256-byte row of the ring (chunks are
-                // 32-sample aligned: they never wrap); samples past the end of the input are
-                // zero-filled (source size 0)
-                const unsigned dst = my_s + (issue_end & (kMskRing - 1)) * 256;
+                const unsigned dst = my_s + ((issue_end >> 1) & (kMskRing / 2 - 1)) * 512;
                 const float2 *src = row + issue_end;
-                const bool first = (issue_end & (kMskRing - 1)) == 0; // also feeds the mirror slots
-                if (issue_end + kMskChunk <= ninput_items) {
+                const bool first = (issue_end & (kMskRing - 1)) == 0; // also feeds the mirror units
+                if (row16 && issue_end + kMskChunk <= ninput_items) {
 #pragma unroll
-                    for (int k = 0; k < kMskChunk; k++)
-                        cp_async_8(dst + 256 * k, src + k, 8);
+                    for (int u = 0; u < kMskChunk / 2; u++)
+                        cp_async_16(dst + 512 * u, src + 2 * u, 16);
                     if (first) {
 #pragma unroll
-                        for (int k = 0; k < kMskMirror; k++)
-                            cp_async_8(my_s + (kMskRing + k) * 256, src + k, 8);
+                        for (int u = 0; u < kMskMirror / 2; u++)
+                            cp_async_16(my_s + (kMskRing / 2 + u) * 512, src + 2 * u, 16);
                     }
                 } else {
                     for (int k = 0; k < kMskChunk; k++) {
                         const int nb = issue_end + k < ninput_items ? 8 : 0;
-                        cp_async_8(dst + 256 * k, nb ? src + k : row, nb);
+                        const unsigned d = dst + 512 * (k >> 1) + 8 * (k & 1);
+                        cp_async_8(d, nb ? src + k : row, nb);
                         if (first && k < kMskMirror)
-                            cp_async_8(my_s + (kMskRing + k) * 256, nb ? src + k : row, nb);
+                            cp_async_8(my_s + (kMskRing / 2 + (k >> 1)) * 512 + 8 * (k & 1), nb ? src + k : row, nb);
                     }
                 }
                 issue_end += kMskChunk;
@@ -332,7 +343,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             for (int it = 0; it < kMskFast; it++) {
                 const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
                 L.bad_imu |= (imu_c != (unsigned)imu);
-                const float x = msk_step<kDebug>(L, (int)imu_c, ring2, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
                 const int fl_i = __float2int_rd(x);
                 imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
                 L.iidx += fl_i;
@@ -366,7 +377,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 const int imu = __float2int_rn(L.mu * 128.0f);
                 const int imu_c = min(max(imu, 0), 128);
                 L.bad_imu |= (imu != imu_c);
-                const float x = msk_step<kDebug>(L, imu_c, ring2, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug>(L, imu_c, ring4, s_mmse, p, oe, om);
                 const float fl = floorf(x);
                 L.iidx += (int)fl;
                 L.mu = x - fl;
