@@ -271,3 +271,58 @@ def test_nmea_reports_a_slot_that_is_too_small():
     B.check(B.lib().b200ais_nmea_format(B.ptr(frames), B.ptr(nframes), 1, 1, B.ptr(des), B.ptr(sent), big,
                                         B.ptr(lens)))
     assert 0 < lens[0, 0] <= big
+
+
+def test_hdlc_adversarial_streams_match_oracle(oracle):
+    """Abort runs, shared flags, truncated frames, and stretches without any flag that run the
+    buffer past length_max (the reset rule drops one bit and starts over): frames, positions and
+    the state carried across ragged calls must equal the oracle's."""
+    rng = np.random.default_rng(43)
+    flag = np.array([0, 1, 1, 1, 1, 1, 1, 0], np.uint8)
+    C = 24
+    rows = []
+    for c in range(C):
+        parts = []
+        for _ in range(12):
+            kind = int(rng.integers(0, 7))
+            pdu = bytes(rng.integers(0, 256, int(rng.integers(9, 62)), dtype=np.uint8).tolist())
+            fcs = synth.crc16_x25(pdu)
+            body = synth.hdlc_stuff(synth.bytes_to_bits_lsb(pdu + bytes([fcs & 0xFF, fcs >> 8])))
+            if kind == 0:
+                parts.append(rng.integers(0, 2, int(rng.integers(1, 300)), dtype=np.uint8))
+            elif kind == 1:
+                parts += [flag, body, flag]
+            elif kind == 2:
+                parts += [flag, body, flag, body, flag]
+            elif kind == 3:
+                parts += [flag, body[:40], np.ones(int(rng.integers(7, 20)), np.uint8), flag]
+            elif kind == 4:
+                parts += [flag, body[:int(rng.integers(1, len(body)))]]
+            elif kind == 5:   # no six ones for a long time: the length_max reset, then a frame
+                parts += [np.tile(np.array([0, 1, 1, 0, 1], np.uint8), int(rng.integers(100, 260))),
+                          flag, body, flag]
+            else:
+                parts += [flag] * int(rng.integers(1, 5))
+        rows.append(np.concatenate(parts).astype(np.uint8))
+    n = max(len(r) for r in rows)
+    bits = np.zeros((C, n), np.uint8)
+    nbits = np.array([len(r) for r in rows], np.int32)
+    for c, r in enumerate(rows):
+        bits[c, :len(r)] = r
+    blk = blocks.hdlc_deframer_bp(11, 64, channels=C)
+    refs = [oracle.HdlcDeframer(11, 64) for _ in range(C)]
+    total = 0
+    pos = 0
+    while pos < n:
+        k = int(rng.integers(1, 700))
+        piece = np.ascontiguousarray(bits[:, pos:pos + k])
+        nb = np.clip(nbits - pos, 0, piece.shape[1]).astype(np.int32)
+        frames, nframes = blk.work(piece, nb, max_frames=16)
+        for c in range(C):
+            ref = refs[c].work(piece[c, :nb[c]])
+            got = frames[c, :nframes[c]]
+            assert nframes[c] == len(ref), (pos, c)
+            assert np.array_equal(got["end_bit"], ref["end_bit"]) and np.array_equal(got["data"], ref["data"])
+            total += len(ref)
+        pos += k
+    assert total > C * 3

@@ -205,3 +205,36 @@ def test_xlat_streams_like_one_call():
     a = O.FreqXlatingFir(D, taps, -25e3, rate).ctaps
     b = O.FreqXlatingFir(D, taps, 25e3, rate).ctaps
     assert np.array_equal(a, np.conj(b))
+
+
+def test_hdlc_oracle_agrees_with_the_independent_deframer_on_random_streams():
+    """Two deframers written independently (the oracle's restatement of hdlc_deframer_bp's
+    counters, synth.hdlc_deframe's flag/frame list) must publish the same payloads from the same
+    bits: random noise with embedded frames, abort runs (seven or more ones), back-to-back and
+    shared flags, and frames cut short."""
+    rng = np.random.default_rng(11)
+    flag = np.array([0, 1, 1, 1, 1, 1, 1, 0], np.uint8)
+    for trial in range(40):
+        parts = []
+        for _ in range(int(rng.integers(3, 9))):
+            kind = int(rng.integers(0, 6))
+            pdu = bytes(rng.integers(0, 256, int(rng.integers(9, 62)), dtype=np.uint8).tolist())
+            fcs = synth.crc16_x25(pdu)
+            body = synth.hdlc_stuff(synth.bytes_to_bits_lsb(pdu + bytes([fcs & 0xFF, fcs >> 8])))
+            if kind == 0:      # noise
+                parts.append(rng.integers(0, 2, int(rng.integers(1, 400)), dtype=np.uint8))
+            elif kind == 1:    # a plain frame
+                parts += [flag, body, flag]
+            elif kind == 2:    # two frames sharing one flag
+                parts += [flag, body, flag, body, flag]
+            elif kind == 3:    # an abort run inside a frame
+                parts += [flag, body[:40], np.ones(int(rng.integers(7, 20)), np.uint8), flag]
+            elif kind == 4:    # a frame cut short by noise
+                parts += [flag, body[:int(rng.integers(1, len(body)))],
+                          rng.integers(0, 2, 30, dtype=np.uint8)]
+            else:              # idle flags
+                parts += [flag] * int(rng.integers(1, 5))
+        bits = np.concatenate(parts).astype(np.uint8)
+        got = O.frames_payloads(O.HdlcDeframer(11, 64).work(bits, max_frames=512))
+        want = synth.hdlc_deframe(bits, min_bytes=9, max_bytes=62)
+        assert got == want, trial
