@@ -386,7 +386,7 @@ size_t reader_read(ItemReader *r, float2 *dst, size_t want) { return r->read(dst
 
 } // namespace
 
-// blocks.file_source(gr.sizeof_gr_complex, filename) (python/radio.py:204-207) feeding every
+// blocks.file_source(gr.sizeof_gr_complex, filename) (python/radio.py:211-213) feeding every
 // source of the receiver with the same recorded capture (replay fan-out): raw interleaved
 // float32 IQ, read in chunks through two pinned buffers -- the read of chunk k+1 runs on a
 // host thread while chunk k is copied and processed -- copied to the device once and
@@ -492,7 +492,7 @@ extern "C" int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chunk
     return rx_pump(h, &rd, chunk_items, max_msgs, sink, user, items_read, ~(uint64_t)0);
 }
 
-// blocks.udp_source(gr.sizeof_gr_complex, ip, port) (python/radio.py:209-213)
+// blocks.udp_source(gr.sizeof_gr_complex, ip, port) (python/radio.py:204-210)
 extern "C" int b200ais_rx_serve_udp(b200ais_rx *h, const char *bind_ip, int port, int chunk_items,
                                     int max_msgs, uint64_t max_items, int idle_ms,
                                     b200ais_rx_sink sink, void *user, uint64_t *items_read)

@@ -105,14 +105,14 @@ class ais_rx:
 
     def replay_file(self, path, chunk_items=None, max_msgs=None):
         """blocks.file_source(gr.sizeof_gr_complex, path) into every source (python/radio.py:
-        204-207): raw interleaved float32 IQ, double-buffered pinned reads.  Returns
+        211-213): raw interleaved float32 IQ, double-buffered pinned reads.  Returns
         (msgs, sentences, items_read) over the whole file, sorted by (channel, end_bit)."""
         return self._pump(lambda cb, items, chunk, mm: B.lib().b200ais_rx_replay_file(
             self._h, os.fsencode(path), chunk, mm, cb, None, C.byref(items)), chunk_items, max_msgs)
 
     def serve_udp(self, ip, port, chunk_items=None, max_msgs=None, max_items=0, idle_ms=1000):
         """blocks.udp_source(gr.sizeof_gr_complex, ip, port) into every source (python/radio.py:
-        209-213).  Blocks until a zero-length datagram, max_items items or idle_ms of silence."""
+        204-210).  Blocks until a zero-length datagram, max_items items or idle_ms of silence."""
         return self._pump(lambda cb, items, chunk, mm: B.lib().b200ais_rx_serve_udp(
             self._h, ip.encode(), int(port), chunk, mm, int(max_items), int(idle_ms), cb, None,
             C.byref(items)), chunk_items, max_msgs)

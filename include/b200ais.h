@@ -428,7 +428,7 @@ B200AIS_API int b200ais_rx_work_dev(b200ais_rx *h, const float *iq, size_t iq_st
                                     b200ais_frame *msgs, char *sentences, int slot, int *lens,
                                     int max_msgs, int *nmsgs, void *stream);
 B200AIS_API int b200ais_rx_status(b200ais_rx *h);
-/* Recorded-IQ replay: blocks.file_source(gr.sizeof_gr_complex, path) (python/radio.py:204-207)
+/* Recorded-IQ replay: blocks.file_source(gr.sizeof_gr_complex, path) (python/radio.py:211-213)
  * feeding every source of the receiver with the same capture.  The file (raw interleaved
  * float32 IQ) is read in chunks of chunk_items through two pinned buffers, the read of the next
  * chunk overlapping the copy and the processing of the current one; each chunk crosses PCIe
@@ -440,7 +440,7 @@ B200AIS_API int b200ais_rx_replay_file(b200ais_rx *h, const char *path, int chun
                                        int max_msgs, b200ais_rx_sink sink, void *user,
                                        uint64_t *items_read);
 /* The same pump fed by blocks.udp_source(gr.sizeof_gr_complex, ip, port) (python/radio.py:
- * 209-213): datagram payloads are a byte stream of raw float32 IQ items.  Returns after a
+ * 204-210): datagram payloads are a byte stream of raw float32 IQ items.  Returns after a
  * zero-length datagram (GNU Radio's end-of-stream mark), after max_items items (0 = no limit), or
  * when no datagram arrives for idle_ms. */
 B200AIS_API int b200ais_rx_serve_udp(b200ais_rx *h, const char *bind_ip, int port, int chunk_items,

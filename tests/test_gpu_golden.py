@@ -47,7 +47,7 @@ def test_ais_rx_equals_golden_sentences():
 
 
 def test_ais_rx_replays_a_recorded_file(tmp_path):
-    """blocks.file_source semantics (python/radio.py:204-207): raw interleaved float32 IQ on
+    """blocks.file_source semantics (python/radio.py:211-213): raw interleaved float32 IQ on
     disk, fanned out to every source; chunked, double-buffered reads give the golden sentences."""
     z = load("rx_kat.npz")
     x = z["iq"]
@@ -65,7 +65,7 @@ def test_ais_rx_replays_a_recorded_file(tmp_path):
 
 
 def test_ais_rx_serves_a_udp_stream():
-    """blocks.udp_source semantics (python/radio.py:209-213): datagram payloads are a byte stream
+    """blocks.udp_source semantics (python/radio.py:204-210): datagram payloads are a byte stream
     of raw float32 IQ items (split anywhere, also inside an item); a zero-length datagram ends
     the stream.  Sentences equal the golden ones."""
     import socket
