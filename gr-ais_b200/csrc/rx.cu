@@ -60,7 +60,7 @@ extern "C" int b200ais_rx_default_config(b200ais_rx_config *c)
     c->bits_per_sec = 9600.0f;       // python/radio.py:47
     c->clockrec_gain = 0.04f;        // :58
     c->omega_relative_limit = 0.01f; // :59
-    c->fftlen = 1024;                // :60
+    c->fftlen = 1024;                // :61
     c->lpf_cutoff = 11000.0;         // :49
     c->lpf_transition = 1000.0;
     c->hdlc_length_min = 11;         // :64

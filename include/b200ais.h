@@ -182,7 +182,7 @@ enum { B200AIS_STAGE_FREQSYNC = 1, B200AIS_STAGE_AGC = 2 };
 typedef struct b200ais_demod_config {
     float sample_rate;   /* samples_per_symbol * bits_per_sec (python/ais_demod.py:30) */
     int data_rate;       /* bits_per_sec */
-    int fftlen;          /* options["fftlen"] (python/radio.py:60) */
+    int fftlen;          /* options["fftlen"] (python/radio.py:61) */
     int agc_nsamples;    /* feedforward_agc_cc(512, 2) (python/ais_demod.py:35) */
     float agc_reference;
     float sps;
