@@ -744,14 +744,14 @@ extern "C" int b200ais_demod_default_config(b200ais_demod_config *cfg)
         return B200AIS_E_INVALID;
     cfg->sample_rate = 48000.0f; // python/radio.py:47-48,62
     cfg->data_rate = 9600;
-    cfg->fftlen = 1024;          // python/radio.py:60
+    cfg->fftlen = 1024;          // python/radio.py:61
     cfg->agc_nsamples = 512;     // python/ais_demod.py:35
     cfg->agc_reference = 2.0f;
     cfg->sps = 5.0f;
     cfg->mark_delay = 1;         // python/ais_demod.py:41
     cfg->threshold = 0.9f;       // python/ais_demod.py:42
-    cfg->gain = 0.04f;           // python/radio.py:57
-    cfg->limit = 0.01f;          // python/radio.py:58
+    cfg->gain = 0.04f;           // python/radio.py:58
+    cfg->limit = 0.01f;          // python/radio.py:59
     cfg->osps = 1;
     cfg->corr_chunk = 0;
     cfg->stages = B200AIS_STAGE_FREQSYNC | B200AIS_STAGE_AGC;

@@ -130,7 +130,7 @@ def test_snr_sweep_gpu_equals_oracle():
 
 @pytest.mark.parametrize("fftlen", [256, 512, 2048, 4096])
 def test_other_fft_lengths_take_the_generic_kernel(oracle, templates, fftlen):
-    """options["fftlen"] (python/radio.py:60) other than 1024: generic shared-memory FFT kernel"""
+    """options["fftlen"] (python/radio.py:61) other than 1024: generic shared-memory FFT kernel"""
     x, _ = _records(3, 3 * 4096, nbursts=2, snr_db=20)
     _compare_chain(oracle, x, templates[120], B.STAGE_FREQSYNC | B.STAGE_AGC, options={"fftlen": fftlen})
 
