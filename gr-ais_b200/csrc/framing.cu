@@ -52,34 +52,37 @@ __device__ __noinline__ int hdlc_emit(const unsigned char *buf, int bytectr, b20
 //    it are the closing flag's).  crc_ccitt(data) == the two bytes that follow, the reference's
 //    test, holds exactly when the register over data + those two bytes is the CRC-16/X.25
 //    residue 0xF0B8 (for a given prefix the last 16 bits map one-to-one onto the register).
+// The step is written with selects: lanes of a warp sit in different states, and as branches
+// every path would run for every bit.  Only a good frame (rare) leaves the straight line.
 #define HDLC_STEP(bit_, i_)                                                                  \
     do {                                                                                     \
         const unsigned b__ = (bit_);                                                         \
-        if (ones >= 5) {                                                                     \
-            if (b__) { /* six ones: frame delimiter */                                       \
-                if (bytectr >= length_min && crcb == 0xF0B8u) {                              \
-                    const int r__ = hdlc_emit(buf, bytectr, myframes, nf, max_frames, c,     \
-                                              base + (unsigned long long)(i_));              \
-                    overflow |= r__ < 0;                                                     \
-                    nf = r__ < 0 ? nf : r__;                                                 \
-                }                                                                            \
-                bitctr = 0;                                                                  \
-                bytectr = 0;                                                                 \
-                crc = crcb = 0xFFFFu;                                                        \
-            } /* else: stuffed zero, dropped */                                              \
-        } else if (bytectr > length_max) {                                                   \
-            bytectr = 0;                                                                     \
-            bitctr = 0;                                                                      \
-            crc = crcb = 0xFFFFu;                                                            \
-        } else {                                                                             \
-            cur = (cur >> 1) | (b__ << 7);                                                   \
-            crc = (crc >> 1) ^ (((crc ^ b__) & 1u) ? 0x8408u : 0u);                          \
-            if (++bitctr == 8) {                                                             \
-                buf[bytectr++] = (unsigned char)cur;                                         \
-                bitctr = 0;                                                                  \
-                crcb = crc;                                                                  \
-            }                                                                                \
+        const bool five__ = ones >= 5;                                                       \
+        const bool delim__ = five__ && b__;             /* six ones: frame delimiter */      \
+        const bool over__ = !five__ && bytectr > length_max;                                 \
+        const bool shift__ = !five__ && !over__;        /* else: stuffed zero, dropped */    \
+        if (delim__ && bytectr >= length_min && crcb == 0xF0B8u) {                           \
+            const int r__ = hdlc_emit(buf, bytectr, myframes, nf, max_frames, c,             \
+                                      base + (unsigned long long)(i_));                      \
+            overflow |= r__ < 0;                                                             \
+            nf = r__ < 0 ? nf : r__;                                                         \
         }                                                                                    \
+        const unsigned cur_n__ = (cur >> 1) | (b__ << 7);                                    \
+        const unsigned crc_n__ = (crc >> 1) ^ (((crc ^ b__) & 1u) ? 0x8408u : 0u);           \
+        cur = shift__ ? cur_n__ : cur;                                                       \
+        crc = shift__ ? crc_n__ : crc;                                                       \
+        bitctr += shift__ ? 1 : 0;                                                           \
+        const bool full__ = shift__ && bitctr == 8;                                          \
+        if (full__)                                                                          \
+            buf[bytectr] = (unsigned char)cur;                                               \
+        bytectr += full__ ? 1 : 0;                                                           \
+        bitctr = full__ ? 0 : bitctr;                                                        \
+        crcb = full__ ? crc : crcb;                                                          \
+        const bool rst__ = delim__ || over__;                                                \
+        bytectr = rst__ ? 0 : bytectr;                                                       \
+        bitctr = rst__ ? 0 : bitctr;                                                         \
+        crc = rst__ ? 0xFFFFu : crc;                                                         \
+        crcb = rst__ ? 0xFFFFu : crcb;                                                       \
         ones = b__ ? ones + 1 : 0;                                                           \
     } while (0)
 
