@@ -221,9 +221,11 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
 #pragma unroll
         for (int q = 0; q < 8; q++)
             u[q] = cx[fphys(hi * 128 + q * 16 + lo)];
-        const float2 w1 = tw[lo << 5];
-        const float2 w2[2] = { tw[lo << 4], tw[(lo + 16) << 4] };
-        const float2 w3[4] = { tw[lo << 3], tw[(lo + 16) << 3], tw[(lo + 32) << 3], tw[(lo + 48) << 3] };
+        // tw[lo << 5], tw[(lo + 16 j) << 4], tw[(lo + 16 j) << 3] from the [slot][lo] copies
+        // behind the table (get_twiddles): a warp's read covers 128 consecutive bytes
+        const float2 w1 = tw[512 + lo];
+        const float2 w2[2] = { tw[528 + lo], tw[544 + lo] };
+        const float2 w3[4] = { tw[560 + lo], tw[576 + lo], tw[592 + lo], tw[608 + lo] };
         pass8(u, w1, w2, w3);
 #pragma unroll
         for (int q = 0; q < 8; q++)
@@ -237,8 +239,8 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
 #pragma unroll
         for (int q = 0; q < 8; q++)
             u[q] = cx[fphys(q * 128 + lo)];
-        const float2 w1 = tw[lo << 2];
-        const float2 w2[2] = { tw[lo << 1], tw[(lo + 128) << 1] };
+        const float2 w1 = tw[624 + lo];                               // tw[lo << 2]
+        const float2 w2[2] = { tw[752 + lo], tw[880 + lo] };          // tw[(lo + 128 j) << 1]
         const float2 w3[4] = { tw[lo], tw[lo + 128], tw[lo + 256], tw[lo + 384] };
         pass8(u, w1, w2, w3);
 #pragma unroll
