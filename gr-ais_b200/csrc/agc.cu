@@ -186,7 +186,7 @@ template <bool kHist>
 __global__ void __launch_bounds__(256, 3)
 k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1, int fftlen,
              const float *__restrict__ fhat, int vstride, const float *__restrict__ ckpt, float sens,
-             int do_mix, float reference, const float4 *__restrict__ sine,
+             int do_mix, float reference, const float4 *__restrict__ sine, cudaTextureObject_t sine_tex,
              float2 *__restrict__ out, size_t out_stride, const float2 *__restrict__ hist_in,
              float2 *__restrict__ hist_out)
 {
@@ -250,7 +250,7 @@ k_mix_agc512(const float2 *__restrict__ x, size_t x_stride, int channels, int n1
             ph = nco_step_inrange(ph, inc);
             const float folded = (ph < -F_PI) ? ph + F_2PI : ph;
             float sn, cs;
-            fxpt_sincos4(float_to_fixed_inrange(folded), sine, &sn, &cs);
+            fxpt_sincos4_tex(float_to_fixed_inrange(folded), sine_tex, &sn, &cs);
             v[k] = cmul_fma(v[k], make_float2(cs, sn));
         }
         if (bad) { // general path (fmod, fold, true division) from the raw samples still in ys
@@ -356,7 +356,7 @@ int launch_mix_agc(const float2 *x, size_t x_stride, int channels, int n1, int f
                                      (int)smem512));                                              \
         k_mix_agc512<H><<<grid512, 256, smem512, s>>>(x, x_stride, channels, n1, fftlen, fhat,  \
                                                          vstride, ckpt, sens, do_mix, agc_reference, \
-                                                         sine, out, out_stride, hi, ho);          \
+                                                         sine, tb.sine4_tex, out, out_stride, hi, ho); \
     } while (0)
             B200_MIX(true, hist_in, hist_out);
         } else {

@@ -76,6 +76,8 @@ struct Tables {
     const float *sine; // [1024][2] gr::fxpt sine table {slope, intercept}
     const float *sine4; // [1024][4] the same, entry i = {sine[i], sine[(i + 256) % 1024]}: the
                         // sine and cosine segments of one angle in a single 16-byte load
+    cudaTextureObject_t sine4_tex; // sine4 as a 1-D float4 texture (point fetch: the same bits
+                                   // through the texture pipe instead of the load/store pipe)
 };
 int get_tables(Tables *t);
 // FFT twiddles for length n on the current device: n/2 complex, W[k] = exp(-2 pi i k/n)
