@@ -44,6 +44,12 @@ def score(pdus, tags, ntags, truth, L, sps=5):
     return det, crc, tot
 
 
+def _record(c, n, nbursts, snr):
+    from gr_ais_b200 import synth
+    return synth.make_record(c, n=n, nbursts=nbursts, snr_db=snr, random_impairments=True,
+                             seed=synth.SEED + int(snr * 10))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--channels", type=int, default=1024)
@@ -51,7 +57,13 @@ def main():
     ap.add_argument("--seconds", type=float, default=0.5)
     ap.add_argument("--snrs", type=float, nargs="+", default=[0, 4, 8, 12, 16, 20])
     ap.add_argument("--threshold", type=float, default=0.9)
+    ap.add_argument("--procs", type=int, default=0,
+                    help="worker processes that synthesise the records (0 = in this process)")
     args = ap.parse_args()
+    pool = None
+    if args.procs > 1:  # forked before anything touches CUDA: the workers only run numpy
+        import multiprocessing as mp
+        pool = mp.get_context("fork").Pool(args.procs)
     from gr_ais_b200 import synth
     from gr_ais_b200.ais_demod import ais_demod, preamble_template
     from oracle import oracle as O
@@ -64,9 +76,11 @@ def main():
     deframer = blocks.hdlc_deframer_bp(11, 64, channels=args.channels)
     rows = []
     for snr in args.snrs:
-        recs = [synth.make_record(c, n=n, nbursts=max(1, int(4 * args.seconds)), snr_db=snr,
-                                  random_impairments=True, seed=synth.SEED + int(snr * 10))
-                for c in range(args.channels)]
+        jobs = [(c, n, max(1, int(4 * args.seconds)), snr) for c in range(args.channels)]
+        if pool is not None:
+            recs = pool.starmap(_record, jobs, chunksize=64)
+        else:
+            recs = [_record(*j) for j in jobs]
         x = np.stack([r[0] for r in recs])
         truth = [r[1] for r in recs]
         bits, nbits, tags, ntags = d.work(x)
@@ -88,6 +102,8 @@ def main():
                          gpu_equals_oracle_on_subset=bool(same)))
         print(json.dumps(rows[-1]), flush=True)
     d.close()
+    if pool is not None:
+        pool.close()
     return rows
 
 
