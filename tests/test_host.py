@@ -176,3 +176,15 @@ def test_numa_binding_is_a_no_op_without_nvml_devices():
     before = os.sched_getaffinity(0)
     assert sharding.bind_to_gpu_numa_node(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/b200ais.h must compile as C99 on its own."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text('#include "b200ais.h"\nint main(void) { b200ais_rx_config c; (void)c; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(root, "include"), str(src)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
