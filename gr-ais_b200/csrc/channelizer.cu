@@ -97,66 +97,51 @@ __device__ __forceinline__ void cp_async_wait_all()
 }
 
 // R taps of one polyphase branch (the branches are zero-padded to whole groups of R taps:
-// fma(0, x, acc) leaves acc as it is for every finite x).  A thread runs NW windows of R outputs
-// (window w starts THREADS*R outputs after window w-1): one tap load feeds all of them, and the
-// unrolled body stays R steps long.
-template <int kR, int NW>
-__device__ __forceinline__ void fir_steps(Acc<kR> (&a)[NW], float2 (&W)[NW][kR], float2 (&nxt)[NW],
-                                          float2 &c, const float2 *__restrict__ tp,
-                                          const float2 *__restrict__ xp, const int (&u_next)[NW])
+// fma(0, x, acc) leaves acc as it is for every finite x)
+template <int kR>
+__device__ __forceinline__ void fir_steps(Acc<kR> &a, float2 (&W)[kR], float2 &nxt, float2 &c,
+                                          const float2 *__restrict__ tp, const float2 *__restrict__ xp,
+                                          int u_next)
 {
 #pragma unroll
     for (int s = 0; s < kR; s++) {
         const float2 cc = c;
         c = tp[s + 1]; // the tap array has one slack item behind it
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-#pragma unroll
-            for (int r = 0; r < kR; r++) {
-                const float2 x = W[w][(r - s) & (kR - 1)];
-                a[w].Pr[r] = __fmaf_rn(cc.x, x.x, a[w].Pr[r]);
-                a[w].Pi[r] = __fmaf_rn(cc.x, x.y, a[w].Pi[r]);
-                a[w].Qr[r] = __fmaf_rn(cc.y, x.x, a[w].Qr[r]);
-                a[w].Qi[r] = __fmaf_rn(cc.y, x.y, a[w].Qi[r]);
-            }
-            W[w][(kR - 1 - s) & (kR - 1)] = nxt[w];
-            nxt[w] = xp[padr<kR>(u_next[w] - s)];
+        for (int r = 0; r < kR; r++) {
+            const float2 x = W[(r - s) & (kR - 1)];
+            a.Pr[r] = __fmaf_rn(cc.x, x.x, a.Pr[r]);
+            a.Pi[r] = __fmaf_rn(cc.x, x.y, a.Pi[r]);
+            a.Qr[r] = __fmaf_rn(cc.y, x.x, a.Qr[r]);
+            a.Qi[r] = __fmaf_rn(cc.y, x.y, a.Qi[r]);
         }
+        W[(kR - 1 - s) & (kR - 1)] = nxt;
+        nxt = xp[padr<kR>(u_next - s)];
     }
 }
 
 // one polyphase branch p: a plain FIR over the residue row xp
-template <int kR, int NW>
-__device__ __forceinline__ void fir_branch(Acc<kR> (&acc)[NW], const float2 *__restrict__ xp,
-                                           const float2 *__restrict__ tp, int r0, int wstride, int b_p,
-                                           int Qpad)
+template <int kR>
+__device__ __forceinline__ void fir_branch(Acc<kR> &acc, const float2 *__restrict__ xp,
+                                           const float2 *__restrict__ tp, int r0, int b_p, int Qpad)
 {
     constexpr int kFront = kR + 2;
-    float2 W[NW][kR], nxt[NW];
-    int u0[NW];
+    const int u0 = r0 + b_p + kFront; // window at tap 0: items u0 .. u0+R-1
+    float2 W[kR];
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
-        u0[w] = r0 + w * wstride + b_p + kFront; // window at tap 0: items u0 .. u0+R-1
-#pragma unroll
-        for (int i = 0; i < kR; i++)
-            W[w][i] = xp[padr<kR>(u0[w] + i)];
-        nxt[w] = xp[padr<kR>(u0[w] - 1)];
-    }
+    for (int i = 0; i < kR; i++)
+        W[i] = xp[padr<kR>(u0 + i)];
+    float2 nxt = xp[padr<kR>(u0 - 1)];
     float2 c = tp[0];
-    for (int q = 0; q < Qpad; q += kR) {
-        int un[NW];
-#pragma unroll
-        for (int w = 0; w < NW; w++)
-            un[w] = u0[w] - q - 2;
-        fir_steps<kR, NW>(acc, W, nxt, c, tp + q, xp, un);
-    }
+    for (int q = 0; q < Qpad; q += kR)
+        fir_steps<kR>(acc, W, nxt, c, tp + q, xp, u0 - q - 2);
 }
 
 // G: residue rows resident in shared memory at a time.  G >= D: the whole tile is staged once,
 // with coalesced reads (row = residue).  G < D (large decimations, e.g. 25 at 1.2 Msps): the
 // branches are walked in groups of G, each group's rows staged just before it (row = branch -
 // first branch of the group; a lane reads every D-th item).
-template <int THREADS, int kR, int NW>
+template <int THREADS, int kR>
 __global__ void __launch_bounds__(THREADS)
 k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int ntaps, int ntp,
            const float2 *__restrict__ taps_pm, const int *__restrict__ pass_a,
@@ -166,7 +151,7 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     extern __shared__ float2 smem[];
     float2 *tps = smem;            // [ntp + 1] this pass's taps, polyphase-major, zero-padded
     float2 *xs = smem + ntp + 1;   // [min(G, D)][Mp] input tile by residue mod D
-    constexpr int J = THREADS * kR * NW;
+    constexpr int J = THREADS * kR;
     constexpr int kFront = kR + 2; // zeroed items in front of every residue row: the window of
                                    // the padded taps and its prefetch end up there
     const int tid = threadIdx.x;
@@ -188,14 +173,11 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
     const float2 *row = in + (size_t)src * in_stride + (size_t)jb * D;
     const int T = (jt - 1) * D + ntaps;
 
-    Acc<kR> acc[NW];
+    Acc<kR> acc;
 #pragma unroll
-    for (int w = 0; w < NW; w++)
-#pragma unroll
-        for (int r = 0; r < kR; r++)
-            acc[w].Pr[r] = acc[w].Pi[r] = acc[w].Qr[r] = acc[w].Qi[r] = 0.f;
+    for (int r = 0; r < kR; r++)
+        acc.Pr[r] = acc.Pi[r] = acc.Qr[r] = acc.Qi[r] = 0.f;
     const int r0 = tid * kR;
-    constexpr int kWs = THREADS * kR; // outputs between a thread's windows
     const float2 *tp = tps;
 
     if (G >= D) {
@@ -217,7 +199,7 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
             const int lag = ntaps - 1 - p;
             const int b_p = lag / D, a_p = lag - b_p * D;
             const int Qpad = (b_p + kR) / kR * kR; // b_p + 1 taps (p, p+D, ... < ntaps), padded
-            fir_branch<kR, NW>(acc, xs + a_p * Mp, tp, r0, kWs, b_p, Qpad);
+            fir_branch<kR>(acc, xs + a_p * Mp, tp, r0, b_p, Qpad);
             tp += Qpad;
         }
     } else {
@@ -236,36 +218,32 @@ k_xlat_fir(const float2 *__restrict__ in, size_t in_stride, int n, int D, int nt
                 const int lag = ntaps - 1 - (p0 + r);
                 const int b_p = lag / D;
                 const int Qpad = (b_p + kR) / kR * kR;
-                fir_branch<kR, NW>(acc, xs + r * Mp, tp, r0, kWs, b_p, Qpad);
+                fir_branch<kR>(acc, xs + r * Mp, tp, r0, b_p, Qpad);
                 tp += Qpad;
             }
         }
     }
 
     const int ka = pass_a[pass], kb = pass_b[pass];
+    float2 *oa = out + ((size_t)src * nfreqs + ka) * out_stride + jb + r0;
+    const float2 *ra = rot + (size_t)ka * rot_stride + jb + r0;
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const int rw = r0 + w * kWs;
-        float2 *oa = out + ((size_t)src * nfreqs + ka) * out_stride + jb + rw;
-        const float2 *ra = rot + (size_t)ka * rot_stride + jb + rw;
+    for (int r = 0; r < kR; r++) {
+        if (r0 + r < jt) {
+            const float yr = acc.Pr[r] - acc.Qi[r], yi = acc.Pi[r] + acc.Qr[r];
+            const float2 ph = ra[r];
+            oa[r] = make_float2(yr * ph.x - yi * ph.y, yr * ph.y + yi * ph.x);
+        }
+    }
+    if (kb >= 0) {
+        float2 *ob = out + ((size_t)src * nfreqs + kb) * out_stride + jb + r0;
+        const float2 *rb = rot + (size_t)kb * rot_stride + jb + r0;
 #pragma unroll
         for (int r = 0; r < kR; r++) {
-            if (rw + r < jt) {
-                const float yr = acc[w].Pr[r] - acc[w].Qi[r], yi = acc[w].Pi[r] + acc[w].Qr[r];
-                const float2 ph = ra[r];
-                oa[r] = make_float2(yr * ph.x - yi * ph.y, yr * ph.y + yi * ph.x);
-            }
-        }
-        if (kb >= 0) {
-            float2 *ob = out + ((size_t)src * nfreqs + kb) * out_stride + jb + rw;
-            const float2 *rb = rot + (size_t)kb * rot_stride + jb + rw;
-#pragma unroll
-            for (int r = 0; r < kR; r++) {
-                if (rw + r < jt) {
-                    const float yr = acc[w].Pr[r] + acc[w].Qi[r], yi = acc[w].Pi[r] - acc[w].Qr[r];
-                    const float2 ph = rb[r];
-                    ob[r] = make_float2(yr * ph.x - yi * ph.y, yr * ph.y + yi * ph.x);
-                }
+            if (r0 + r < jt) {
+                const float yr = acc.Pr[r] + acc.Qi[r], yi = acc.Pi[r] - acc.Qr[r];
+                const float2 ph = rb[r];
+                ob[r] = make_float2(yr * ph.x - yi * ph.y, yr * ph.y + yi * ph.x);
             }
         }
     }
@@ -280,9 +258,9 @@ int xlat_padded_taps(int R, int D, int ntaps)
     return n;
 }
 
-size_t xlat_smem_bytes(int threads, int R, int D, int ntaps, int *Mp_out, int rows = 0, int NW = 1)
+size_t xlat_smem_bytes(int threads, int R, int D, int ntaps, int *Mp_out, int rows = 0)
 {
-    const int J = threads * R * NW;
+    const int J = threads * R;
     const int M = J + (ntaps + D - 1) / D + (R + 2) + 1;
     const int Mp = M + M / R + 1;
     if (Mp_out)
@@ -547,17 +525,17 @@ extern "C" int b200ais_xlat_reset(b200ais_xlat *h)
     return B200AIS_OK;
 }
 
-template <int THREADS, int R, int NW = 1>
+template <int THREADS, int R>
 static int xlat_launch(b200ais_xlat *h, int n, const float2 *in, size_t in_stride, float2 *out,
                        size_t out_stride, int G, cudaStream_t s)
 {
     int Mp = 0;
-    const size_t smem = xlat_smem_bytes(THREADS, R, h->D, h->ntaps, &Mp, G, NW);
-    B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = xlat_smem_bytes(THREADS, R, h->D, h->ntaps, &Mp, G);
+    B200_CU(cudaFuncSetAttribute(k_xlat_fir<THREADS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  227 * 1024));
-    const int J = THREADS * R * NW;
+    const int J = THREADS * R;
     dim3 grid((unsigned)((n + J - 1) / J), (unsigned)h->sources, (unsigned)h->npass);
-    k_xlat_fir<THREADS, R, NW><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps,
+    k_xlat_fir<THREADS, R><<<grid, THREADS, smem, s>>>(in, in_stride, n, h->D, h->ntaps,
                                                        h->ntp[R == 16], h->d_taps[R == 16],
                                                        h->d_pass, h->d_pass + kMaxFreqs, h->nfreqs,
                                                        h->rottab.as<float2>(), (size_t)n, out,
@@ -596,13 +574,6 @@ extern "C" int b200ais_xlat_work_dev(b200ais_xlat *h, int noutput_items, const f
     if (g_xlat_shape < 0) {
         const char *e = getenv("B200AIS_XLAT_SHAPE");
         g_xlat_shape = e ? atoi(e) : 99;
-    }
-    // experiment: two interleaved 8-output windows per thread (shape 5: 64 threads, 6: 128)
-    if ((g_xlat_shape == 5 || g_xlat_shape == 6) &&
-        xlat_smem_bytes(g_xlat_shape == 5 ? 64 : 128, 8, h->D, h->ntaps, nullptr, 0, 2) <= 227 * 1024) {
-        if (g_xlat_shape == 5)
-            return xlat_launch<64, 8, 2>(h, n, x, in_stride, y, out_stride, h->D, s);
-        return xlat_launch<128, 8, 2>(h, n, x, in_stride, y, out_stride, h->D, s);
     }
     // a 16-outputs-per-thread tile with two CTAs per SM: whole (all D residue rows resident) if
     // it fits, else with as many rows at a time as fit; the small tiles are the last resort
