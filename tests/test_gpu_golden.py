@@ -94,7 +94,7 @@ def test_ais_rx_serves_a_udp_stream():
             tx.sendto(raw[pos:pos + n], ("127.0.0.1", port))
             pos += n
             k += 1
-            if k % 4 == 0:
+            if k % 2 == 0:   # ~3 MB/s: the socket buffer rides out a slow chunk on the device
                 time.sleep(0.001)
         for _ in range(3):
             tx.sendto(b"", ("127.0.0.1", port))

@@ -188,3 +188,38 @@ def test_header_is_plain_c(tmp_path):
                         "-I", os.path.join(root, "include"), str(src)],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_receiver_rows_have_no_cpu_fallback_either(oracle):
+    """firdes.low_pass is init-time host code (as in the reference) and works anywhere; the
+    channeliser, deframer, NMEA formatter and ais_rx need the device and say so."""
+    from gr_ais_b200 import blocks
+    from gr_ais_b200.radio import ais_rx
+    taps = blocks.firdes_low_pass(1.0, 250e3, 11e3, 1e3)
+    assert np.array_equal(taps, oracle.firdes_low_pass(1.0, 250e3, 11e3, 1e3))
+    with pytest.raises(B.B200AisError) as e:
+        blocks.firdes_low_pass(1.0, 250e3, 200e3, 1e3)     # cutoff beyond fs/2: std::out_of_range
+    assert e.value.code == B.E_RANGE
+    if _cuda_present():
+        pytest.skip("a CUDA device is present")
+    for make in (lambda: blocks.freq_xlating_fir_filter_ccf(5, taps, [-25e3, 25e3], 250e3),
+                 lambda: blocks.hdlc_deframer_bp(11, 64),
+                 lambda: ais_rx([-25e3, 25e3], 250e3, ["A", "B"])):
+        with pytest.raises(B.B200AisError) as e:
+            make()
+        assert e.value.code in (B.E_CUDA, B.E_NOMEM)
+    with pytest.raises(B.B200AisError):
+        blocks.pdu_to_nmea("A").to_nmea(bytes(21))
+
+
+def test_rx_default_config_matches_the_reference_receiver():
+    import ctypes as C
+    cfg = B.RxConfig()
+    B.check(B.lib().b200ais_rx_default_config(C.byref(cfg)))
+    assert cfg.rate == 250e3 and cfg.nfreqs == 2                  # python/radio.py:120, :88-89
+    assert (cfg.freqs[0], cfg.freqs[1]) == (161.975e6 - 162.0e6, 162.025e6 - 162.0e6)
+    assert cfg.designators[0].value == b"A" and cfg.designators[1].value == b"B"
+    assert (cfg.hdlc_length_min, cfg.hdlc_length_max) == (11, 64)  # :64
+    assert (cfg.lpf_cutoff, cfg.lpf_transition) == (11000.0, 1000.0)  # :49
+    assert abs(cfg.clockrec_gain - 0.04) < 1e-7 and abs(cfg.omega_relative_limit - 0.01) < 1e-7
+    assert cfg.fftlen == 1024 and cfg.bits_per_sec == 9600.0
