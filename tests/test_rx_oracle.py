@@ -238,3 +238,32 @@ def test_hdlc_oracle_agrees_with_the_independent_deframer_on_random_streams():
         got = O.frames_payloads(O.HdlcDeframer(11, 64).work(bits, max_frames=512))
         want = synth.hdlc_deframe(bits, min_bytes=9, max_bytes=62)
         assert got == want, trial
+
+
+def test_xlat_indexing_against_numpy_convolution():
+    """History convention, decimation phase and rotator direction checked against an independent
+    formulation: out[j] = conv(x, ctaps)[j*D + ntaps-1] * exp(-j fwT0 D j), with x = history + new."""
+    rate, freq, D = 250e3, -25e3, 5
+    taps = O.firdes_low_pass(1.0, rate, 11e3, 1e3)
+    nt = len(taps)
+    rng = np.random.default_rng(9)
+    nout = 400
+    x = (rng.standard_normal(nt - 1 + nout * D) + 1j * rng.standard_normal(nt - 1 + nout * D)).astype(np.complex64)
+    f = O.FreqXlatingFir(D, taps, freq, rate)
+    y, fir = f.work(x, fir=True)
+    wf = float(np.float32(2 * np.pi * freq / rate))
+    # GNU Radio forms the angle as the float product i * fwT0 (one rounding per tap)
+    theta = (np.arange(nt, dtype=np.float32) * np.float32(wf)).astype(np.float64)
+    ctaps = taps.astype(np.float64) * np.exp(1j * theta)
+    assert np.abs(f.ctaps - ctaps).max() < 1e-7          # the band-pass taps GNU Radio composes
+    full = np.convolve(x.astype(np.complex128), ctaps)
+    want_fir = full[nt - 1:nt - 1 + nout * D:D]
+    assert np.abs(fir - want_fir).max() < 1e-5
+    want = want_fir * np.exp(-1j * wf * D * np.arange(nout))
+    assert np.abs(y - want).max() < 1e-4
+    # a tone at the channel centre lands at DC with the filter's unit gain
+    t = np.arange(len(x))
+    tone = np.exp(2j * np.pi * freq * t / rate).astype(np.complex64)
+    z = O.FreqXlatingFir(D, taps, freq, rate).work(tone)
+    assert np.abs(np.abs(z[200:]) - 1.0).max() < 1e-3
+    assert np.abs(np.angle(z[201:] * np.conj(z[200:-1]))).max() < 1e-3
