@@ -57,9 +57,10 @@ def max_over_ranks(value, device=None):
 
 def bind_to_gpu_numa_node(device_index):
     """Pin the calling process to the CPUs local to `device_index` (NVML's ideal affinity), so
-    that the pinned staging buffers it allocates next live on the GPU's own NUMA node: with
-    eight ranks streaming 6 GB per step each, buffers on the wrong socket halve the host-to-device
-    rate.  Returns the CPU set, or None when NVML is unavailable (nothing is changed then)."""
+    that the pinned staging buffers it allocates next live on the GPU's own NUMA node (each rank
+    streams 6 GB per step through them).  On the single-NUMA-node boxes this was measured on it
+    changes nothing (8 GPUs: 448 k channels/s end to end with and without).  Returns the CPU set,
+    or None when NVML is unavailable (nothing is changed then)."""
     import os
     try:
         import pynvml
