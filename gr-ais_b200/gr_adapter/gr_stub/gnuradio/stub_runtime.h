@@ -15,6 +15,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -167,9 +168,11 @@ public:
         for (auto &v : ninput_items_required)
             v = noutput_items + (int)history() - 1;
     }
-    virtual int general_work(int noutput_items, gr_vector_int &ninput_items,
-                             gr_vector_const_void_star &input_items,
-                             gr_vector_void_star &output_items) = 0;
+    // not pure, as in GNU Radio (message-only blocks such as pdu_to_nmea do not override it)
+    virtual int general_work(int, gr_vector_int &, gr_vector_const_void_star &, gr_vector_void_star &)
+    {
+        throw std::runtime_error("block::general_work() not implemented");
+    }
 
     unsigned history() const { return d_history; }
     void set_history(unsigned h) { d_history = h; }
@@ -231,6 +234,7 @@ protected:
         : basic_block(name, in, out)
     {
     }
+    gr::thread::mutex d_setlock; // gr::block's own member (corr_est_cc_impl.cc:135,169 lock it)
 
 private:
     unsigned d_history = 1;

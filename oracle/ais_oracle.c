@@ -1,6 +1,7 @@
 /*
  * ais_oracle.c -- CPU restatement of the gr-ais IQ-demod hot path (see ais_oracle.h).
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (no reference vectors exist).
+ * TEST INFRASTRUCTURE ONLY.  Parity status: see the header (the [R] blocks are pinned to the
+ * reference sources compiled under oracle/ref_build; the [G] kernels are restated).
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off -mfma -fopenmp (oracle/Makefile).
  * -mfma only makes fmaf() a single instruction; -ffp-contract=off guarantees no
@@ -374,8 +375,6 @@ static int fft_filter_fftsize(int ntaps)
     return 2 * p;
 }
 
-static int fft_filter_nsamples(int ntaps) { return fft_filter_fftsize(ntaps) - ntaps + 1; }
-
 static void make_twiddles(int n, float *w)
 {
     for (int k = 0; k < n / 2; k++) {
@@ -450,32 +449,80 @@ int ao_ifft_dit_inplace(float *x, int n)
     return 0;
 }
 
-/* fft_filter_ccc::set_taps [G]: taps scaled by 1/fftsize, zero padded, transformed once.
- * The tail keeps its contents and is resized to ntaps-1 (std::vector::resize). */
-static void corr_set_taps(ao_corr_est *c, int old_L)
+/* kernel::fft_filter_ccc [G].  set_taps: taps scaled by 1/fftsize, zero padded, transformed
+ * once; the tail keeps its contents and is resized to ntaps-1 (std::vector::resize). */
+void ao_fftfilt_init(ao_fftfilt *f) { memset(f, 0, sizeof(*f)); }
+
+int ao_fftfilt_set_taps(ao_fftfilt *f, const float *taps, int ntaps)
 {
-    int F = fft_filter_fftsize(c->L);
-    c->fftsize = F;
-    c->nsamples = F - c->L + 1;
-    free(c->H);
-    free(c->tw);
-    c->H = (float *)calloc((size_t)F * 2, sizeof(float));
-    c->tw = (float *)malloc(sizeof(float) * F);
-    make_twiddles(F, c->tw);
+    int old = f->ntaps;
+    int F = fft_filter_fftsize(ntaps);
+    f->ntaps = ntaps;
+    f->fftsize = F;
+    f->nsamples = F - ntaps + 1;
+    free(f->H);
+    free(f->tw);
+    f->H = (float *)calloc((size_t)F * 2, sizeof(float));
+    f->tw = (float *)malloc(sizeof(float) * F);
+    make_twiddles(F, f->tw);
     float scale = 1.0f / (float)F;
-    for (int k = 0; k < c->L; k++) {
-        c->H[2 * k] = c->taps[2 * k] * scale;
-        c->H[2 * k + 1] = c->taps[2 * k + 1] * scale;
+    for (int k = 0; k < ntaps; k++) {
+        f->H[2 * k] = taps[2 * k] * scale;
+        f->H[2 * k + 1] = taps[2 * k + 1] * scale;
     }
-    fft_dif(c->H, F, c->tw);
-    float *nt = (float *)calloc((size_t)(c->L > 1 ? c->L - 1 : 1) * 2, sizeof(float));
-    if (c->tail) {
-        int keep = (old_L < c->L ? old_L : c->L) - 1;
+    fft_dif(f->H, F, f->tw);
+    float *nt = (float *)calloc((size_t)(ntaps > 1 ? ntaps - 1 : 1) * 2, sizeof(float));
+    if (f->tail) {
+        int keep = (old < ntaps ? old : ntaps) - 1;
         if (keep > 0)
-            memcpy(nt, c->tail, sizeof(float) * 2 * (size_t)keep);
-        free(c->tail);
+            memcpy(nt, f->tail, sizeof(float) * 2 * (size_t)keep);
+        free(f->tail);
     }
-    c->tail = nt;
+    f->tail = nt;
+    return f->nsamples;
+}
+
+/* filter(): blocks of nsamples items, zero padded to fftsize, forward FFT, multiplied by the
+ * transformed taps (volk multiply order), inverse FFT, the first ntaps-1 outputs get the
+ * previous block's tail added, the last ntaps-1 become the new tail.  Canonical transforms:
+ * the radix-2 DIF / DIT pair above. */
+int ao_fftfilt_filter(ao_fftfilt *f, int nitems, const float *x, float *out)
+{
+    int L = f->ntaps, F = f->fftsize, ns = f->nsamples;
+    float *buf = (float *)malloc(sizeof(float) * 2 * (size_t)F);
+    for (int i0 = 0; i0 < nitems; i0 += ns) {
+        memcpy(buf, x + 2 * (size_t)i0, sizeof(float) * 2 * (size_t)ns);
+        memset(buf + 2 * (size_t)ns, 0, sizeof(float) * 2 * (size_t)(F - ns));
+        fft_dif(buf, F, f->tw);
+        for (int p = 0; p < F; p++)
+            cmul(buf[2 * p], buf[2 * p + 1], f->H[2 * p], f->H[2 * p + 1], &buf[2 * p], &buf[2 * p + 1]);
+        ifft_dit(buf, F, f->tw);
+        for (int j = 0; j < L - 1; j++) {
+            buf[2 * j] += f->tail[2 * j];
+            buf[2 * j + 1] += f->tail[2 * j + 1];
+        }
+        memcpy(out + 2 * (size_t)i0, buf, sizeof(float) * 2 * (size_t)ns);
+        memcpy(f->tail, buf + 2 * (size_t)ns, sizeof(float) * 2 * (size_t)(L - 1));
+    }
+    free(buf);
+    return nitems;
+}
+
+void ao_fftfilt_free(ao_fftfilt *f)
+{
+    free(f->H);
+    free(f->tail);
+    free(f->tw);
+    memset(f, 0, sizeof(*f));
+}
+
+/* volk_32fc_magnitude_squared_32f [G] (corr_est_cc_impl.cc:191) */
+void ao_mag_squared(const float *in, int n, float *out)
+{
+    for (int i = 0; i < n; i++) {
+        float re = in[2 * i], im = in[2 * i + 1];
+        out[i] = re * re + im * im;
+    }
 }
 
 /* lib/corr_est_cc_impl.cc:48-117 */
@@ -499,7 +546,8 @@ int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, uns
         corr += re * re + im * im;
     }
     c->thresh = threshold * corr * corr;
-    corr_set_taps(c, L);
+    ao_fftfilt_init(&c->f);
+    ao_fftfilt_set_taps(&c->f, c->taps, L); /* :77 (the kernel's ctor) and :84 */
     return 0;
 }
 
@@ -507,22 +555,19 @@ int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, uns
  * reverse) and d_thresh is NOT recomputed. */
 void ao_corr_est_set_symbols(ao_corr_est *c, const float *symbols, int L)
 {
-    int old_L = c->L;
     free(c->taps);
     c->taps = (float *)malloc(sizeof(float) * 2 * (size_t)L);
     memcpy(c->taps, symbols, sizeof(float) * 2 * (size_t)L);
     c->L = L;
-    corr_set_taps(c, old_L);
+    ao_fftfilt_set_taps(&c->f, c->taps, L);
     c->mark_delay = c->mark_delay >= (unsigned)L ? (unsigned)L - 1 : c->mark_delay;
 }
 
 void ao_corr_est_free(ao_corr_est *c)
 {
     free(c->taps);
-    free(c->H);
-    free(c->tail);
-    free(c->tw);
-    c->taps = c->H = c->tail = c->tw = 0;
+    ao_fftfilt_free(&c->f);
+    c->taps = 0;
 }
 
 /* float64 direct-form truth of the same filter on a fresh block: like fft_filter_ccc, it is
@@ -559,43 +604,21 @@ static void push_tag(ao_tag *tags, int max_tags, int *ntags, uint64_t off, int k
 }
 
 /* lib/corr_est_cc_impl.cc:164-279.  The correlation filter (:188) is GNU Radio's
- * kernel::fft_filter_ccc [G]: blocks of nsamples items, zero padded to fftsize, forward FFT,
- * multiplied by the transformed taps (volk multiply order), inverse FFT, the first ntaps-1
- * outputs get the previous block's tail added, the last ntaps-1 become the new tail.
- * Canonical transforms: the radix-2 DIF / DIT pair above. */
+ * kernel::fft_filter_ccc [G] (ao_fftfilt_filter above). */
 int ao_corr_est_work(ao_corr_est *c, int n, const float *in, uint64_t nitems_written,
                      float *out0, float *corr, float *mag, int two_ports, ao_tag *tags,
                      int max_tags, int *ntags)
 {
-    int L = c->L, F = c->fftsize, ns = c->nsamples;
+    int L = c->L, ns = c->f.nsamples;
     *ntags = 0;
     if (n % ns)
         return -1; /* set_output_multiple(nsamples) */
     float *corr_buf = corr ? corr : (float *)malloc(sizeof(float) * 2 * (size_t)(n > 0 ? n : 1));
     float *mag_buf = mag ? mag : (float *)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
     if (out0)
-        memcpy(out0, in, sizeof(float) * 2 * (size_t)n); /* :184 */
-    const float *x = in + 2 * (size_t)L;                 /* &in[hist_len] (:188) */
-    float *buf = (float *)malloc(sizeof(float) * 2 * (size_t)F);
-    for (int i0 = 0; i0 < n; i0 += ns) {
-        memcpy(buf, x + 2 * (size_t)i0, sizeof(float) * 2 * (size_t)ns);
-        memset(buf + 2 * (size_t)ns, 0, sizeof(float) * 2 * (size_t)(F - ns));
-        fft_dif(buf, F, c->tw);
-        for (int p = 0; p < F; p++)
-            cmul(buf[2 * p], buf[2 * p + 1], c->H[2 * p], c->H[2 * p + 1], &buf[2 * p], &buf[2 * p + 1]);
-        ifft_dit(buf, F, c->tw);
-        for (int j = 0; j < L - 1; j++) {
-            buf[2 * j] += c->tail[2 * j];
-            buf[2 * j + 1] += c->tail[2 * j + 1];
-        }
-        memcpy(corr_buf + 2 * (size_t)i0, buf, sizeof(float) * 2 * (size_t)ns);
-        memcpy(c->tail, buf + 2 * (size_t)ns, sizeof(float) * 2 * (size_t)(L - 1));
-    }
-    free(buf);
-    for (int i = 0; i < n; i++) {
-        float re = corr_buf[2 * i], im = corr_buf[2 * i + 1];
-        mag_buf[i] = re * re + im * im; /* volk_32fc_magnitude_squared_32f (:191) */
-    }
+        memcpy(out0, in, sizeof(float) * 2 * (size_t)n);           /* :184 */
+    ao_fftfilt_filter(&c->f, n, in + 2 * (size_t)L, corr_buf);      /* &in[hist_len] (:188) */
+    ao_mag_squared(corr_buf, n, mag_buf);                          /* :191 */
     int isps = (int)(c->sps + 0.5f);
     int i = 0;
     while (i < n) {
@@ -667,7 +690,7 @@ int ao_msk_forecast(const ao_msk *m, int noutput_items)
 /* mmse_fir_interpolator_cc::interpolate [G]: imu = rint(mu*128); 8-tap dot
  * product with the reversed table row.  Canonical summation: four two-term fmaf
  * partial sums p_j = in[j]*t[j] + in[j+4]*t[j+4], combined (p0+p1)+(p2+p3). */
-static int interp8(const float *s /* 8 complex */, float mu, float *vr, float *vi)
+int ao_mmse_interpolate(const float *s /* 8 complex */, float mu, float *vr, float *vi)
 {
     int imu = (int)rintf(mu * 128.0f);
     if (imu < 0 || imu > 128)
@@ -747,7 +770,7 @@ int ao_msk_general_work(ao_msk *m, int noutput_items, int ninput_items, const fl
             }
         }
         float vr, vi;
-        if (interp8(s8, m->mu, &vr, &vi) != 0) {
+        if (ao_mmse_interpolate(s8, m->mu, &vr, &vi) != 0) {
             free(tv);
             *consumed = iidx;
             return -1; /* mmse interpolator would throw */
@@ -838,12 +861,120 @@ void ao_invert(const uint8_t *in, int n, uint8_t *out)
         out[i] = (in[i] ^ 0x01) & 0x01;
 }
 
+/* ------------------------------------------- block provider: the oracle's own */
+
+static void *ob_corr_new(const float *symbols, int L, float sps, unsigned mark_delay, float threshold)
+{
+    ao_corr_est *c = (ao_corr_est *)malloc(sizeof(*c));
+    if (c && ao_corr_est_init(c, symbols, L, sps, mark_delay, threshold)) {
+        free(c);
+        c = 0;
+    }
+    return c;
+}
+static void ob_corr_delete(void *h)
+{
+    if (h) {
+        ao_corr_est_free((ao_corr_est *)h);
+        free(h);
+    }
+}
+static int ob_corr_output_multiple(void *h) { return ((ao_corr_est *)h)->f.nsamples; }
+static int ob_corr_set_symbols(void *h, const float *symbols, int L)
+{
+    ao_corr_est_set_symbols((ao_corr_est *)h, symbols, L);
+    return 0;
+}
+static int ob_corr_work(void *h, int n, const float *in, uint64_t nitems_written, float *out0,
+                        float *corr, float *mag, int two_ports, ao_tag *tags, int max_tags, int *ntags)
+{
+    return ao_corr_est_work((ao_corr_est *)h, n, in, nitems_written, out0, corr, mag, two_ports, tags,
+                            max_tags, ntags);
+}
+static void *ob_msk_new(float sps, float gain, float limit, int osps, int *status)
+{
+    ao_msk *m = (ao_msk *)malloc(sizeof(*m));
+    int rc = m ? ao_msk_init(m, sps, gain, limit, osps) : -1;
+    if (status)
+        *status = rc;
+    if (rc) {
+        free(m);
+        m = 0;
+    }
+    return m;
+}
+static void ob_free(void *h) { free(h); }
+static float ob_msk_get_sps(void *h) { return ((ao_msk *)h)->sps; }
+static int ob_msk_general_work(void *h, int noutput_items, int ninput_items, const float *in,
+                               uint64_t nitems_read, const ao_tag *tags, int ntags, float *out,
+                               float *out_err, float *out_mu, int *consumed)
+{
+    return ao_msk_general_work((ao_msk *)h, noutput_items, ninput_items, in, nitems_read, tags, ntags,
+                               out, out_err, out_mu, consumed);
+}
+static void *ob_freqest_new(float sample_rate, int data_rate, int fftlen)
+{
+    ao_freqest *f = (ao_freqest *)malloc(sizeof(*f));
+    if (f)
+        ao_freqest_init(f, sample_rate, data_rate, fftlen);
+    return f;
+}
+static int ob_freqest_work(void *h, const float *spec, int nvec, float *out)
+{
+    return ao_freqest_work((const ao_freqest *)h, spec, nvec, out, 0);
+}
+
+const ao_blocks *ao_blocks_oracle(void)
+{
+    static const ao_blocks b = { "oracle",
+                                 ob_corr_new,
+                                 ob_corr_delete,
+                                 ob_corr_output_multiple,
+                                 ob_corr_set_symbols,
+                                 ob_corr_work,
+                                 ob_msk_new,
+                                 ob_free,
+                                 ob_msk_get_sps,
+                                 ob_msk_general_work,
+                                 ob_freqest_new,
+                                 ob_free,
+                                 ob_freqest_work,
+                                 ao_invert };
+    return &b;
+}
+
 /* ----------------------------------------------------------- the chain */
 
 int ao_default_corr_chunk(int L)
 {
-    int ns = fft_filter_nsamples(L);
+    int ns = fft_filter_fftsize(L) - L + 1;
     return (24576 / ns) * ns; /* set_output_multiple(nsamples) under set_max_noutput_items(24576) */
+}
+
+/* square -> stream_to_vector -> fft_vcc(shift) -> freqest -> repeat -> FM -> mix over nvec
+ * whole vectors (python/gmsk_sync.py:22-37); freqest sees them in ONE work() call */
+static void freq_sync(const ao_blocks *blk, void *fe, const ao_chain_cfg *cfg, const float *x, int n1,
+                      float *phase, float *mixed, float *fhat_out)
+{
+    int fftlen = cfg->fftlen, nvec = n1 / fftlen;
+    float *sq = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
+    float *sp = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
+    float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen * (size_t)(nvec + 1));
+    float *fh = (float *)malloc(sizeof(float) * (size_t)(nvec + 1));
+    for (int b = 0; b < nvec; b++) {
+        ao_square(x + 2 * (size_t)b * fftlen, sq, fftlen);
+        ao_fft_forward(sq, sp, fftlen);
+        ao_fft_shift(sp, spec + 2 * (size_t)b * fftlen, fftlen);
+    }
+    blk->freqest_work(fe, spec, nvec, fh);
+    if (fhat_out)
+        memcpy(fhat_out, fh, sizeof(float) * (size_t)nvec);
+    float sens = (float)(-1.0 / ((double)cfg->sample_rate / (2 * M_PI))); /* gmsk_sync.py:27 */
+    ao_nco_mix(phase, sens, fh, fftlen, x, n1, mixed);
+    free(sq);
+    free(sp);
+    free(spec);
+    free(fh);
 }
 
 /* python/ais_demod.py:34-56 + python/gmsk_sync.py:22-37 over one record, every
@@ -852,9 +983,11 @@ int ao_default_corr_chunk(int L)
  * of nsamples; the remainder shorter than nsamples is left unprocessed, as the
  * scheduler would); msk_timing_recovery sees corr_est's whole output in one
  * general_work() call with unbounded noutput_items. */
-int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x, int n,
-                   ao_chain_out *o)
+int ao_demod_chain_with(const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols, int L,
+                        const float *x, int n, ao_chain_out *o)
 {
+    if (!blk)
+        blk = ao_blocks_oracle();
     int rc = 0;
     int fftlen = cfg->fftlen;
     int n1 = (cfg->stages & AO_STAGE_FREQSYNC) ? (n / fftlen) * fftlen : n;
@@ -867,28 +1000,10 @@ int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const f
         return -1;
 
     if (cfg->stages & AO_STAGE_FREQSYNC) {
-        int nvec = n1 / fftlen;
-        float *sq = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
-        float *sp = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
-        float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen * (size_t)(nvec + 1));
-        float *fh = (float *)malloc(sizeof(float) * (size_t)(nvec + 1));
-        for (int b = 0; b < nvec; b++) {
-            ao_square(x + 2 * (size_t)b * fftlen, sq, fftlen);
-            ao_fft_forward(sq, sp, fftlen);
-            ao_fft_shift(sp, spec + 2 * (size_t)b * fftlen, fftlen);
-        }
-        ao_freqest fe;
-        ao_freqest_init(&fe, cfg->sample_rate, cfg->data_rate, fftlen);
-        ao_freqest_work(&fe, spec, nvec, fh, 0);
-        if (o->fhat)
-            memcpy(o->fhat, fh, sizeof(float) * (size_t)nvec);
+        void *fe = blk->freqest_new(cfg->sample_rate, cfg->data_rate, fftlen);
         float phase = 0.0f;
-        float sens = (float)(-1.0 / ((double)cfg->sample_rate / (2 * M_PI))); /* gmsk_sync.py:27 */
-        ao_nco_mix(&phase, sens, fh, fftlen, x, n1, mixed);
-        free(sq);
-        free(sp);
-        free(spec);
-        free(fh);
+        freq_sync(blk, fe, cfg, x, n1, &phase, mixed, o->fhat);
+        blk->freqest_delete(fe);
     } else {
         memcpy(mixed, x, sizeof(float) * 2 * (size_t)n1);
     }
@@ -904,32 +1019,32 @@ int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const f
     if (o->agc)
         memcpy(o->agc, agc, sizeof(float) * 2 * (size_t)n1);
 
-    ao_corr_est ce;
-    ao_corr_est_init(&ce, symbols, L, cfg->sps, cfg->mark_delay, cfg->threshold);
+    void *ce = blk->corr_new(symbols, L, cfg->sps, cfg->mark_delay, cfg->threshold);
+    int ns = blk->corr_output_multiple(ce);
     int chunk = cfg->corr_chunk > 0 ? cfg->corr_chunk : ao_default_corr_chunk(L);
-    chunk = (chunk / ce.nsamples) * ce.nsamples;
+    chunk = (chunk / ns) * ns;
     if (chunk <= 0)
-        chunk = ce.nsamples;
+        chunk = ns;
     float *out0 = (float *)malloc(sizeof(float) * 2 * (size_t)(n1 + 1));
     int n2 = 0;
     o->ntags = 0;
-    while (n1 - n2 >= ce.nsamples) {
+    while (n1 - n2 >= ns) {
         int nn = n1 - n2;
-        nn = nn > chunk ? chunk : (nn / ce.nsamples) * ce.nsamples;
+        nn = nn > chunk ? chunk : (nn / ns) * ns;
         int nt = 0;
-        ao_corr_est_work(&ce, nn, X + 2 * (size_t)n2, (uint64_t)n2, out0 + 2 * (size_t)n2,
-                         o->corr ? o->corr + 2 * (size_t)n2 : 0, o->mag ? o->mag + n2 : 0, 0,
-                         o->tags + (o->ntags < o->max_tags ? o->ntags : o->max_tags),
-                         o->max_tags - (o->ntags < o->max_tags ? o->ntags : o->max_tags), &nt);
+        blk->corr_work(ce, nn, X + 2 * (size_t)n2, (uint64_t)n2, out0 + 2 * (size_t)n2,
+                       o->corr ? o->corr + 2 * (size_t)n2 : 0, o->mag ? o->mag + n2 : 0, 0,
+                       o->tags + (o->ntags < o->max_tags ? o->ntags : o->max_tags),
+                       o->max_tags - (o->ntags < o->max_tags ? o->ntags : o->max_tags), &nt);
         o->ntags += nt;
         n2 += nn;
     }
-    ao_corr_est_free(&ce);
+    blk->corr_delete(ce);
     if (o->ntags > o->max_tags)
         rc = -3; /* tag buffer too small */
 
-    ao_msk mk;
-    int mrc = ao_msk_init(&mk, cfg->sps, cfg->gain, cfg->limit, cfg->osps);
+    int mrc = 0;
+    void *mk = blk->msk_new(cfg->sps, cfg->gain, cfg->limit, cfg->osps, &mrc);
     if (mrc)
         rc = mrc;
     int maxsym = o->max_bits;
@@ -941,18 +1056,19 @@ int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const f
     int consumed = 0, k = 0;
     if (!mrc) {
         int usable = o->ntags < o->max_tags ? o->ntags : o->max_tags;
-        k = ao_msk_general_work(&mk, maxsym, n2, out0, 0, o->tags, usable, sym, err, mu, &consumed);
+        k = blk->msk_general_work(mk, maxsym, n2, out0, 0, o->tags, usable, sym, err, mu, &consumed);
         if (k < 0) {
             rc = -4;
             k = 0;
         }
+        blk->msk_delete(mk);
     }
     float prev[2] = { 0, 0 };
     uint8_t dprev = 0;
     ao_quad_demod(prev, sym, k, (float)(M_PI / 2), soft);
     ao_binary_slicer(soft, k, b0);
     ao_diff_decoder(&dprev, b0, k, 2, b1);
-    ao_invert(b1, k, o->bits);
+    blk->invert_work(b1, k, o->bits);
     o->nbits = k;
     o->n1 = n1;
     o->n2 = n2;
@@ -978,9 +1094,16 @@ int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const f
     return rc;
 }
 
-int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x,
-                         int channels, int n, uint8_t *bits, int max_bits, int *nbits,
-                         ao_tag *tags, int max_tags, int *ntags, int nthreads)
+int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x, int n,
+                   ao_chain_out *o)
+{
+    return ao_demod_chain_with(0, cfg, symbols, L, x, n, o);
+}
+
+int ao_demod_chain_batch_with(const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols,
+                              int L, const float *x, int channels, int n, uint8_t *bits,
+                              int max_bits, int *nbits, ao_tag *tags, int max_tags, int *ntags,
+                              int nthreads)
 {
     int status = 0;
 #ifdef _OPENMP
@@ -997,7 +1120,7 @@ int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, c
         o.max_bits = max_bits;
         o.tags = tags + (size_t)c * max_tags;
         o.max_tags = max_tags;
-        int rc = ao_demod_chain(cfg, symbols, L, x + 2 * (size_t)c * n, n, &o);
+        int rc = ao_demod_chain_with(blk, cfg, symbols, L, x + 2 * (size_t)c * n, n, &o);
         nbits[c] = o.nbits;
         ntags[c] = o.ntags;
         if (rc) {
@@ -1009,36 +1132,59 @@ int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, c
     return status;
 }
 
+int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x,
+                         int channels, int n, uint8_t *bits, int max_bits, int *nbits,
+                         ao_tag *tags, int max_tags, int *ntags, int nthreads)
+{
+    return ao_demod_chain_batch_with(0, cfg, symbols, L, x, channels, n, bits, max_bits, nbits, tags,
+                                     max_tags, ntags, nthreads);
+}
+
 /* ----------------------------------------------------- the chain as a stream */
 
-int ao_stream_init(ao_stream *s, const ao_chain_cfg *cfg, const float *symbols, int L)
+int ao_stream_init(ao_stream *s, const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols,
+                   int L)
 {
     memset(s, 0, sizeof(*s));
+    if (!blk)
+        blk = ao_blocks_oracle();
+    s->blk = blk;
     s->cfg = *cfg;
     s->L = L;
-    if (ao_corr_est_init(&s->ce, symbols, L, cfg->sps, cfg->mark_delay, cfg->threshold))
+    s->ce = blk->corr_new(symbols, L, cfg->sps, cfg->mark_delay, cfg->threshold);
+    if (!s->ce)
         return -1;
-    int rc = ao_msk_init(&s->mk, cfg->sps, cfg->gain, cfg->limit, cfg->osps);
-    if (rc)
+    s->ns = blk->corr_output_multiple(s->ce);
+    int rc = 0;
+    s->mk = blk->msk_new(cfg->sps, cfg->gain, cfg->limit, cfg->osps, &rc);
+    if (rc) {
+        blk->corr_delete(s->ce);
+        s->ce = 0;
         return rc;
-    ao_freqest_init(&s->fe, cfg->sample_rate, cfg->data_rate, cfg->fftlen);
+    }
+    s->fe = blk->freqest_new(cfg->sample_rate, cfg->data_rate, cfg->fftlen);
     s->xcarry = (float *)calloc((size_t)cfg->fftlen * 2, sizeof(float));
     s->agc_hist = (float *)calloc((size_t)(cfg->agc_nsamples > 1 ? cfg->agc_nsamples - 1 : 1) * 2, sizeof(float));
-    s->acarry = (float *)calloc((size_t)(L + s->ce.nsamples) * 2, sizeof(float)); /* L zeros of history */
+    s->acarry = (float *)calloc((size_t)(L + s->ns) * 2, sizeof(float)); /* L zeros of history */
     s->ocarry = (float *)calloc(64 * 2, sizeof(float));
     s->captags = 64;
     s->tags = (ao_tag *)calloc((size_t)s->captags, sizeof(ao_tag));
     return 0;
 }
 
-ao_stream *ao_stream_new(const ao_chain_cfg *cfg, const float *symbols, int L)
+ao_stream *ao_stream_new_with(const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols, int L)
 {
     ao_stream *s = (ao_stream *)malloc(sizeof(ao_stream));
-    if (s && ao_stream_init(s, cfg, symbols, L)) {
+    if (s && ao_stream_init(s, blk, cfg, symbols, L)) {
         free(s);
         s = 0;
     }
     return s;
+}
+
+ao_stream *ao_stream_new(const ao_chain_cfg *cfg, const float *symbols, int L)
+{
+    return ao_stream_new_with(0, cfg, symbols, L);
 }
 
 void ao_stream_delete(ao_stream *s)
@@ -1051,7 +1197,14 @@ void ao_stream_delete(ao_stream *s)
 
 void ao_stream_free(ao_stream *s)
 {
-    ao_corr_est_free(&s->ce);
+    if (s->blk) {
+        if (s->ce)
+            s->blk->corr_delete(s->ce);
+        if (s->mk)
+            s->blk->msk_delete(s->mk);
+        if (s->fe)
+            s->blk->freqest_delete(s->fe);
+    }
     free(s->xcarry);
     free(s->agc_hist);
     free(s->acarry);
@@ -1065,7 +1218,8 @@ int ao_stream_set_symbols(ao_stream *s, const float *symbols, int L)
 {
     if (L != s->L)
         return -1;
-    ao_corr_est_set_symbols(&s->ce, symbols, L);
+    s->blk->corr_set_symbols(s->ce, symbols, L);
+    s->ns = s->blk->corr_output_multiple(s->ce);
     return 0;
 }
 
@@ -1073,7 +1227,8 @@ int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_b
                    ao_tag *tags_out, int max_tags, int *ntags_out)
 {
     const ao_chain_cfg *cfg = &s->cfg;
-    const int L = s->L, fftlen = cfg->fftlen, W = cfg->agc_nsamples, ns = s->ce.nsamples;
+    const ao_blocks *blk = s->blk;
+    const int L = s->L, fftlen = cfg->fftlen, W = cfg->agc_nsamples, ns = s->ns;
     int rc = 0;
     *nbits = 0;
     *ntags_out = 0;
@@ -1084,27 +1239,10 @@ int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_b
     memcpy(xin + 2 * (size_t)s->nxcarry, x, sizeof(float) * 2 * (size_t)n);
     int n1 = (cfg->stages & AO_STAGE_FREQSYNC) ? (navail / fftlen) * fftlen : navail;
     float *mixed = (float *)malloc(sizeof(float) * 2 * (size_t)(n1 + 1));
-    if (cfg->stages & AO_STAGE_FREQSYNC) {
-        int nvec = n1 / fftlen;
-        float *sq = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
-        float *sp = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen);
-        float *spec = (float *)malloc(sizeof(float) * 2 * (size_t)fftlen * (size_t)(nvec + 1));
-        float *fh = (float *)malloc(sizeof(float) * (size_t)(nvec + 1));
-        for (int b = 0; b < nvec; b++) {
-            ao_square(xin + 2 * (size_t)b * fftlen, sq, fftlen);
-            ao_fft_forward(sq, sp, fftlen);
-            ao_fft_shift(sp, spec + 2 * (size_t)b * fftlen, fftlen);
-        }
-        ao_freqest_work(&s->fe, spec, nvec, fh, 0); /* one work() call: maxpos starts at 0 */
-        float sens = (float)(-1.0 / ((double)cfg->sample_rate / (2 * M_PI)));
-        ao_nco_mix(&s->nco_phase, sens, fh, fftlen, xin, n1, mixed);
-        free(sq);
-        free(sp);
-        free(spec);
-        free(fh);
-    } else {
+    if (cfg->stages & AO_STAGE_FREQSYNC)
+        freq_sync(blk, s->fe, cfg, xin, n1, &s->nco_phase, mixed, 0); /* one work(): maxpos starts at 0 */
+    else
         memcpy(mixed, xin, sizeof(float) * 2 * (size_t)n1);
-    }
     s->nxcarry = navail - n1;
     memcpy(s->xcarry, xin + 2 * (size_t)n1, sizeof(float) * 2 * (size_t)s->nxcarry);
     free(xin);
@@ -1140,9 +1278,9 @@ int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_b
             s->captags = s->ntags + 8 * (nn / 5 + 2) + 64;
             s->tags = (ao_tag *)realloc(s->tags, sizeof(ao_tag) * (size_t)s->captags);
         }
-        ao_corr_est_work(&s->ce, nn, s->acarry + 2 * (size_t)done, s->written,
-                         s->ocarry + 2 * (size_t)s->nocarry, 0, 0, 0, s->tags + s->ntags,
-                         s->captags - s->ntags, &nt);
+        blk->corr_work(s->ce, nn, s->acarry + 2 * (size_t)done, s->written,
+                       s->ocarry + 2 * (size_t)s->nocarry, 0, 0, 0, s->tags + s->ntags,
+                       s->captags - s->ntags, &nt);
         for (int k = 0; k < nt; k++) { /* this call's tags for the caller */
             if (ntag_new < max_tags)
                 tags_out[ntag_new] = s->tags[s->ntags + k];
@@ -1165,12 +1303,12 @@ int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_b
     float *soft = (float *)malloc(sizeof(float) * (size_t)(maxsym + 1));
     uint8_t *b0 = (uint8_t *)malloc((size_t)maxsym + 1), *b1 = (uint8_t *)malloc((size_t)maxsym + 1);
     int consumed = 0;
-    int k = ao_msk_general_work(&s->mk, maxsym, s->nocarry, s->ocarry, s->read, s->tags, s->ntags, sym,
-                                0, 0, &consumed);
+    int k = blk->msk_general_work(s->mk, maxsym, s->nocarry, s->ocarry, s->read, s->tags, s->ntags, sym,
+                                  0, 0, &consumed);
     if (k < 0) {
         rc = -4;
         k = 0;
-    } else if (k >= maxsym && consumed < (int)((double)s->nocarry - 3.0 * (double)s->mk.sps)) {
+    } else if (k >= maxsym && consumed < (int)((double)s->nocarry - 3.0 * (double)blk->msk_get_sps(s->mk))) {
         rc = -7; /* output row too small */
     }
     memmove(s->ocarry, s->ocarry + 2 * (size_t)consumed, sizeof(float) * 2 * (size_t)(s->nocarry - consumed));
@@ -1185,7 +1323,7 @@ int ao_stream_work(ao_stream *s, const float *x, int n, uint8_t *bits, int max_b
     ao_quad_demod(s->qprev, sym, k, (float)(M_PI / 2), soft);
     ao_binary_slicer(soft, k, b0);
     ao_diff_decoder(&s->dprev, b0, k, 2, b1);
-    ao_invert(b1, k, bits);
+    blk->invert_work(b1, k, bits);
     *nbits = k;
     free(sym);
     free(soft);

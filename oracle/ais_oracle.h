@@ -6,18 +6,22 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs use it, and only as the checker / the CPU arm.
  *
- * PARITY UNPINNED: the reference (bistromath/gr-ais @ 2162103) ships no tests,
- * fixtures or golden vectors (lib/qa_ais.cc:30-36 is an empty suite) and cannot
- * be built here (every hot-path source includes GNU Radio 3.8 / VOLK headers,
- * which are absent).  This file restates
- *   [R] the gr-ais C++ it can read:  lib/corr_est_cc_impl.cc:48-117,164-279,
+ * PARITY STATUS.  The reference (bistromath/gr-ais @ 2162103) ships no tests,
+ * fixtures or golden vectors (lib/qa_ais.cc:30-36 is an empty suite).  This file restates
+ *   [R] the gr-ais C++:  lib/corr_est_cc_impl.cc:48-117,164-279,
  *       lib/msk_timing_recovery_cc_impl.cc:45-105,107-206,
  *       lib/freqest_impl.cc:41-48,57-88, lib/invert_impl.cc:54-68,
+ *       lib/pdu_to_nmea_impl.cc:63-131,
  *       wiring python/ais_demod.py:28-56, python/gmsk_sync.py:22-37;
- *   [G] the GNU Radio 3.8 blocks between them, from their published
- *       algorithms.
- * It is pinned by first-principles known-answer tests (tests/test_oracle_*.py)
- * and float64 truth versions of each stage, not by reference vectors.
+ *   [G] the GNU Radio 3.8 / VOLK kernels those sources call and the stock blocks between
+ *       them, from their published algorithms -- GNU Radio itself
+ *       is not installed here.
+ * The [R] part is PINNED TO THE REFERENCE'S OWN CODE: oracle/ref_build compiles the five
+ * reference sources unmodified (against a stub of the GNU Radio runtime whose [G] kernels
+ * call the restatements below) into oracle/_ref/libais_ref.so, and tests/test_ref_pin.py
+ * asserts block by block, and over the whole chain, that it and this file agree bit for
+ * bit.  The [G] part stays unpinned against a real GNU Radio (no vectors exist): it is
+ * held by first-principles known-answer tests and float64 truth versions of each stage.
  *
  * Canonical arithmetic (DESIGN.md "Canonical arithmetic"): IEEE-754 binary32,
  * round-to-nearest-even, no implicit contraction (-ffp-contract=off); fused
@@ -87,6 +91,26 @@ void ao_nco_mix(float *phase, float sensitivity, const float *freq, int rep, con
 /* in holds n + nsamples - 1 items (history first), out n items. */
 void ao_agc_work(const float *in, int n, int nsamples, float reference, float *out);
 
+/* ---- filter::kernel::fft_filter_ccc [G] (the kernel behind corr_est_cc_impl.cc:77,84,188) ---- */
+typedef struct ao_fftfilt {
+    int ntaps;
+    int fftsize;  /* 2 * 2^ceil(log2 ntaps) */
+    int nsamples; /* fftsize - ntaps + 1: items per block = what set_taps() returns */
+    float *H;     /* [fftsize] complex: transformed taps/fftsize, bit-reversed order */
+    float *tail;  /* [ntaps-1] complex overlap-add tail, zero at construction, kept across calls */
+    float *tw;    /* [fftsize/2] complex twiddles */
+} ao_fftfilt;
+void ao_fftfilt_init(ao_fftfilt *f);                                  /* empty kernel */
+int ao_fftfilt_set_taps(ao_fftfilt *f, const float *taps, int ntaps); /* returns nsamples */
+/* nitems must be a multiple of nsamples (the caller's output multiple); returns nitems */
+int ao_fftfilt_filter(ao_fftfilt *f, int nitems, const float *in, float *out);
+void ao_fftfilt_free(ao_fftfilt *f);
+/* volk_32fc_magnitude_squared_32f [G] */
+void ao_mag_squared(const float *in, int n, float *out);
+/* mmse_fir_interpolator_cc::interpolate [G] on in[0..7]; -1 when rint(mu*128) is outside
+ * [0,128] (GNU Radio throws std::runtime_error) */
+int ao_mmse_interpolate(const float *in8, float mu, float *vr, float *vi);
+
 /* ---- A1-A4: corr_est_cc ---- */
 typedef struct ao_corr_est {
     float *taps; /* [L] complex: ctor stores reverse(conj(symbols)); set_symbols stores verbatim */
@@ -94,12 +118,7 @@ typedef struct ao_corr_est {
     float sps;
     unsigned mark_delay;
     float thresh;
-    int nsamples; /* fft_filter block size = output multiple */
-    /* kernel::fft_filter_ccc state [G]: fftsize, transformed taps (bit-reversed order), tail */
-    int fftsize;
-    float *H;    /* [fftsize] complex */
-    float *tail; /* [L-1] complex, zero at construction */
-    float *tw;   /* [fftsize/2] complex twiddles */
+    ao_fftfilt f; /* d_filter; f.nsamples = the block's output multiple */
 } ao_corr_est;
 int ao_corr_est_init(ao_corr_est *c, const float *symbols, int L, float sps, unsigned mark_delay,
                      float threshold);
@@ -183,7 +202,40 @@ typedef struct ao_chain_out {
     int consumed; /* msk consume_each */
 } ao_chain_out;
 
+/* Who implements the gr-ais blocks [R] inside the chain.  ao_blocks_oracle() = the
+ * restatements in this file; oracle/_ref/libais_ref.so exports ref_blocks() = the reference's
+ * own classes (its lib/ sources compiled unmodified).  Everything between the blocks (the stock
+ * GNU Radio blocks [G] and the schedule) is shared, so the two chains differ exactly by
+ * "restated" against "the reference's code". */
+typedef struct ao_blocks {
+    const char *name;
+    void *(*corr_new)(const float *symbols, int L, float sps, unsigned mark_delay, float threshold);
+    void (*corr_delete)(void *h);
+    int (*corr_output_multiple)(void *h);
+    int (*corr_set_symbols)(void *h, const float *symbols, int L);
+    int (*corr_work)(void *h, int n, const float *in, uint64_t nitems_written, float *out0,
+                     float *corr, float *mag, int two_ports, ao_tag *tags, int max_tags, int *ntags);
+    void *(*msk_new)(float sps, float gain, float limit, int osps, int *status);
+    void (*msk_delete)(void *h);
+    float (*msk_get_sps)(void *h); /* d_sps = sps / 2 */
+    int (*msk_general_work)(void *h, int noutput_items, int ninput_items, const float *in,
+                            uint64_t nitems_read, const ao_tag *tags, int ntags, float *out,
+                            float *out_err, float *out_mu, int *consumed);
+    void *(*freqest_new)(float sample_rate, int data_rate, int fftlen);
+    void (*freqest_delete)(void *h);
+    int (*freqest_work)(void *h, const float *spec, int nvec, float *out);
+    void (*invert_work)(const uint8_t *in, int n, uint8_t *out);
+} ao_blocks;
+const ao_blocks *ao_blocks_oracle(void);
+
 int ao_default_corr_chunk(int L);
+/* ..._with: the same chain over another block provider (NULL = ao_blocks_oracle()) */
+int ao_demod_chain_with(const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols, int L,
+                        const float *x, int n, ao_chain_out *out);
+int ao_demod_chain_batch_with(const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols,
+                              int L, const float *x, int channels, int n, uint8_t *bits,
+                              int max_bits, int *nbits, ao_tag *tags, int max_tags, int *ntags,
+                              int nthreads);
 int ao_demod_chain(const ao_chain_cfg *cfg, const float *symbols, int L, const float *x, int n,
                    ao_chain_out *out);
 /* batch over channels with OpenMP; x is [C][n] complex, bits [C][max_bits], nbits [C],
@@ -199,9 +251,9 @@ int ao_demod_chain_batch(const ao_chain_cfg *cfg, const float *symbols, int L, c
  * corr_est has produced so far through one msk general_work(), then the bit tail. */
 typedef struct ao_stream {
     ao_chain_cfg cfg;
-    ao_corr_est ce;
-    ao_msk mk;
-    ao_freqest fe;
+    const ao_blocks *blk;
+    void *ce, *mk, *fe; /* block handles of the provider */
+    int ns;             /* corr_est output multiple */
     int L;
     float nco_phase;
     float *xcarry;   /* input items waiting for a whole FFT vector */
@@ -218,8 +270,9 @@ typedef struct ao_stream {
     float qprev[2];
     uint8_t dprev;
 } ao_stream;
-int ao_stream_init(ao_stream *s, const ao_chain_cfg *cfg, const float *symbols, int L);
+int ao_stream_init(ao_stream *s, const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols, int L);
 ao_stream *ao_stream_new(const ao_chain_cfg *cfg, const float *symbols, int L);
+ao_stream *ao_stream_new_with(const ao_blocks *blk, const ao_chain_cfg *cfg, const float *symbols, int L);
 void ao_stream_delete(ao_stream *s);
 void ao_stream_free(ao_stream *s);
 int ao_stream_set_symbols(ao_stream *s, const float *symbols, int L);

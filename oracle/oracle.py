@@ -24,11 +24,15 @@ class Tag(C.Structure):
                 ("value", C.c_double)]
 
 
+class FftFilt(C.Structure):
+    _fields_ = [("ntaps", C.c_int), ("fftsize", C.c_int), ("nsamples", C.c_int),
+                ("H", C.POINTER(C.c_float)), ("tail", C.POINTER(C.c_float)),
+                ("tw", C.POINTER(C.c_float))]
+
+
 class CorrEst(C.Structure):
     _fields_ = [("taps", C.POINTER(C.c_float)), ("L", C.c_int), ("sps", C.c_float),
-                ("mark_delay", C.c_uint), ("thresh", C.c_float), ("nsamples", C.c_int),
-                ("fftsize", C.c_int), ("H", C.POINTER(C.c_float)), ("tail", C.POINTER(C.c_float)),
-                ("tw", C.POINTER(C.c_float))]
+                ("mark_delay", C.c_uint), ("thresh", C.c_float), ("f", FftFilt)]
 
 
 class Msk(C.Structure):
@@ -273,7 +277,7 @@ class CorrEstBlock:
 
     @property
     def nsamples(self):
-        return self._c.nsamples
+        return self._c.f.nsamples
 
     @property
     def mark_delay(self):
@@ -306,11 +310,11 @@ class CorrEstBlock:
 
     @property
     def fftsize(self):
-        return self._c.fftsize
+        return self._c.f.fftsize
 
     def tail(self):
         n = max(self._c.L - 1, 0)
-        return np.ctypeslib.as_array(self._c.tail, shape=(2 * max(n, 1),)).copy().view(np.complex64)[:n]
+        return np.ctypeslib.as_array(self._c.f.tail, shape=(2 * max(n, 1),)).copy().view(np.complex64)[:n]
 
     def direct_f64(self, n, inbuf):
         """float64 direct-form correlation of the same call (truth for tests; ignores the tail)"""
@@ -407,8 +411,10 @@ def max_bits_for(n, sps=5.0, osps=1):
     return int(n / sps * osps * 1.05) + 64
 
 
-def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096):
-    """One record from fresh state.  Returns dict(bits, tags, [debug taps])."""
+def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096, blocks=None):
+    """One record from fresh state.  Returns dict(bits, tags, [debug taps]).
+    blocks: ao_blocks pointer (oracle.ref.blocks() = the reference's own classes); None = the
+    restated blocks."""
     cfg = cfg or chain_cfg()
     x = _c64(x)
     symbols = _c64(symbols)
@@ -427,7 +433,10 @@ def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096):
                    soft=np.zeros(mb, np.float32))
         for k, v in dbg.items():
             setattr(o, k, _fp(v).value)
-    rc = lib().ao_demod_chain(C.byref(cfg), _fp(symbols), len(symbols), _fp(x), n, C.byref(o))
+    lib().ao_demod_chain_with.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_int, C.c_void_p]
+    rc = lib().ao_demod_chain_with(blocks, C.addressof(cfg), _fp(symbols), len(symbols), _fp(x), n,
+                                   C.addressof(o))
     if rc:
         raise RuntimeError("ao_demod_chain failed: %d" % rc)
     res = dict(bits=bits[:o.nbits].copy(), tags=tags[:o.ntags].copy(), n1=o.n1, n2=o.n2,
@@ -443,16 +452,16 @@ def demod_chain(x, symbols, cfg=None, debug=False, max_tags=4096):
 class DemodStream:
     """The chain as a stream (ao_stream): state carried from work() call to work() call."""
 
-    def __init__(self, symbols, cfg=None):
+    def __init__(self, symbols, cfg=None, blocks=None):
         self.cfg = cfg or chain_cfg()
         symbols = _c64(symbols)
         L = lib()
-        L.ao_stream_new.restype = C.c_void_p
-        L.ao_stream_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ao_stream_new_with.restype = C.c_void_p
+        L.ao_stream_new_with.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ao_stream_delete.argtypes = [C.c_void_p]
         L.ao_stream_work.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]
-        self._s = L.ao_stream_new(C.addressof(self.cfg), _fp(symbols), len(symbols))
+        self._s = L.ao_stream_new_with(blocks, C.addressof(self.cfg), _fp(symbols), len(symbols))
         if not self._s:
             raise RuntimeError("ao_stream_new failed")
 
@@ -484,7 +493,7 @@ class DemodStream:
         return bits[:nb.value].copy(), tags[:nt.value].copy()
 
 
-def demod_chain_batch(x, symbols, cfg=None, max_tags=256, nthreads=0):
+def demod_chain_batch(x, symbols, cfg=None, max_tags=256, nthreads=0, blocks=None):
     """x: [C, n] complex64.  Returns bits [C, max_bits], nbits [C], tags [C, max_tags], ntags [C]."""
     cfg = cfg or chain_cfg()
     x = np.ascontiguousarray(x, dtype=np.complex64)
@@ -495,9 +504,12 @@ def demod_chain_batch(x, symbols, cfg=None, max_tags=256, nthreads=0):
     nbits = np.zeros(Cn, dtype=np.int32)
     tags = np.zeros((Cn, max_tags), dtype=TAG_DTYPE)
     ntags = np.zeros(Cn, dtype=np.int32)
-    rc = lib().ao_demod_chain_batch(C.byref(cfg), _fp(symbols), len(symbols), _fp(x), Cn, n,
-                                    _fp(bits), mb, _fp(nbits), _fp(tags), max_tags, _fp(ntags),
-                                    int(nthreads))
+    lib().ao_demod_chain_batch_with.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    rc = lib().ao_demod_chain_batch_with(blocks, C.addressof(cfg), _fp(symbols), len(symbols), _fp(x),
+                                         Cn, n, _fp(bits), mb, _fp(nbits), _fp(tags), max_tags,
+                                         _fp(ntags), int(nthreads))
     if rc:
         raise RuntimeError("ao_demod_chain_batch failed: %d" % rc)
     return bits, nbits, tags, ntags
