@@ -216,6 +216,28 @@ class ais_demod:
                                            B.ptr(tags), B.ptr(ntags)))
         return bits, nbits, tags, ntags
 
+    def work_sc16(self, iq16, scale, bits=None, nbits=None, tags=None, ntags=None):
+        """work() with the IQ as interleaved int16: iq16 [channels, nsamples, 2] int16 host array;
+        every component becomes float(v) * scale on the device (b200ais_demod_work_sc16)."""
+        iq16 = np.asarray(iq16)
+        if iq16.dtype != np.int16 or not iq16.flags.c_contiguous:
+            iq16 = np.ascontiguousarray(iq16, dtype=np.int16)
+        if iq16.ndim != 3 or iq16.shape[0] != self.channels or iq16.shape[2] != 2:
+            raise ValueError("expected [%d, nsamples, 2] int16" % self.channels)
+        n = iq16.shape[1]
+        mb = self.max_bits(n) if bits is None else bits.shape[1]
+        if bits is None:
+            bits = np.zeros((self.channels, mb), dtype=np.uint8)
+        if nbits is None:
+            nbits = np.zeros(self.channels, dtype=np.int32)
+        if tags is None:
+            tags = np.zeros((self.channels, self.max_tags), dtype=B.TAG_DTYPE)
+        if ntags is None:
+            ntags = np.zeros(self.channels, dtype=np.int32)
+        B.check(B.lib().b200ais_demod_work_sc16(self._h, B.ptr(iq16), C.c_float(scale), n, B.ptr(bits), mb,
+                                                B.ptr(nbits), B.ptr(tags), B.ptr(ntags)))
+        return bits, nbits, tags, ntags
+
     def work_dev(self, iq_ptr, nsamples, bits_ptr, max_bits, nbits_ptr, tags_ptr=None,
                  ntags_ptr=None, stream=None):
         """Device-resident variant: raw device addresses (e.g. torch_tensor.data_ptr()),

@@ -37,7 +37,7 @@ EXPORTS = [
     "b200ais_freqest_work_dev",
     "b200ais_invert_work", "b200ais_invert_work_dev",
     "b200ais_demod_default_config", "b200ais_demod_create", "b200ais_demod_destroy",
-    "b200ais_demod_max_bits", "b200ais_demod_work", "b200ais_demod_work_dev",
+    "b200ais_demod_max_bits", "b200ais_demod_work", "b200ais_demod_work_sc16", "b200ais_demod_work_dev",
     "b200ais_demod_status", "b200ais_demod_enable_taps", "b200ais_demod_tap",
     "b200ais_demod_read_tap", "b200ais_demod_profile", "b200ais_demod_stage_ms",
     "b200ais_demod_set_overlap", "b200ais_demod_stream_reset", "b200ais_demod_stream_max_bits",
@@ -53,6 +53,7 @@ EXPORTS = [
     "b200ais_rx_default_config", "b200ais_rx_create", "b200ais_rx_destroy", "b200ais_rx_reset",
     "b200ais_rx_decimation", "b200ais_rx_channels", "b200ais_rx_samples_per_symbol",
     "b200ais_rx_sentence_slot", "b200ais_rx_work", "b200ais_rx_work_dev", "b200ais_rx_status",
+    "b200ais_rx_tag_overflows",
     "b200ais_rx_replay_file", "b200ais_rx_serve_udp",
 ]
 FRAME_MAX = 248
@@ -154,6 +155,7 @@ def lib():
     L.b200ais_demod_destroy.argtypes = [vp]
     L.b200ais_demod_max_bits.argtypes = [vp, i]
     L.b200ais_demod_work.argtypes = [vp, vp, i, vp, i, vp, vp, vp]
+    L.b200ais_demod_work_sc16.argtypes = [vp, vp, C.c_float, i, vp, i, vp, vp, vp]
     L.b200ais_demod_work_dev.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp]
     L.b200ais_demod_status.argtypes = [vp]
     L.b200ais_demod_enable_taps.argtypes = [vp, i]
@@ -197,6 +199,8 @@ def lib():
               "b200ais_rx_status"):
         getattr(L, f).argtypes = [vp]
     L.b200ais_rx_samples_per_symbol.restype = C.c_float
+    L.b200ais_rx_tag_overflows.argtypes = [vp]
+    L.b200ais_rx_tag_overflows.restype = u64
     L.b200ais_rx_work.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, C.POINTER(i)]
     L.b200ais_rx_work_dev.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, vp, vp]
     L.b200ais_rx_replay_file.argtypes = [vp, C.c_char_p, i, i, RX_SINK, vp, C.POINTER(u64)]

@@ -251,7 +251,7 @@ extern "C" int b200ais_corr_est_work_dev(b200ais_corr_est *h, int noutput_items,
     const float2 *in_eff = in2 + h->L; // &in[hist_len] (lib/corr_est_cc_impl.cc:188)
     rc = launch_corr_fft(in_eff, in_stride, h->channels, n, h->L, tw, h->d_hbr, h->thresh,
                          h->d_tail[h->tail_cur], h->d_tail[h->tail_cur ^ 1], h->mask.as<uint8_t>(), ms,
-                         corr, corr_stride, s);
+                         corr, corr_stride, out1 == nullptr, (int)(in_stride - (size_t)h->L), s);
     if (rc)
         return rc;
     if (n > 0)
@@ -691,6 +691,7 @@ struct b200ais_demod {
     float2 *d_corr = nullptr;      // correlator stream [channels][corr_stride]
     size_t corr_stride = 0;
     float2 *d_x = nullptr; // staging for the host variant [channels][max_samples]
+    int16_t *d_x16 = nullptr; // staging of interleaved int16 I/Q (b200ais_demod_work_sc16)
     float2 *d_a = nullptr;
     uint8_t *d_mask = nullptr;
     int *d_raw = nullptr;
@@ -894,7 +895,7 @@ extern "C" int b200ais_demod_destroy(b200ais_demod *h)
 {
     if (!h)
         return B200AIS_OK;
-    void *ptrs[] = { h->d_taps_time, h->d_corr, h->d_x, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
+    void *ptrs[] = { h->d_taps_time, h->d_corr, h->d_x, h->d_x16, h->d_a, h->d_mask, h->d_raw, h->d_fhat, h->d_ckpt,
                      h->d_tags, h->d_ntags, h->d_nbits, h->d_ncons, h->d_state, h->d_bits,
                      h->d_status, h->d_xcarry, h->d_phase, h->d_yhist[0], h->d_yhist[1],
                      h->d_ctail[0], h->d_ctail[1], h->d_unc, h->d_nold, h->d_tcarry, h->d_a_alt,
@@ -1007,7 +1008,8 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     if ((rc = get_twiddles(corr_fft_size(h->L), &tw)))
         return rc;
     if ((rc = launch_corr_fft(a_rows, h->a_stride, cn, n2, h->L, tw, h->d_taps_time, h->thresh,
-                              nullptr, nullptr, mask, h->mask_stride, corr, h->corr_stride, s)))
+                              nullptr, nullptr, mask, h->mask_stride, corr, h->corr_stride, 1,
+                              (int)(h->a_stride - (size_t)h->HP), s)))
         return rc;
     B200_MARK(B200AIS_STAGE_T_CORR);
     if ((rc = launch_detect(corr, h->corr_stride, cn, n2, h->chunk, h->nsamples, h->isps,
@@ -1303,10 +1305,15 @@ extern "C" int b200ais_demod_status(b200ais_demod *h)
     return B200AIS_OK;
 }
 
-extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
-                                  int max_bits, int *nbits, b200ais_tag *tags, int *ntags)
+// host-buffer entry points: iq is complex64 rows, or (iq16 != nullptr) interleaved int16 I/Q rows
+// converted on the device as (float)v * scale -- one IEEE multiply per component, exact for a
+// power-of-two scale -- the format UHD / osmosdr sources carry on the wire before their host-side
+// conversion (python/radio.py:151-203)
+static int demod_work_host(b200ais_demod *h, const float *iq, const int16_t *iq16, float scale,
+                           int nsamples, uint8_t *bits, int max_bits, int *nbits, b200ais_tag *tags,
+                           int *ntags)
 {
-    if (!h || !iq || !bits || !nbits) {
+    if (!h || (!iq && !iq16) || !bits || !nbits) {
         set_error("demod_work: null argument");
         return B200AIS_E_INVALID;
     }
@@ -1317,8 +1324,10 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
         return rc;
     const int C = h->channels, n = nsamples;
     const bool direct = (h->cfg.stages & (B200AIS_STAGE_FREQSYNC | B200AIS_STAGE_AGC)) == 0;
-    if (!direct && !h->d_x)
+    if ((!direct || iq16) && !h->d_x)
         B200_CU(cudaMalloc(&h->d_x, sizeof(float2) * (size_t)h->max_samples * C));
+    if (iq16 && !h->d_x16)
+        B200_CU(cudaMalloc(&h->d_x16, sizeof(int16_t) * 2 * (size_t)h->max_samples * C));
     if (h->bits_cap < (size_t)max_bits * C) {
         if (h->d_bits)
             cudaFree(h->d_bits);
@@ -1336,22 +1345,36 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
         if (cn <= 0)
             continue;
         cudaStream_t s = h->streams[g];
-        const float2 *src = reinterpret_cast<const float2 *>(iq) + (size_t)c0 * n;
         const float2 *dev_iq;
         size_t dev_stride;
-        if (direct) {
+        int in_a = 0;
+        if (iq16) {
+            int16_t *d16 = h->d_x16 + (size_t)c0 * n * 2;
+            B200_CU(cudaMemcpyAsync(d16, iq16 + (size_t)c0 * n * 2, sizeof(int16_t) * 2 * (size_t)n * cn,
+                                    cudaMemcpyHostToDevice, s));
+            float2 *dst = direct ? h->d_a + (size_t)c0 * h->a_stride + h->HP : h->d_x + (size_t)c0 * n;
+            const size_t dst_stride = direct ? h->a_stride : (size_t)n;
+            if ((rc = launch_sc16_to_fc(d16, (size_t)n, dst, dst_stride, cn, n, scale, s)))
+                return rc;
+            dev_iq = dst;
+            dev_stride = dst_stride;
+            in_a = direct ? 1 : 0;
+        } else if (direct) {
+            const float2 *src = reinterpret_cast<const float2 *>(iq) + (size_t)c0 * n;
             float2 *a_rows = h->d_a + (size_t)c0 * h->a_stride + h->HP;
             B200_CU(cudaMemcpy2DAsync(a_rows, h->a_stride * sizeof(float2), src, (size_t)n * sizeof(float2),
                                       (size_t)n * sizeof(float2), cn, cudaMemcpyHostToDevice, s));
             dev_iq = a_rows;
             dev_stride = h->a_stride;
+            in_a = 1;
         } else {
+            const float2 *src = reinterpret_cast<const float2 *>(iq) + (size_t)c0 * n;
             float2 *dx = h->d_x + (size_t)c0 * n;
             B200_CU(cudaMemcpyAsync(dx, src, sizeof(float2) * (size_t)n * cn, cudaMemcpyHostToDevice, s));
             dev_iq = dx;
             dev_stride = (size_t)n;
         }
-        rc = demod_launch_group(h, c0, cn, dev_iq, dev_stride, n, direct ? 1 : 0,
+        rc = demod_launch_group(h, c0, cn, dev_iq, dev_stride, n, in_a,
                                 h->d_bits + (size_t)c0 * max_bits, max_bits, h->d_nbits + c0,
                                 h->d_tags + (size_t)c0 * h->max_tags, h->d_ntags + c0,
                                 h->d_status + 1 + g, s);
@@ -1372,6 +1395,27 @@ extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsample
     for (int g = 0; g < ngroups; g++)
         B200_CU(cudaStreamSynchronize(h->streams[g]));
     return b200ais_demod_status(h);
+}
+
+extern "C" int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
+                                  int max_bits, int *nbits, b200ais_tag *tags, int *ntags)
+{
+    if (!iq) {
+        set_error("demod_work: null argument");
+        return B200AIS_E_INVALID;
+    }
+    return demod_work_host(h, iq, nullptr, 1.0f, nsamples, bits, max_bits, nbits, tags, ntags);
+}
+
+extern "C" int b200ais_demod_work_sc16(b200ais_demod *h, const int16_t *iq, float scale, int nsamples,
+                                       uint8_t *bits, int max_bits, int *nbits, b200ais_tag *tags,
+                                       int *ntags)
+{
+    if (!iq) {
+        set_error("demod_work_sc16: null argument");
+        return B200AIS_E_INVALID;
+    }
+    return demod_work_host(h, nullptr, iq, scale, nsamples, bits, max_bits, nbits, tags, ntags);
 }
 
 
@@ -1533,7 +1577,8 @@ static int stream_run(b200ais_demod *h, const float2 *xin, size_t xin_stride, bo
     if (n2 > 0) {
         if ((rc = launch_corr_fft(h->d_a + h->HP, h->a_stride, C, n2, h->L, tw, h->d_taps_time,
                                   h->thresh, h->d_ctail[h->ct_cur], h->d_ctail[h->ct_cur ^ 1], h->d_mask,
-                                  h->mask_stride, h->d_corr, h->corr_stride, s)))
+                                  h->mask_stride, h->d_corr, h->corr_stride, 1,
+                                  (int)(h->a_stride - (size_t)h->HP), s)))
             return rc;
         h->ct_cur ^= 1;
     }
@@ -1584,8 +1629,11 @@ static int stream_prepare(b200ais_demod *h, int n, int max_bits, cudaStream_t s)
         set_error("demod_stream_work: nsamples %d outside [0, %d]", n, h->max_samples);
         return B200AIS_E_INVALID;
     }
-    if (max_bits < 1) {
-        set_error("demod_stream_work: max_bits must be positive");
+    // a shorter output row would stop the timing loop on noutput_items and leave more than the
+    // kKeep items the rows carry between calls unconsumed
+    if (max_bits < b200ais_demod_stream_max_bits(h, n)) {
+        set_error("demod_stream_work: max_bits %d below b200ais_demod_stream_max_bits(%d) = %d", max_bits, n,
+                  b200ais_demod_stream_max_bits(h, n));
         return B200AIS_E_INVALID;
     }
     int rc = demod_drain(h);

@@ -139,10 +139,15 @@ int corr_fft_size(int L);
 int corr_blocks_per_cta(int L);
 size_t corr_mask_stride_bytes(int L, int n);
 int make_corr_spectrum(const float *taps_iq, int L, float2 *hbr_host /* [fftsize] */);
+// the kernel's immediates for the 16th roots of unity against a host twiddle table of length n
+int corr_check_w16(const float2 *tw_host, int n);
+// sparse != 0: corr_out only has to serve k_detect (blocks without a sample above the threshold
+// write their first and last item only).  in_readable: items readable from `in` in every row
+// (>= n; the bulk-copy path rounds an odd n up to the next 16 bytes).
 int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int L,
                     const float2 *tw, const float2 *hbr, float thresh, const float2 *tail_in,
                     float2 *tail_out, uint8_t *mask, size_t mask_stride, float2 *corr_out,
-                    size_t corr_stride, cudaStream_t s);
+                    size_t corr_stride, int sparse, int in_readable, cudaStream_t s);
 // A4: the serial detector, one warp per channel, on the correlator stream.
 int launch_detect(const float2 *corr, size_t corr_stride, int channels, int n_total, int chunk,
                   int nsamples_mult, int isps, unsigned mark_delay, const uint8_t *mask,
@@ -171,6 +176,9 @@ int launch_roll_rows(float2 *rows, size_t stride, int channels, int from, int le
 int launch_msk_reset(MskState *state, int channels, float sps_half, cudaStream_t s);
 int launch_msk_set_omega(MskState *state, int channels, float omega, cudaStream_t s);
 int launch_invert(const uint8_t *in, uint8_t *out, size_t n, cudaStream_t s);
+// interleaved int16 I/Q rows -> complex float rows: out = (float)in * scale per component
+int launch_sc16_to_fc(const int16_t *in, size_t in_stride, float2 *out, size_t out_stride, int channels,
+                      int n, float scale, cudaStream_t s);
 // ais_rx output (framing.cu): dense message list + its sentences
 int launch_gather_frames(const b200ais_frame *frames, const int *nframes, int channels,
                          int max_frames, b200ais_frame *dense, int max_msgs, int *count,

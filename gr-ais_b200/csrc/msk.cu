@@ -9,6 +9,8 @@
 //
 // The loop carries mu / omega / the delay registers from one half-symbol to the next, so a
 // channel is strictly serial: one thread per channel, thousands of channels in flight.
+#include <cstdlib>
+
 #include "device_math.cuh"
 #include "internal.h"
 
@@ -38,23 +40,45 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
     return true;
 }
 
-constexpr int kMskChunk = 32;   // samples per prefetch chunk
-constexpr int kMskRing = 128;   // ring samples per channel (4 chunks)
+// Ring geometry.  The loop's throughput is the number of warps an SM holds (a lone warp issues
+// one instruction every ~3 cycles), and what bounds that is the shared memory of the per-lane
+// rings; but a small ring leaves less room to request samples ahead of the DRAM latency
+// (~2 us under load = ~2 rounds).  Three geometries, picked by the channel count (launch_msk):
+//   kind 0: 128-sample ring, 32-sample chunks, 8-step rounds, 39 KB/warp ->  5 warps/SM (23 680 ch)
+//   kind 1:  96-sample ring, 16-sample chunks, 8-step rounds, 29 KB/warp ->  7 warps/SM (33 152 ch)
+//   kind 2:  48-sample ring, 16-sample chunks, 4-step rounds, 15 KB/warp -> 14 warps/SM (66 304 ch)
+// The warps of a CTA are on their own; they share the 4 KB interpolator table, which has to sit
+// in shared memory (a table row read through L1 misses often enough to show on the critical
+// path).  Small batches run one warp per CTA so that every SM gets its share of the warps; the
+// large ones pack 7 warps behind one table (7 or 14 warps per SM).
+template <int KIND> struct MskCfg;
+template <> struct MskCfg<0> {
+    static constexpr int Chunk = 32, Ring = 128, Fast = 8, Need = 32, TagCap = 16;
+};
+template <> struct MskCfg<1> {
+    static constexpr int Chunk = 16, Ring = 96, Fast = 8, Need = 32, TagCap = 8;
+};
+template <> struct MskCfg<2> {
+    static constexpr int Chunk = 16, Ring = 48, Fast = 4, Need = 20, TagCap = 4;
+};
 constexpr int kMskMirror = 8;   // samples 0..7 repeated after the ring: 10-sample reads never wrap
-constexpr int kMskUnits = (kMskRing + kMskMirror) / 2; // 16-byte units (2 samples) per lane
-constexpr int kMskInner = 4;    // half-symbol steps per careful round
-constexpr int kMskFast = 8;     // half-symbol steps per straight-line round
-constexpr int kMskNeed = 32;    // samples past iidx a round may touch
-constexpr int kMskAhead = 63;   // request the next chunk once fewer than this many samples are requested ahead
-constexpr int kMskTagCap = 32;  // time_est tags per channel staged in shared memory
+constexpr int kMskInner = 4;    // half-symbol steps per careful round (fewer when sps is large)
+constexpr int kMskTable = 129 * 8 * 4 + 32; // the interpolator table in front of the rings (16-byte multiple)
+template <int KIND> __host__ __device__ constexpr int msk_warp_smem()
+{
+    return (MskCfg<KIND>::Ring + kMskMirror) / 2 * 32 * 16 + MskCfg<KIND>::TagCap * 32 * 8;
+}
 
 __device__ __forceinline__ void cp_async_8(unsigned smem, const void *gmem, int src_bytes)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
 }
+// .cg: every item is read once, so it goes past L1 (which keeps the interpolator table);
+// .L2::128B: the first 16 bytes a lane asks of a line bring the whole line into L2, so DRAM sees
+// one 128-byte request per line instead of eight partial ones (each lane streams its own row)
 __device__ __forceinline__ void cp_async_16(unsigned smem, const void *gmem, int src_bytes)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+    asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16, %2;\n" ::"r"(smem), "l"(gmem), "r"(src_bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -66,9 +90,16 @@ struct MskLane {
     float diff1_re, diff1_im;
     float2 vlast;
     int div, iidx, oidx;
+    int rpos;                 // iidx mod kMskRing
     float2 *op;               // next symbol slot
     bool bad_imu;
 };
+
+template <int RING> __device__ __forceinline__ int ring_pos(int iidx)
+{
+    int r = iidx % RING;
+    return r < 0 ? r + RING : r;
+}
 
 // One half-symbol step from the row index imu (:170-201 without the tag test): interpolate,
 // error detector, loop filter on odd steps, output on even steps, advance.  ring4: this lane's
@@ -79,11 +110,10 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
                                           float *oe, float *om)
 {
     // mmse_fir_interpolator_cc::interpolate: in[0..7] . reversed row.  The 8 samples start at
-    // ring sample iidx: five 16-byte units (conflict-free: the lane picks the banks), then the
+    // ring sample rpos: five 16-byte units (conflict-free: the lane picks the banks), then the
     // odd/even start is a select
-    const int k = L.iidx;
-    const int u0 = (k >> 1) & (kMskRing / 2 - 1);
-    const bool par = k & 1;
+    const int u0 = L.rpos >> 1;
+    const bool par = L.rpos & 1;
     const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8);
     const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8 + 4);
     const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
@@ -140,16 +170,20 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
 }
 
 // The serial core of msk_timing_recovery_cc: one lane per channel.  A channel's loop is a
-// recurrence on (mu, omega, iidx, div, previous interpolant), so the kernel's run time is
-// (#half-symbols) x (latency of one step) however many channels run: the step is kept as
-// short as possible and everything off the recurrence (the bit tail) lives in k_tail.
-// Each lane streams its own channel through a private shared-memory ring (4 chunks of 32
-// samples, stored as 16-byte units interleaved across lanes so that a lane's reads never
-// meet another lane's banks) with cp.async, requesting a 256-byte chunk ~60 samples before it
-// is needed, so no step waits on HBM.  The lane's time_est tags are staged in shared memory
-// by a prologue (a tag fetched from HBM on the loop's critical path costs a DRAM round trip).
-template <bool kDebug>
-__global__ void __launch_bounds__(32)
+// recurrence on (mu, omega, iidx, div, previous interpolant): a lone warp issues one
+// instruction every ~3 cycles and a step takes ~450 cycles however many channels run, so the
+// kernel's throughput is the number of warps an SM can hold.  What bounds that is shared
+// memory: each lane streams its own channel through a private ring (3 chunks of 16 samples +
+// 8 mirrored, stored as 16-byte units interleaved across lanes so that a lane's reads never
+// meet another lane's banks) filled by cp.async, 15 KB per warp -> 14 warps per SM, 2072
+// warps = 66 304 channels in flight on 148 SMs (BASELINE configs[2]'s 65 536 in one wave; the
+// previous 128-sample ring + table + 32 staged tags held 4 warps per SM, 18 944 channels).
+// A lane requests a 128-byte chunk at least one round (4 steps, ~10 samples) before it is
+// needed, so no step waits on HBM.  Up to 4 of the lane's time_est tags are staged in shared
+// memory and refilled from the list when they run out (a tag fetched on the loop's critical
+// path costs a DRAM round trip; a burst carries about six).
+template <bool kDebug, int KIND, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput_items,
       int ninput_items, uint64_t nitems_read, const b200ais_tag *__restrict__ tags, int max_tags,
       const int *__restrict__ ntags, MskParams p, MskState *__restrict__ state,
@@ -158,14 +192,24 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
       int *__restrict__ nconsumed, int require_unbounded, int *__restrict__ status,
       int *__restrict__ unconsumed)
 {
-    __shared__ __align__(16) float s_mmse[129 * 8];
-    __shared__ __align__(16) float4 ring[kMskUnits * 32];
-    __shared__ int2 s_tags[kMskTagCap * 32];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < 129 * 8; i += 32)
+    using Cfg = MskCfg<KIND>;
+    constexpr int kMskChunk = Cfg::Chunk, kMskRing = Cfg::Ring, kMskFast = Cfg::Fast, kMskNeed = Cfg::Need;
+    constexpr int kMskTagCap = Cfg::TagCap;
+    constexpr int kMskUnits = (kMskRing + kMskMirror) / 2; // 16-byte units (2 samples) per lane
+    // request the next chunk once fewer than this many samples are requested ahead: the chunk it
+    // replaces then ends at or before iidx - 2, so in[iidx - 1] (negative centre) stays
+    constexpr int kMskAhead = kMskRing - kMskChunk - 1;
+    constexpr int kMskWarpSmem = msk_warp_smem<KIND>();
+    constexpr int kMskWarps = WARPS;
+    extern __shared__ __align__(16) unsigned char msk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *s_mmse = reinterpret_cast<float *>(msk_smem);
+    float4 *ring = reinterpret_cast<float4 *>(msk_smem + kMskTable + warp * kMskWarpSmem);
+    int2 *s_tags = reinterpret_cast<int2 *>(msk_smem + kMskTable + warp * kMskWarpSmem + kMskUnits * 32 * 16);
+    for (int i = threadIdx.x; i < 129 * 8; i += 32 * kMskWarps)
         s_mmse[i] = g_mmse[i];
-    __syncwarp();
-    const int c = blockIdx.x * 32 + lane;
+    __syncthreads(); // the only block-wide step: from here on every warp is on its own
+    const int c = (blockIdx.x * kMskWarps + warp) * 32 + lane;
     if (c >= channels)
         return;
 
@@ -199,50 +243,37 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     const unsigned my_s = (unsigned)__cvta_generic_to_shared(ring4);
     const bool row16 = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
 
-    // time_est tags inside [read, read+ninp), in offset order (:125-130): staged in shared
-    // memory; a channel with more than kMskTagCap of them reads them from HBM as it goes
+    // time_est tags inside [read, read+ninp), in offset order (:125-130): up to kMskTagCap of
+    // them wait in shared memory; the list is scanned on from gpos when they have been used
     const b200ais_tag *tg = tags ? tags + (size_t)c * max_tags : nullptr;
     const int nt = (tags && ntags) ? min(ntags[c], max_tags) : 0;
     auto matches = [&](const b200ais_tag &t) {
         return t.key == B200AIS_TAG_TIME_EST && t.port == 0 && t.offset >= nitems_read &&
                t.offset < nitems_read + (uint64_t)ninp;
     };
-    int nstaged = 0;
-#pragma unroll 4
-    for (int k = 0; k < nt; k++) {
-        const b200ais_tag t = tg[k];
-        if (matches(t)) {
-            if (nstaged < kMskTagCap)
-                s_tags[nstaged * 32 + lane] =
-                    make_int2((int)(t.offset - nitems_read), __float_as_int((float)t.value));
-            nstaged++;
-        }
-    }
-    const bool tags_global = nstaged > kMskTagCap;
-    int thead = 0;            // next entry of the staged list, or index into tg[] (tags_global)
+    int gpos = 0;             // next entry of tg[] to look at
+    int nstaged = 0, thead = 0;
     int tag_off = 0x7fffffff; // pending tag, relative to the read pointer
     float tag_val = 0.0f;
-    auto fetch_tag = [&]() { // the first tag at or after thead
+    auto fetch_tag = [&]() { // the next tag in list order
+        if (thead >= nstaged) {
+            nstaged = 0;
+            thead = 0;
+            while (gpos < nt && nstaged < kMskTagCap) {
+                const b200ais_tag t = tg[gpos++];
+                if (matches(t)) {
+                    s_tags[nstaged * 32 + lane] =
+                        make_int2((int)(t.offset - nitems_read), __float_as_int((float)t.value));
+                    nstaged++;
+                }
+            }
+        }
         tag_off = 0x7fffffff;
-        if (!tags_global) {
-            if (thead < nstaged) {
-                const int2 e = s_tags[thead * 32 + lane];
-                tag_off = e.x;
-                tag_val = __int_as_float(e.y);
-            }
-            return;
+        if (thead < nstaged) {
+            const int2 e = s_tags[thead * 32 + lane];
+            tag_off = e.x;
+            tag_val = __int_as_float(e.y);
         }
-        int k = thead;
-        while (k < nt) {
-            const b200ais_tag t = tg[k];
-            if (matches(t)) {
-                tag_off = (int)(t.offset - nitems_read);
-                tag_val = (float)t.value;
-                break;
-            }
-            k++;
-        }
-        thead = k;
     };
     fetch_tag();
     const int tag_span = (int)ceilf(p.sps_half) + 1; // integer pre-test before the float compare
@@ -263,25 +294,29 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     L.diff1_im = st.diff1_im;
     L.div = st.div;
     L.iidx = mis;
+    L.rpos = mis;
     L.oidx = 0;
     L.op = oc;
     L.bad_imu = false;
 
     int issue_end = 0; // samples [0, issue_end) of this lane's channel have been requested
+    int issue_u = 0;   // ring unit the next chunk goes to (0, 8, 16)
     int ready_end = 0; // samples [0, ready_end) are known to have landed
     int err_code = 0;
     bool active = true;
     const unsigned FULL = __activemask(); // the lanes that own a channel (a prefix of the warp)
 
-    // One step advances the read index by floor(mu + omega) <= advmax items.  The straight-line
-    // round needs kMskFast steps' worth of samples inside what a round may touch.
+    // One step advances the read index by floor(mu + omega) <= advmax items.  A round may touch
+    // kMskNeed samples: the straight-line round needs kMskFast steps' worth of them, the careful
+    // round runs as many steps as fit (launch_msk rejects rates for which not even one does).
     const int advmax = (int)floorf(1.0f + 3.0f * p.gain + p.sps_half + fabsf(p.limit) + 1e-3f);
     const int fast_in = kMskFast * advmax;
     const bool fast_ok = advmax >= 1 && fast_in + 8 <= kMskNeed && 3.0f * p.gain < 0.5f;
+    const int inner = max(1, min(kMskInner, (kMskNeed - 8) / max(advmax, 1)));
 
     // cp.async groups are tracked per warp, not per lane, so requests and waits happen in
     // warp-wide rounds, decided by one warp-wide OR per round: a round first waits (only for
-    // chunks requested in EARLIER rounds, microseconds ago), then requests the next chunk for
+    // chunks requested in EARLIER rounds, a microsecond ago), then requests the next chunk for
     // every lane that is within kMskAhead samples of the end of what it has requested, then
     // runs its steps.
     //
@@ -307,11 +342,10 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             starved = __any_sync(FULL, active && (L.iidx + kMskNeed > ready_end));
         }
         if (any & 4u) {
-            // (want implies room: the chunk being replaced ends at issue_end - 96 <= iidx - 33)
             if (want) {
-                const unsigned dst = my_s + ((issue_end >> 1) & (kMskRing / 2 - 1)) * 512;
+                const unsigned dst = my_s + issue_u * 512;
                 const float2 *src = row + issue_end;
-                const bool first = (issue_end & (kMskRing - 1)) == 0; // also feeds the mirror units
+                const bool first = issue_u == 0; // also feeds the mirror units
                 if (row16 && issue_end + kMskChunk <= ninput_items) {
 #pragma unroll
                     for (int u = 0; u < kMskChunk / 2; u++)
@@ -331,6 +365,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                     }
                 }
                 issue_end += kMskChunk;
+                issue_u = issue_u + kMskChunk / 2 == kMskRing / 2 ? 0 : issue_u + kMskChunk / 2;
             }
             cp_async_commit();
         }
@@ -347,15 +382,17 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 const int fl_i = __float2int_rd(x);
                 imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
                 L.iidx += fl_i;
+                const int rp = L.rpos + fl_i; // 0 <= fl_i <= advmax < kMskRing
+                L.rpos = rp >= kMskRing ? rp - kMskRing : rp;
                 L.mu = x - floorf(x);
             }
             active = (L.oidx < noutput_items) && (L.iidx < ninp);
             continue;
         }
-        // ---- careful round: kMskInner steps with every test ----
+        // ---- careful round: up to kMskInner steps with every test ----
 #pragma unroll
         for (int it = 0; it < kMskInner; it++) {
-            if (active) {
+            if (active && it < inner) {
                 // tag reset (:139-164); rare: an integer window test guards the float compare
                 if (((unsigned)tag_off - (unsigned)L.iidx) < (unsigned)tag_span) {
                     if ((float)tag_off < ((float)L.iidx + p.sps_half)) {
@@ -366,6 +403,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                                 L.mu = L.mu + 1.0f;
                                 L.iidx--;
                             }
+                            L.rpos = ring_pos<kMskRing>(L.iidx);
                             L.div = 0;
                             L.omega = p.sps_half;
                         }
@@ -380,6 +418,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 const float x = msk_step<kDebug>(L, imu_c, ring4, s_mmse, p, oe, om);
                 const float fl = floorf(x);
                 L.iidx += (int)fl;
+                L.rpos = ring_pos<kMskRing>(L.iidx);
                 L.mu = x - fl;
                 active = (L.oidx < noutput_items) && (L.iidx < ninp);
             }
@@ -566,7 +605,52 @@ __global__ void k_invert(const uint8_t *__restrict__ in, uint8_t *__restrict__ o
     }
 }
 
+// interleaved int16 I/Q -> complex float, four items (16 bytes in, 32 bytes out) per thread
+__global__ void __launch_bounds__(256)
+k_sc16_to_fc(const int16_t *__restrict__ in, size_t in_stride, float2 *__restrict__ out,
+             size_t out_stride, int channels, int n, float scale)
+{
+    const int c = channel_index();
+    if (c >= channels)
+        return;
+    const int16_t *ic = in + (size_t)c * in_stride * 2;
+    float2 *oc = out + (size_t)c * out_stride;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n)
+        return;
+    const bool vec = i0 + 4 <= n && ((reinterpret_cast<uintptr_t>(ic + 2 * (size_t)i0) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(oc + i0) & 15) == 0);
+    if (vec) {
+        const int4 w = *reinterpret_cast<const int4 *>(ic + 2 * (size_t)i0);
+        const int v[4] = { w.x, w.y, w.z, w.w };
+        float4 o[2];
+        float *of = reinterpret_cast<float *>(o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            of[2 * k] = (float)(short)(v[k] & 0xffff) * scale;
+            of[2 * k + 1] = (float)(short)(v[k] >> 16) * scale;
+        }
+        float4 *o4 = reinterpret_cast<float4 *>(oc + i0);
+        o4[0] = o[0];
+        o4[1] = o[1];
+    } else {
+        for (int k = i0; k < min(i0 + 4, n); k++)
+            oc[k] = make_float2((float)ic[2 * k] * scale, (float)ic[2 * k + 1] * scale);
+    }
+}
+
 } // namespace
+
+int launch_sc16_to_fc(const int16_t *in, size_t in_stride, float2 *out, size_t out_stride, int channels,
+                      int n, float scale, cudaStream_t s)
+{
+    if (channels <= 0 || n <= 0)
+        return B200AIS_OK;
+    dim3 grid = channel_grid((unsigned)((n + 1023) / 1024), channels);
+    k_sc16_to_fc<<<grid, 256, 0, s>>>(in, in_stride, out, out_stride, channels, n, scale);
+    B200_LAUNCH_CHECK("k_sc16_to_fc");
+    return B200AIS_OK;
+}
 
 int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
@@ -580,17 +664,76 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
     int rc = get_tables(&tb);
     if (rc)
         return rc;
-    const int blocks = (channels + 31) / 32; // one warp (32 channels) per block
-    if (out_err || out_mu)
-        k_msk<true><<<blocks, 32, 0, s>>>(in, in_stride, channels, noutput_items, ninput_items,
-                                          nitems_read, tags, max_tags, ntags, p, state, tb.mmse, out,
-                                          out_err, out_mu, out_stride, nproduced, nconsumed,
-                                          require_unbounded, status, unconsumed);
+    // ring geometry by occupancy need (see MskCfg): the smallest number of warps per SM that
+    // runs every channel in one wave; B200AIS_MSK_KIND=0/1/2 overrides (experiments)
+    const int advmax = (int)floorf(1.0f + 3.0f * p.gain + p.sps_half + fabsf(p.limit) + 1e-3f);
+    const int warps = (channels + 31) / 32;
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess)
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int per_sm = (warps + sms - 1) / sms;
+    // (kind, warps per CTA): 5 x 1, 6 x 1, 1 x 7 or 2 x 7 warps per SM
+    int kind = per_sm <= 5 ? 0 : (per_sm <= 7 ? 1 : 2);
+    bool packed = per_sm > 6;
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("B200AIS_MSK_KIND");
+        forced = (e && *e) ? atoi(e) : -1;
+    }
+    if (forced >= 0 && forced <= 2) {
+        kind = forced;
+        packed = kind == 2 || (kind == 1 && per_sm > 6);
+    }
+    // a round must be able to make one step inside the ring's ready window
+    if (kind == 2 && !(advmax + 8 <= MskCfg<2>::Need)) {
+        kind = 1;
+        packed = true;
+    }
+    if (!(advmax + 8 <= MskCfg<1>::Need)) {
+        set_error("msk_timing_recovery: sps %g with gain %g / limit %g advances up to %d items per "
+                  "half-symbol step; this build supports up to %d", 2.0 * p.sps_half, p.gain, p.limit,
+                  advmax, MskCfg<1>::Need - 8);
+        return B200AIS_E_INVALID;
+    }
+    const bool dbg = out_err || out_mu;
+#define B200_MSK(DBG, KIND, W)                                                                     \
+    do {                                                                                           \
+        const int per_cta = 32 * W;                                                                \
+        const int blocks = (channels + per_cta - 1) / per_cta;                                     \
+        const size_t smem = (size_t)kMskTable + (size_t)W * msk_warp_smem<KIND>();                 \
+        static bool attr_set = false;                                                              \
+        if (!attr_set) { /* all the shared memory the SM has: occupancy is the throughput */       \
+            B200_CU(cudaFuncSetAttribute(k_msk<DBG, KIND, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                              \
+            B200_CU(cudaFuncSetAttribute(k_msk<DBG, KIND, W>,                                      \
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
+            attr_set = true;                                                                       \
+        }                                                                                          \
+        k_msk<DBG, KIND, W><<<blocks, per_cta, smem, s>>>(                                         \
+            in, in_stride, channels, noutput_items, ninput_items, nitems_read, tags, max_tags, ntags, \
+            p, state, tb.mmse, out, out_err, out_mu, out_stride, nproduced, nconsumed,             \
+            require_unbounded, status, unconsumed);                                                \
+    } while (0)
+#define B200_MSK_KIND(DBG)                                                                         \
+    do {                                                                                           \
+        if (kind == 0)                                                                             \
+            B200_MSK(DBG, 0, 1);                                                                   \
+        else if (kind == 1 && !packed)                                                             \
+            B200_MSK(DBG, 1, 1);                                                                   \
+        else if (kind == 1)                                                                        \
+            B200_MSK(DBG, 1, 7);                                                                   \
+        else                                                                                       \
+            B200_MSK(DBG, 2, 7);                                                                   \
+    } while (0)
+    if (dbg)
+        B200_MSK_KIND(true);
     else
-        k_msk<false><<<blocks, 32, 0, s>>>(in, in_stride, channels, noutput_items, ninput_items,
-                                           nitems_read, tags, max_tags, ntags, p, state, tb.mmse, out,
-                                           out_err, out_mu, out_stride, nproduced, nconsumed,
-                                           require_unbounded, status, unconsumed);
+        B200_MSK_KIND(false);
+#undef B200_MSK_KIND
+#undef B200_MSK
     B200_LAUNCH_CHECK("k_msk");
     return B200AIS_OK;
 }

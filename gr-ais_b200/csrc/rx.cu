@@ -11,6 +11,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <future>
@@ -33,6 +34,7 @@ struct b200ais_rx {
     int carry = 0; // items of every row kept from the last call
     uint8_t *d_bits = nullptr;
     int *d_nbits = nullptr, *d_nframes = nullptr, *d_count = nullptr, *d_status = nullptr;
+    uint64_t tag_overflows = 0; // calls in which a channel met more tags than its row holds
     b200ais_frame *d_frames = nullptr;
     char *d_des = nullptr;
     // device-side outputs of the host variant
@@ -138,7 +140,13 @@ extern "C" int b200ais_rx_create(b200ais_rx **out, const b200ais_rx_config *cfg,
         dc.fftlen = cfg->fftlen;
         dc.gain = cfg->clockrec_gain;
         dc.limit = cfg->omega_relative_limit;
-        rc = b200ais_demod_create(&h->dm, &dc, symbols_iq, nsymbols, h->channels, h->max_out, 256);
+        // corr_est_cc adds four tags per detection and at most one detection per isps items
+        // (lib/corr_est_cc_impl.cc:213-256,270); a busy channel carries 37.5 slots/s and about six
+        // detections per burst.  The row holds the worst case up to 4096 tags; beyond that the
+        // call counts an overflow (b200ais_rx_tag_overflows) and goes on.
+        const int isps = (int)(sps + 0.5f);
+        const int max_tags = std::min(4096, std::max(256, 4 * (h->max_out / std::max(isps, 1) + 2)));
+        rc = b200ais_demod_create(&h->dm, &dc, symbols_iq, nsymbols, h->channels, h->max_out, max_tags);
     }
     if (!rc)
         rc = b200ais_hdlc_create(&h->hd, cfg->hdlc_length_min, cfg->hdlc_length_max, h->channels);
@@ -254,8 +262,15 @@ extern "C" int b200ais_rx_status(b200ais_rx *h)
     int rc = b200ais_hdlc_status(h->hd);
     if (rc)
         return rc;
-    return b200ais_demod_status(h->dm);
+    rc = b200ais_demod_status(h->dm);
+    if (rc == B200AIS_E_TAG_OVERFLOW) { // tags beyond the row were dropped: the messages stand
+        h->tag_overflows++;
+        rc = B200AIS_OK;
+    }
+    return rc;
 }
+
+extern "C" uint64_t b200ais_rx_tag_overflows(const b200ais_rx *h) { return h ? h->tag_overflows : 0; }
 
 extern "C" int b200ais_rx_work(b200ais_rx *h, const float *iq, size_t iq_stride, int nitems,
                                b200ais_frame *msgs, char *sentences, int slot, int *lens,
@@ -361,9 +376,13 @@ struct UdpReader : ItemReader {
         while (have < want_b && !eof) {
             pollfd pf = {fd, POLLIN, 0};
             const int pr = poll(&pf, 1, idle_ms);
+            if (pr < 0 && errno == EINTR)
+                continue; // a signal, not the end of the capture
             if (pr <= 0)
                 break; // idle (or error): the capture is over
             const ssize_t n = recv(fd, dgram, sizeof(dgram), 0);
+            if (n < 0 && (errno == EINTR || errno == EAGAIN))
+                continue;
             if (n < 0)
                 break;
             if (n == 0) {

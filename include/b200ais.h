@@ -214,6 +214,14 @@ B200AIS_API int b200ais_demod_set_symbols(b200ais_demod *h, const float *symbols
  * nbits: [channels]; tags (nullable): [channels][max_tags]; ntags (nullable): [channels]. */
 B200AIS_API int b200ais_demod_work(b200ais_demod *h, const float *iq, int nsamples, uint8_t *bits,
                                    int max_bits, int *nbits, b200ais_tag *tags, int *ntags);
+/* The same call with the IQ delivered as interleaved int16 I/Q (the SDR wire format: UHD "sc16",
+ * osmosdr; the reference's sources convert it to gr_complex on the host, python/radio.py:151-203).
+ * Every component becomes (float)v * scale on the device (exact for a power-of-two scale), then
+ * the chain runs as in b200ais_demod_work: half the bytes cross PCIe.
+ * iq: [channels][nsamples][2] int16. */
+B200AIS_API int b200ais_demod_work_sc16(b200ais_demod *h, const int16_t *iq, float scale, int nsamples,
+                                        uint8_t *bits, int max_bits, int *nbits, b200ais_tag *tags,
+                                        int *ntags);
 B200AIS_API int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsamples,
                                        uint8_t *bits, int max_bits, int *nbits, b200ais_tag *tags,
                                        int *ntags, void *stream);
@@ -428,6 +436,9 @@ B200AIS_API int b200ais_rx_work_dev(b200ais_rx *h, const float *iq, size_t iq_st
                                     b200ais_frame *msgs, char *sentences, int slot, int *lens,
                                     int max_msgs, int *nmsgs, void *stream);
 B200AIS_API int b200ais_rx_status(b200ais_rx *h);
+/* calls in which some channel met more corr_est tags than its row holds (the extra tags were
+ * dropped, i.e. some timing resets were missed; the call's messages are delivered all the same) */
+B200AIS_API uint64_t b200ais_rx_tag_overflows(const b200ais_rx *h);
 /* Recorded-IQ replay: blocks.file_source(gr.sizeof_gr_complex, path) (python/radio.py:211-213)
  * feeding every source of the receiver with the same capture.  The file (raw interleaved
  * float32 IQ) is read in chunks of chunk_items through two pinned buffers, the read of the next
