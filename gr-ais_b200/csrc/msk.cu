@@ -44,7 +44,7 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
 // one instruction every ~3 cycles), and what bounds that is the shared memory of the per-lane
 // rings; but a small ring leaves less room to request samples ahead of the DRAM latency
 // (~2 us under load = ~2 rounds).  Three geometries, picked by the channel count (launch_msk):
-//   kind 0: 128-sample ring, 32-sample chunks, 8-step rounds, 39 KB/warp ->  5 warps/SM (23 680 ch)
+//   kind 0: 128-sample ring, 32-sample chunks, 8-step rounds, 43 KB/warp ->  4 warps/SM (18 944 ch)
 //   kind 1:  96-sample ring, 16-sample chunks, 8-step rounds, 29 KB/warp ->  7 warps/SM (33 152 ch)
 //   kind 2:  48-sample ring, 16-sample chunks, 4-step rounds, 15 KB/warp -> 14 warps/SM (66 304 ch)
 // The warps of a CTA are on their own; they share the 4 KB interpolator table, which has to sit
@@ -53,7 +53,7 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
 // large ones pack 7 warps behind one table (7 or 14 warps per SM).
 template <int KIND> struct MskCfg;
 template <> struct MskCfg<0> {
-    static constexpr int Chunk = 32, Ring = 128, Fast = 8, Need = 32, TagCap = 16;
+    static constexpr int Chunk = 32, Ring = 128, Fast = 8, Need = 32, TagCap = 32;
 };
 template <> struct MskCfg<1> {
     static constexpr int Chunk = 16, Ring = 96, Fast = 8, Need = 32, TagCap = 8;
@@ -63,7 +63,7 @@ template <> struct MskCfg<2> {
 };
 constexpr int kMskMirror = 8;   // samples 0..7 repeated after the ring: 10-sample reads never wrap
 constexpr int kMskInner = 4;    // half-symbol steps per careful round (fewer when sps is large)
-constexpr int kMskTable = 129 * 8 * 4 + 32; // the interpolator table in front of the rings (16-byte multiple)
+constexpr int kMskTable = 2 * 132 * 16; // the interpolator table (two arrays of half rows) in front of the rings
 template <int KIND> __host__ __device__ constexpr int msk_warp_smem()
 {
     return (MskCfg<KIND>::Ring + kMskMirror) / 2 * 32 * 16 + MskCfg<KIND>::TagCap * 32 * 8;
@@ -114,8 +114,10 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
     // odd/even start is a select
     const int u0 = L.rpos >> 1;
     const bool par = L.rpos & 1;
-    const float4 ta = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8);
-    const float4 tb = *reinterpret_cast<const float4 *>(s_mmse + imu_c * 8 + 4);
+    // the table is kept as two arrays of half rows (16 bytes each): a row index then spreads the
+    // lanes over all eight 16-byte bank groups instead of four
+    const float4 ta = reinterpret_cast<const float4 *>(s_mmse)[imu_c];
+    const float4 tb = reinterpret_cast<const float4 *>(s_mmse)[132 + imu_c];
     const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
     const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
     const float2 s0 = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
@@ -206,8 +208,10 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     float *s_mmse = reinterpret_cast<float *>(msk_smem);
     float4 *ring = reinterpret_cast<float4 *>(msk_smem + kMskTable + warp * kMskWarpSmem);
     int2 *s_tags = reinterpret_cast<int2 *>(msk_smem + kMskTable + warp * kMskWarpSmem + kMskUnits * 32 * 16);
-    for (int i = threadIdx.x; i < 129 * 8; i += 32 * kMskWarps)
-        s_mmse[i] = g_mmse[i];
+    for (int i = threadIdx.x; i < 129 * 8; i += 32 * kMskWarps) { // row r, tap k -> half (k >> 2), row r
+        const int r = i >> 3, k = i & 7;
+        s_mmse[((k >> 2) * 132 + r) * 4 + (k & 3)] = g_mmse[i];
+    }
     __syncthreads(); // the only block-wide step: from here on every warp is on its own
     const int c = (blockIdx.x * kMskWarps + warp) * 32 + lane;
     if (c >= channels)
@@ -259,13 +263,26 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         if (thead >= nstaged) {
             nstaged = 0;
             thead = 0;
+            // four list entries per trip: their loads are independent, so a refill costs one or
+            // two DRAM round trips instead of one per entry
             while (gpos < nt && nstaged < kMskTagCap) {
-                const b200ais_tag t = tg[gpos++];
-                if (matches(t)) {
-                    s_tags[nstaged * 32 + lane] =
-                        make_int2((int)(t.offset - nitems_read), __float_as_int((float)t.value));
-                    nstaged++;
+                b200ais_tag t[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    t[j] = tg[min(gpos + j, nt - 1)];
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (gpos + j < nt && nstaged < kMskTagCap) {
+                        used = j + 1;
+                        if (matches(t[j])) {
+                            s_tags[nstaged * 32 + lane] =
+                                make_int2((int)(t[j].offset - nitems_read), __float_as_int((float)t[j].value));
+                            nstaged++;
+                        }
+                    }
                 }
+                gpos += used;
             }
         }
         tag_off = 0x7fffffff;
@@ -675,8 +692,8 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int per_sm = (warps + sms - 1) / sms;
-    // (kind, warps per CTA): 5 x 1, 6 x 1, 1 x 7 or 2 x 7 warps per SM
-    int kind = per_sm <= 5 ? 0 : (per_sm <= 7 ? 1 : 2);
+    // (kind, warps per CTA): 4 x 1, 6 x 1, 1 x 7 or 2 x 7 warps per SM
+    int kind = per_sm <= 4 ? 0 : (per_sm <= 7 ? 1 : 2);
     bool packed = per_sm > 6;
     static int forced = -2;
     if (forced == -2) {

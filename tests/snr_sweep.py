@@ -10,7 +10,7 @@ Reports, for the GPU path and (on a subset of channels) the oracle:
                 (GPU path: b200ais_hdlc_work; oracle: its C restatement)
 and checks the two paths agree bit for bit on the oracle subset.
 
-    python tests/snr_sweep.py --channels 16384 --snrs 0 2 4 6 8 10 12 14 16 18 20
+    python tests/snr_sweep.py --channels 16384 --oracle-channels 1024 --procs 16 --snrs 0 2 4 6 8 10 12 14 16 18 20
 """
 import argparse
 import json
@@ -53,7 +53,7 @@ def _record(c, n, nbursts, snr):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--channels", type=int, default=1024)
-    ap.add_argument("--oracle-channels", type=int, default=64)
+    ap.add_argument("--oracle-channels", type=int, default=1024)
     ap.add_argument("--seconds", type=float, default=0.5)
     ap.add_argument("--snrs", type=float, nargs="+", default=[0, 4, 8, 12, 16, 20])
     ap.add_argument("--threshold", type=float, default=0.9)
@@ -68,6 +68,14 @@ def main():
     from gr_ais_b200.ais_demod import ais_demod, preamble_template
     from oracle import oracle as O
 
+    # the CPU side runs the reference's own block classes (oracle/_ref) when they were built
+    ref_blocks, cpu_kind = None, "oracle port"
+    try:
+        from oracle import ref as R
+        if R.available():
+            ref_blocks, cpu_kind = R.blocks(), "reference blocks (oracle/_ref) in the oracle's schedule"
+    except Exception:
+        pass
     n = int(args.seconds * 48000)
     tmpl = preamble_template("north_star")
     d = ais_demod(channels=args.channels, max_samples=n, template=tmpl, threshold=args.threshold,
@@ -89,7 +97,7 @@ def main():
         det, crc, tot = score(deframer.pdus(frames, nframes), tags, ntags, truth, len(tmpl))
         k = min(args.oracle_channels, args.channels)
         ob, onb, ot, ont = O.demod_chain_batch(x[:k], tmpl, O.chain_cfg(threshold=args.threshold),
-                                               max_tags=1024)
+                                               max_tags=1024, blocks=ref_blocks)
         same = all(onb[c] == nbits[c] and np.array_equal(ob[c, :onb[c]], bits[c, :nbits[c]])
                    and ont[c] == ntags[c]
                    and np.array_equal(ot[c, :ont[c]]["offset"], tags[c, :ntags[c]]["offset"])
@@ -99,7 +107,8 @@ def main():
         odet, ocrc, otot = score(opdus, ot.view(tags.dtype), ont, truth[:k], len(tmpl))
         rows.append(dict(snr_db=snr, bursts=tot, gpu_detect=det / tot, gpu_crc=crc / tot,
                          oracle_bursts=otot, oracle_detect=odet / otot, oracle_crc=ocrc / otot,
-                         gpu_equals_oracle_on_subset=bool(same)))
+                         gpu_equals_oracle_on_subset=bool(same), cpu_path=cpu_kind,
+                         channels=args.channels, oracle_channels=k, seconds=args.seconds))
         print(json.dumps(rows[-1]), flush=True)
     d.close()
     if pool is not None:
