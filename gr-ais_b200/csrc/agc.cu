@@ -408,6 +408,35 @@ k_mix_agc512_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         ph0 = ckpt[(size_t)(n0 >> 4) * channels + c];
         inc = sens * fhat[(size_t)c * vstride + n0 / fftlen];
     }
+    // the NCO of this thread's 16 samples does not need the samples: it runs while the tile is
+    // still in flight (phase recurrence, fixed-point angle, table fetch, sin / cos)
+    float2 osc[16]; // (cos, sin) per sample
+    if (mix) {
+        const float F_PI = 3.14159265358979323846f;
+        const float F_2PI = 2.0f * F_PI;
+        // straight-line fast path and its one range test: see k_mix_agc512 above
+        const bool bad = !(fabsf(inc) <= F_PI && ph0 >= -1.5f * F_2PI && ph0 < F_PI);
+        if (!bad) {
+            float ph = ph0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                ph = nco_step_inrange(ph, inc);
+                const float folded = (ph < -F_PI) ? ph + F_2PI : ph;
+                float sn, cs;
+                fxpt_sincos4_tex(float_to_fixed_inrange(folded), sine_tex, &sn, &cs);
+                osc[k] = make_float2(cs, sn);
+            }
+        } else { // general path (fmod, fold, true division)
+            float ph = ph0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                ph = nco_step(ph, inc);
+                float sn, cs;
+                fxpt_sincos4(float_to_fixed(ph), sine, &sn, &cs);
+                osc[k] = make_float2(cs, sn);
+            }
+        }
+    }
     __syncthreads(); // the barrier's initialisation is visible before anyone polls it
     agc_mbar_wait(bar_s, 0);
     float2 v[16];
@@ -433,30 +462,9 @@ k_mix_agc512_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constan
         }
     }
     if (mix) {
-        const float F_PI = 3.14159265358979323846f;
-        const float F_2PI = 2.0f * F_PI;
-        // straight-line fast path and its one range test: see k_mix_agc512 above
-        const bool bad = !(fabsf(inc) <= F_PI && ph0 >= -1.5f * F_2PI && ph0 < F_PI);
-        if (!bad) {
-            float ph = ph0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                ph = nco_step_inrange(ph, inc);
-                const float folded = (ph < -F_PI) ? ph + F_2PI : ph;
-                float sn, cs;
-                fxpt_sincos4_tex(float_to_fixed_inrange(folded), sine_tex, &sn, &cs);
-                v[k] = cmul_fma(v[k], make_float2(cs, sn));
-            }
-        } else { // general path (fmod, fold, true division)
-            float ph = ph0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                ph = nco_step(ph, inc);
-                float sn, cs;
-                fxpt_sincos4(float_to_fixed(ph), sine, &sn, &cs);
-                v[k] = cmul_fma(v[k], make_float2(cs, sn));
-            }
-        }
+        for (int k = 0; k < 16; k++)
+            v[k] = cmul_fma(v[k], osc[k]);
     }
     if (kHist) { // the last 511 mixed items become the next call's AGC history
 #pragma unroll

@@ -121,25 +121,30 @@ k_sqfft_freqest(const float2 *__restrict__ x, size_t x_stride, int vstride, int 
 // multiply: fma(1,b,-0) = b and fma(0,x,y) = y are exact.
 constexpr int kFast = 64;
 
-__device__ __forceinline__ int fphys(int e) { return e + (e >> 4); } // 1-in-16 padding
+// 1-in-16 padding plus one slot per 64 elements: conflict-free for the pass-A writers (thread
+// tid owns the 16 elements of group bitrev6(tid), so that its loads are coalesced) and for the
+// pass-B / pass-C accesses (16 consecutive `lo` per half-warp)
+__device__ __forceinline__ int fphys(int e) { return e + (e >> 4) + (e >> 6); }
 
+// butterflies in packed FP32 (FFMA2 / FADD2 / FMUL2 on the (re, im) pair, device_math.cuh):
+// the same roundings as the scalar forms, half the issue slots
 __device__ __forceinline__ void bf(float2 &a, float2 &b, const float2 w)
 {
-    const float2 t = cmul_fma(w, b), a0 = a;
-    a = make_float2(a0.x + t.x, a0.y + t.y);
-    b = make_float2(a0.x - t.x, a0.y - t.y);
+    const float2 t = cmul_fma2(w, b), a0 = a;
+    a = f2_add(a0, t);
+    b = f2_sub(a0, t);
 }
 __device__ __forceinline__ void bf_one(float2 &a, float2 &b) // W = (1, 0)
 {
     const float2 t = b, a0 = a;
-    a = make_float2(a0.x + t.x, a0.y + t.y);
-    b = make_float2(a0.x - t.x, a0.y - t.y);
+    a = f2_add(a0, t);
+    b = f2_sub(a0, t);
 }
 __device__ __forceinline__ void bf_mi(float2 &a, float2 &b) // W = (0, -1): t = (b.y, -b.x)
 {
     const float2 a0 = a, b0 = b;
-    a = make_float2(a0.x + b0.y, a0.y - b0.x);
-    b = make_float2(a0.x - b0.y, a0.y + b0.x);
+    a = f2_add(a0, make_float2(b0.y, -b0.x));
+    b = f2_add(a0, make_float2(-b0.y, b0.x));
 }
 
 // three radix-2 stages on 8 register values whose pair distances are 1, 2, 4
@@ -165,7 +170,7 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
     constexpr int N = 1024;
     if (channel_index() >= channels)
         return;
-    __shared__ float2 cx[N + N / 16];
+    __shared__ float2 cx[N + N / 16 + N / 64];
     __shared__ float hs[N];
     __shared__ Best sh[kFast / 32];
     __shared__ float s_max[kFast / 32];
@@ -173,15 +178,17 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
     const int b = blockIdx.x, c = channel_index();
     const float2 *src = x + (size_t)c * x_stride + (size_t)b * N;
 
-    // ---- pass A: stages 1-4 on elements e = 16*tid + q, loaded from x[bitrev10(e)] ----
+    // ---- pass A: stages 1-4 on elements e = 16*t6 + q, loaded from x[bitrev10(e)] =
+    // x[bitrev4(q)*64 + bitrev6(t6)]; thread tid takes the group t6 = bitrev6(tid), so that the
+    // threads of a warp read consecutive items ----
     {
         float2 v[16];
-        const int r6 = (int)(__brev((unsigned)tid) >> 26); // bitrev6(tid)
+        const int t6 = (int)(__brev((unsigned)tid) >> 26); // bitrev6(tid)
 #pragma unroll
         for (int q = 0; q < 16; q++) {
             const int r4 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
-            const float2 in = src[r4 * 64 + r6];
-            v[q] = cmul_fma(in, in); // blocks.multiply_cc(x, x)
+            const float2 in = src[r4 * 64 + tid];
+            v[q] = cmul_fma2(in, in); // blocks.multiply_cc(x, x)
         }
         const float2 w128 = tw[128], w384 = tw[384];
         const float2 w64 = tw[64], w192 = tw[192], w320 = tw[320], w448 = tw[448];
@@ -208,12 +215,20 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
         bf(v[5], v[13], w320);
         bf(v[6], v[14], w384);
         bf(v[7], v[15], w448);
+        const int base = 17 * t6 + (t6 >> 2); // fphys(16*t6 + q) = base + q
 #pragma unroll
         for (int q = 0; q < 16; q++)
-            cx[17 * tid + q] = v[q]; // fphys(16*tid + q)
+            cx[base + q] = v[q];
     }
     __syncthreads();
     // ---- pass B: stages 5-7 on e = hi*128 + q*16 + lo ----
+    // tw[lo << 5], tw[(lo + 16 j) << 4], tw[(lo + 16 j) << 3] from the [slot][lo] copies
+    // behind the table (get_twiddles): a warp's read covers 128 consecutive bytes.  Both of a
+    // thread's groups (g = tid, tid + 64) have the same lo: one set of loads serves them.
+    const int loB = tid & 15;
+    const float2 wB1 = tw[512 + loB];
+    const float2 wB2[2] = { tw[528 + loB], tw[544 + loB] };
+    const float2 wB3[4] = { tw[560 + loB], tw[576 + loB], tw[592 + loB], tw[608 + loB] };
 #pragma unroll 1
     for (int g = tid; g < 128; g += kFast) {
         const int hi = g >> 4, lo = g & 15;
@@ -221,12 +236,7 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
 #pragma unroll
         for (int q = 0; q < 8; q++)
             u[q] = cx[fphys(hi * 128 + q * 16 + lo)];
-        // tw[lo << 5], tw[(lo + 16 j) << 4], tw[(lo + 16 j) << 3] from the [slot][lo] copies
-        // behind the table (get_twiddles): a warp's read covers 128 consecutive bytes
-        const float2 w1 = tw[512 + lo];
-        const float2 w2[2] = { tw[528 + lo], tw[544 + lo] };
-        const float2 w3[4] = { tw[560 + lo], tw[576 + lo], tw[592 + lo], tw[608 + lo] };
-        pass8(u, w1, w2, w3);
+        pass8(u, wB1, wB2, wB3);
 #pragma unroll
         for (int q = 0; q < 8; q++)
             cx[fphys(hi * 128 + q * 16 + lo)] = u[q];
