@@ -133,6 +133,8 @@ class ClockSampler:
 
 
 POOL = 64  # distinct seeded records behind the "independent" batch
+# warp-instructions k_corr_fft executes per input sample, by template length (ncu, see bench note)
+CORR_WIPS = {120: 3.885}
 
 
 def record_plan(args, n, channels, first_channel=0):
@@ -506,6 +508,11 @@ def run_b200(args):
                 "fp32_pipe_floor_ms": fp32_floor_ms,
                 "fp32_pipe_frac": (fp32_floor_ms / corr_ms) if corr_ms > 0 else None,
                 "hbm_frac_at_fp32_pipe_floor": alg_bytes / (fp32_floor_ms * 1e-3) / 1e9 / peak,
+                # instruction-issue ceiling: the kernel executes WIPS warp-instructions per sample (a
+                # property of its code, counted by ncu: smsp__inst_executed.sum / samples of the capture
+                # in profiles/r02_ncu_corr.csv); 148 SMs x 4 schedulers issue one per cycle each
+                "warp_instructions_per_sample": CORR_WIPS.get(taps),
+                "issue_ceiling_frac": (148 * 4 * sm_hz / CORR_WIPS[taps] * 8.0 / 1e9 / peak) if taps in CORR_WIPS else None,
                 "note": "GNU Radio's fft_filter (FFT overlap-add, fftsize %d, %d items per block) costs %d FP32 lane-operations "
                         "per 8-byte sample: at %.0f MHz the FP32 pipe alone holds the kernel to %.2f ms = the "
                         "hbm_frac_at_fp32_pipe_floor above, so the kernel is bound by the FP32 pipe / instruction issue, "

@@ -99,7 +99,10 @@ __device__ __forceinline__ float2 w16(int k)
 
 // one pass: R radix-2 stages on index bits [S0, S0+R), forward DIF or inverse DIT
 // twr: the pass's 15 twiddles of this thread in registers (TWREG: they do not depend on the block)
-template <int LOGF, int S0, int R, bool INV, bool TWREG = false>
+// ZQ: slots ZQ .. 15 hold zero padding on entry (forward top pass with a compile-time tap count):
+// the first stage's butterflies on them are a' = a + 0, b' = W (a - 0), so only the product is
+// computed (a' keeps a: the value is the same, and a zero keeps its own sign instead of +0)
+template <int LOGF, int S0, int R, bool INV, bool TWREG = false, int ZQ = 16>
 __device__ __forceinline__ void run_pass(float2 (&v)[16], int t, const float4 *__restrict__ twp,
                                          const float2 (&twr)[15])
 {
@@ -120,6 +123,10 @@ __device__ __forceinline__ void run_pass(float2 (&v)[16], int t, const float4 *_
                 const int k16 = jq << (3 - bq);
                 float2 &a = v[g * Q + q], &b = v[g * Q + q1];
                 const float2 a0 = a, b0 = b;
+                if (!INV && st == 0 && g * Q + q1 >= ZQ && TWREG) { // b0 == 0: b' = W a, a' = a
+                    b = cmul_fma2(twr[((1 << bq) - 1) + jq], a0);
+                    continue;
+                }
                 if (S0 == 0 && k16 == 0) { // W = 1
                     a = f2_add(a0, b0);
                     b = f2_sub(a0, b0);
@@ -185,7 +192,7 @@ __device__ __forceinline__ void from_smem(float2 (&v)[16], int t, const float2 *
 
 // forward transform, multiply by the taps spectrum, inverse transform; v enters and leaves in
 // the top-pass mapping (element t + NT*q in slot q)
-template <int LOGF>
+template <int LOGF, int ZQ>
 __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float4 *__restrict__ twp,
                                              const float2 (&twr)[15], const float4 *__restrict__ h4,
                                              float2 *xb)
@@ -205,7 +212,7 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
                          "r"(Plan<LOGF>::NT));
     };
     // ---- forward, top bits first ----
-    run_pass<LOGF, TOP, 4, false, TR>(v, t, twp, twr);
+    run_pass<LOGF, TOP, 4, false, TR, ZQ>(v, t, twp, twr);
     if constexpr (NP >= 2) {
         to_smem<TOP, 4>(v, t, xb);
         xsync();
@@ -444,7 +451,9 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
         } else {
             fetch(v, b);
         }
-        block_filter<LOGF>(v, t, s_twp, twr, reinterpret_cast<const float4 *>(s_h), xb);
+        // slots whose smallest element t + NT q is zero padding for every thread: q >= ns / NT
+        constexpr int ZQ = LT ? ((P::F - LT + 1) + NT - 1) / NT : 16;
+        block_filter<LOGF, ZQ>(v, t, s_twp, twr, reinterpret_cast<const float4 *>(s_h), xb);
         // stash this block's tail (outputs ns .. F-1) for the next block
         float2 *my_tail = g < GROUPS - 1 ? s_tail + ((r & 1) * (GROUPS - 1) + g) * tl : s_last + (r % 3) * tl;
 #pragma unroll

@@ -104,44 +104,68 @@ template <int RING> __device__ __forceinline__ int ring_pos(int iidx)
 // One half-symbol step from the row index imu (:170-201 without the tag test): interpolate,
 // error detector, loop filter on odd steps, output on even steps, advance.  ring4: this lane's
 // column of the 16-byte-unit ring.  Returns x = mu + omega before the floor.
-template <bool kDebug>
+// WIDE: the eight samples come as five 16-byte loads and an odd / even select (fewest shared-
+// memory wavefronts: the choice when many warps share an SM); otherwise as eight 8-byte loads at
+// the samples' own addresses (13 fewer instructions on a step whose cost is its instruction
+// count when a warp has a scheduler to itself).  The arithmetic is packed FP32 on the (re, im)
+// pairs (device_math.cuh): same roundings as the scalar forms in the comments.
+template <bool kDebug, bool WIDE>
 __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *__restrict__ ring4,
                                           const float *__restrict__ s_mmse, const MskParams &p,
                                           float *oe, float *om)
 {
     // mmse_fir_interpolator_cc::interpolate: in[0..7] . reversed row.  The 8 samples start at
-    // ring sample rpos: five 16-byte units (conflict-free: the lane picks the banks), then the
-    // odd/even start is a select
-    const int u0 = L.rpos >> 1;
-    const bool par = L.rpos & 1;
+    // ring sample rpos (conflict-free: the lane picks the banks).
     // the table is kept as two arrays of half rows (16 bytes each): a row index then spreads the
     // lanes over all eight 16-byte bank groups instead of four
     const float4 ta = reinterpret_cast<const float4 *>(s_mmse)[imu_c];
     const float4 tb = reinterpret_cast<const float4 *>(s_mmse)[132 + imu_c];
-    const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
-    const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
-    const float2 s0 = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
-    const float2 s1 = par ? make_float2(U1.x, U1.y) : make_float2(U0.z, U0.w);
-    const float2 s2 = par ? make_float2(U1.z, U1.w) : make_float2(U1.x, U1.y);
-    const float2 s3 = par ? make_float2(U2.x, U2.y) : make_float2(U1.z, U1.w);
-    const float2 s4 = par ? make_float2(U2.z, U2.w) : make_float2(U2.x, U2.y);
-    const float2 s5 = par ? make_float2(U3.x, U3.y) : make_float2(U2.z, U2.w);
-    const float2 s6 = par ? make_float2(U3.z, U3.w) : make_float2(U3.x, U3.y);
-    const float2 s7 = par ? make_float2(U4.x, U4.y) : make_float2(U3.z, U3.w);
-    // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3)
-    const float p0r = __fmaf_rn(s4.x, ta.w, s0.x * tb.w), p0i = __fmaf_rn(s4.y, ta.w, s0.y * tb.w);
-    const float p1r = __fmaf_rn(s5.x, ta.z, s1.x * tb.z), p1i = __fmaf_rn(s5.y, ta.z, s1.y * tb.z);
-    const float p2r = __fmaf_rn(s6.x, ta.y, s2.x * tb.y), p2i = __fmaf_rn(s6.y, ta.y, s2.y * tb.y);
-    const float p3r = __fmaf_rn(s7.x, ta.x, s3.x * tb.x), p3i = __fmaf_rn(s7.y, ta.x, s3.y * tb.x);
-    float2 v;
-    v.x = (p0r + p1r) + (p2r + p3r);
-    v.y = (p0i + p1i) + (p2i + p3i);
+    float2 s0, s1, s2, s3, s4, s5, s6, s7;
+    if (WIDE) {
+        const int u0 = L.rpos >> 1;
+        const bool par = L.rpos & 1;
+        const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
+        const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
+        s0 = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
+        s1 = par ? make_float2(U1.x, U1.y) : make_float2(U0.z, U0.w);
+        s2 = par ? make_float2(U1.z, U1.w) : make_float2(U1.x, U1.y);
+        s3 = par ? make_float2(U2.x, U2.y) : make_float2(U1.z, U1.w);
+        s4 = par ? make_float2(U2.z, U2.w) : make_float2(U2.x, U2.y);
+        s5 = par ? make_float2(U3.x, U3.y) : make_float2(U2.z, U2.w);
+        s6 = par ? make_float2(U3.z, U3.w) : make_float2(U3.x, U3.y);
+        s7 = par ? make_float2(U4.x, U4.y) : make_float2(U3.z, U3.w);
+    } else {
+        // sample k of the lane sits at byte ((k >> 1) * 32) * 16 + (k & 1) * 8 of its column
+        const unsigned char *col = reinterpret_cast<const unsigned char *>(ring4);
+        const unsigned char *q0 = col + (L.rpos >> 1) * 512 + (L.rpos & 1) * 8; // sample rpos
+        const unsigned char *q1 = col + ((L.rpos + 1) >> 1) * 512 + ((L.rpos + 1) & 1) * 8; // sample rpos + 1
+        s0 = *reinterpret_cast<const float2 *>(q0);
+        s1 = *reinterpret_cast<const float2 *>(q1);
+        s2 = *reinterpret_cast<const float2 *>(q0 + 512);
+        s3 = *reinterpret_cast<const float2 *>(q1 + 512);
+        s4 = *reinterpret_cast<const float2 *>(q0 + 1024);
+        s5 = *reinterpret_cast<const float2 *>(q1 + 1024);
+        s6 = *reinterpret_cast<const float2 *>(q0 + 1536);
+        s7 = *reinterpret_cast<const float2 *>(q1 + 1536);
+    }
+    // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3), re and im side by side
+    const float2 p0 = f2_fma(s4, make_float2(ta.w, ta.w), f2_mul(s0, make_float2(tb.w, tb.w)));
+    const float2 p1 = f2_fma(s5, make_float2(ta.z, ta.z), f2_mul(s1, make_float2(tb.z, tb.z)));
+    const float2 p2 = f2_fma(s6, make_float2(ta.y, ta.y), f2_mul(s2, make_float2(tb.y, tb.y)));
+    const float2 p3 = f2_fma(s7, make_float2(ta.x, ta.x), f2_mul(s3, make_float2(tb.x, tb.x)));
+    const float2 v = f2_add(f2_add(p0, p1), f2_add(p2, p3));
     // std::complex arithmetic as GCC emits it: (ac - bd, ad + bc), no contraction
+    //   sq = v*v:            (v.x*v.x - v.y*v.y, v.x*v.y + v.y*v.x)
+    //   nl = sq*conj(dly2^2): (sq_re*d_re - sq_im*d_im, sq_re*d_im + sq_im*d_re)
+    const float2 m = f2_mul(v, v);
     const float vxy = v.x * v.y;
-    const float sq_re = v.x * v.x - v.y * v.y, sq_im = vxy + vxy;
+    const float sq_re = m.x - m.y, sq_im = vxy + vxy;
     const float d_re = L.psq_re, d_im = -L.psq_im;
-    const float nl_re = sq_re * d_re - sq_im * d_im;
-    const float nl_im = sq_re * d_im + sq_im * d_re;
+    const float2 A = f2_mul(make_float2(d_re, d_im), make_float2(sq_re, sq_re));
+    const float2 Bp = f2_mul(make_float2(d_im, d_re), make_float2(sq_im, sq_im));
+    // scalar adds on purpose: ptxas 12.9 contracts mul.rn.f32x2 -> add.rn.f32x2 into one FFMA2
+    // (even under -fmad=false), which would drop the rounding of the product
+    const float nl_re = A.x - Bp.x, nl_im = A.y + Bp.y;
     const float err_raw = nl_re - L.diff1_re;
     // odd half-steps run the loop filter (:179-184); evaluated always, selected by parity
     const bool odd = L.div & 1;
@@ -395,7 +419,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             for (int it = 0; it < kMskFast; it++) {
                 const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
                 L.bad_imu |= (imu_c != (unsigned)imu);
-                const float x = msk_step<kDebug>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug, KIND != 0>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
                 const int fl_i = __float2int_rd(x);
                 imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
                 L.iidx += fl_i;
@@ -432,7 +456,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 const int imu = __float2int_rn(L.mu * 128.0f);
                 const int imu_c = min(max(imu, 0), 128);
                 L.bad_imu |= (imu != imu_c);
-                const float x = msk_step<kDebug>(L, imu_c, ring4, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug, KIND != 0>(L, imu_c, ring4, s_mmse, p, oe, om);
                 const float fl = floorf(x);
                 L.iidx += (int)fl;
                 L.rpos = ring_pos<kMskRing>(L.iidx);
@@ -673,7 +697,7 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
                const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
                float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
-               int require_unbounded, int *status, int *unconsumed, cudaStream_t s)
+               int require_unbounded, int *status, int *unconsumed, cudaStream_t s, int share_sm)
 {
     if (channels <= 0)
         return B200AIS_OK;
@@ -700,10 +724,16 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
         const char *e = getenv("B200AIS_MSK_KIND");
         forced = (e && *e) ? atoi(e) : -1;
     }
+    // share_sm: the loop runs on a side stream under the next record's front kernels (pipelined
+    // submission): the smallest ring leaves them the shared memory they need, and what the small
+    // ring costs the loop itself (exposed DRAM latency at low occupancy) is hidden under them
+    if (share_sm && kind < 2 && advmax + 8 <= MskCfg<2>::Need)
+        kind = 2;
     if (forced >= 0 && forced <= 2) {
         kind = forced;
         packed = kind == 2 || (kind == 1 && per_sm > 6);
     }
+    const bool small_spread = kind == 2 && per_sm <= 7; // one warp per CTA: every SM gets its share
     // a round must be able to make one step inside the ring's ready window
     if (kind == 2 && !(advmax + 8 <= MskCfg<2>::Need)) {
         kind = 1;
@@ -742,6 +772,8 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
             B200_MSK(DBG, 1, 1);                                                                   \
         else if (kind == 1)                                                                        \
             B200_MSK(DBG, 1, 7);                                                                   \
+        else if (small_spread)                                                                     \
+            B200_MSK(DBG, 2, 1);                                                                   \
         else                                                                                       \
             B200_MSK(DBG, 2, 7);                                                                   \
     } while (0)

@@ -137,5 +137,9 @@ class ais_rx:
         order = np.lexsort((msgs["end_bit"], msgs["channel"]))
         return msgs[order], [got_s[i] for i in order], items.value
 
+    def tag_overflows(self):
+        """calls in which a channel met more corr_est tags than its row holds (extra tags dropped)"""
+        return int(B.lib().b200ais_rx_tag_overflows(self._h))
+
     def status(self):
         B.check(B.lib().b200ais_rx_status(self._h))

@@ -221,6 +221,27 @@ def test_ais_rx_end_to_end_matches_oracle_and_decodes_truth(oracle, rate, pieces
             assert text.startswith("!AIVDM,1,1,,%s," % des[c])
 
 
+def test_ais_rx_dense_traffic_30_bursts_per_second(oracle):
+    """A busy port: 30 bursts in one second on each AIS channel, one 240 000-item
+    call.  Every burst brings about six detections = 24 tags, far beyond the 256-tag row round 1
+    hard-coded: the row is now sized from the call, nothing overflows, and messages, positions
+    and sentences equal the oracle's."""
+    from gr_ais_b200.radio import ais_rx
+    from gr_ais_b200.ais_demod import preamble_template
+    rate, n = 240e3, 240000
+    freqs, des = [-25e3, 25e3], ["A", "B"]
+    x, truth = synth.make_wideband(77, rate, n, nbursts=30, snr_db=25.0, freqs=freqs)
+    rx = ais_rx(freqs, rate, des, sources=1, max_input_items=n, max_frames=64)
+    msgs, sents = rx.work(x.reshape(1, -1))
+    assert rx.tag_overflows() == 0
+    got = sorted((int(m["channel"]), int(m["end_bit"]), bytes(m["data"][:m["len"]]), s)
+                 for m, s in zip(msgs, sents))
+    want = sorted(oracle_ais_rx(oracle, x, rate, freqs, des, [n], preamble_template("north_star", 5)))
+    assert got == want
+    sent = {(t["channel"], t["payload"]) for t in truth}
+    assert len(sent) == 60 and len(sent & {(c, p) for c, _, p, _ in got}) >= 50
+
+
 def test_xlat_set_taps_and_argument_errors(oracle):
     import ctypes as C
     rate, D = 250e3, 5
