@@ -1031,7 +1031,11 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     // msk reads corr_est output 0: out0[k] = in[k - L] (history delay), zeros for k < L
     rc = launch_msk(a_rows - h->L, h->a_stride, cn, max_bits, n2, 0, tags, h->max_tags, ntags,
                     h->mp, h->d_state + c0, t_sym, t_err, t_mu, (size_t)max_bits, nbits,
-                    h->d_ncons + c0, 1, d_status, nullptr, s, back != nullptr);
+                    h->d_ncons + c0, 1, d_status, nullptr, s,
+                    // pipelined submission: the loop shares the SMs with the next record's front
+                    // kernels.  The small ring that lets them in costs a lone warp ~7 ms whatever
+                    // the batch, so it only pays when that front is longer (whole chain, >= 12 k channels)
+                    back != nullptr && cn >= 12288 && fs && (cfg.stages & B200AIS_STAGE_AGC));
     B200_MARK(B200AIS_STAGE_T_MSK);
     if (!rc)
         rc = launch_tail(t_sym, (size_t)max_bits, nbits, cn, max_bits, bits, (size_t)max_bits, t_soft, nullptr, s);
