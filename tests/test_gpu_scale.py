@@ -85,3 +85,67 @@ def test_grid_z_split_above_65535_channels(oracle):
             assert nbits[base + p] == nbits[p]
             assert np.array_equal(bits[base + p, :nbits[p]], bits[p, :nbits[p]])
             same_tags(tags[base + p, :ntags[base + p]], tags[p, :ntags[p]])
+
+
+@pytest.mark.parametrize("C", [24000, 32000])
+def test_timing_loop_geometries_between_the_configs(oracle, C):
+    """The timing loop picks its shared-memory ring from the channel count: 24 000 channels run the
+    96-sample ring with one warp per CTA (6 warps per SM), 32 000 (BASELINE configs[3]'s per-GPU
+    batch) the same ring with 7 warps behind one table.  (4096 / 16 384 channels above take the
+    128-sample ring, 65 600 the 48-sample one.)"""
+    n = 4096
+    tmpl = preamble_template("north_star")
+    x, pid, off = build_batch(C, n, 16, 600, snr_db=18.0)
+    d = ais_demod(channels=C, max_samples=n, template=tmpl)
+    bits, nbits, tags, ntags = d.work(x)
+    d.close()
+    sample = list(range(0, 16)) + list(range(C - 40, C)) + list(range(7, C, C // 200))
+    assert len(sample) >= 256
+    check_against_oracle(oracle, x, tmpl, bits, nbits, tags, ntags, sample,
+                         oracle.STAGE_FREQSYNC | oracle.STAGE_AGC)
+
+
+def test_pipelined_submission_with_the_small_ring_equals_strict_calls():
+    """enqueue_dev on >= 12 288 channels runs the timing loop with the 48-sample ring on the side
+    stream (it shares the SMs with the next record's front kernels); work_dev on the same handle
+    takes the 128-sample ring.  Record by record the bits, counts and tags must be the same."""
+    torch = pytest.importorskip("torch")
+    C, n, K = 12320, 8192, 3
+    tmpl = preamble_template("north_star")
+    recs = [build_batch(C, n, 16, 700 + k, snr_db=18.0)[0] for k in range(K)]
+    d = ais_demod(channels=C, max_samples=n, template=tmpl)
+    mb = d.max_bits(n)
+    st = torch.cuda.Stream()
+    xs = [torch.from_numpy(r.view(np.float32).reshape(C, n, 2)).cuda() for r in recs]
+
+    def buffers():
+        return (torch.zeros((C, mb), dtype=torch.uint8, device="cuda"),
+                torch.zeros(C, dtype=torch.int32, device="cuda"),
+                torch.zeros((C, d.max_tags, 24), dtype=torch.uint8, device="cuda"),
+                torch.zeros(C, dtype=torch.int32, device="cuda"))
+    ref = []
+    for k in range(K):
+        b = buffers()
+        d.work_dev(xs[k].data_ptr(), n, b[0].data_ptr(), mb, b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
+                   st.cuda_stream)
+        st.synchronize()
+        d.status()
+        ref.append([t.cpu().numpy() for t in b])
+    outs = []
+    for k in range(K):
+        b = buffers()
+        d.enqueue_dev(xs[k].data_ptr(), n, b[0].data_ptr(), mb, b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr(),
+                      st.cuda_stream)
+        outs.append(b)
+    d.join(st.cuda_stream)
+    st.synchronize()
+    d.status()
+    for k in range(K):
+        bits, nb, tg, nt = (t.cpu().numpy() for t in outs[k])
+        rb, rn, rt, rnt = ref[k]
+        assert np.array_equal(nb, rn) and np.array_equal(nt, rnt), k
+        assert int(nt.sum()) > 0
+        for c in range(0, C, 7):
+            assert np.array_equal(bits[c, :nb[c]], rb[c, :nb[c]]), (k, c)
+            assert np.array_equal(tg[c, :nt[c]], rt[c, :nt[c]]), (k, c)
+    d.close()
