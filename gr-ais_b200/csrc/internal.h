@@ -89,6 +89,8 @@ struct MskParams {
     float sps_half; // d_sps
     float gain, gain_omega, limit;
     int osps;
+    int pair_fetch; // experiments: B200AIS_MSK_NO_PAIR_FETCH=1
+    int no_slide; // experiments: B200AIS_MSK_NO_SLIDE=1 turns the sliding-window round off
 };
 
 // Per-channel loop state of msk_timing_recovery_cc (lib/msk_timing_recovery_cc_impl.h:37-46)

@@ -82,6 +82,7 @@ __device__ __forceinline__ void cp_async_16(unsigned smem, const void *gmem, int
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 // Loop registers of one channel (lib/msk_timing_recovery_cc_impl.h:37-46), in registers.
 struct MskLane {
@@ -92,6 +93,8 @@ struct MskLane {
     int div, iidx, oidx;
     int rpos;                 // iidx mod kMskRing
     float2 *op;               // next symbol slot
+    float2 hold;              // a symbol waiting for its neighbour: pairs go out as one 16-byte store
+    bool have_hold;
     bool bad_imu;
 };
 
@@ -109,45 +112,59 @@ template <int RING> __device__ __forceinline__ int ring_pos(int iidx)
 // the samples' own addresses (13 fewer instructions on a step whose cost is its instruction
 // count when a warp has a scheduler to itself).  The arithmetic is packed FP32 on the (re, im)
 // pairs (device_math.cuh): same roundings as the scalar forms in the comments.
-template <bool kDebug, bool WIDE>
-__device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *__restrict__ ring4,
+// The eight samples in[rpos .. rpos+7] of a lane's ring.
+// WIDE: five 16-byte loads and an odd / even select (fewest shared-memory wavefronts: the choice
+// when many warps share an SM); otherwise eight 8-byte loads at the samples' own addresses (13
+// fewer instructions on a step whose cost is its instruction count when a warp has a scheduler
+// to itself).
+template <bool WIDE>
+__device__ __forceinline__ void msk_load_window(const float4 *__restrict__ ring4, int rpos, float2 (&s)[8])
+{
+    if (WIDE) {
+        const int u0 = rpos >> 1;
+        const bool par = rpos & 1;
+        const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
+        const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
+        s[0] = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
+        s[1] = par ? make_float2(U1.x, U1.y) : make_float2(U0.z, U0.w);
+        s[2] = par ? make_float2(U1.z, U1.w) : make_float2(U1.x, U1.y);
+        s[3] = par ? make_float2(U2.x, U2.y) : make_float2(U1.z, U1.w);
+        s[4] = par ? make_float2(U2.z, U2.w) : make_float2(U2.x, U2.y);
+        s[5] = par ? make_float2(U3.x, U3.y) : make_float2(U2.z, U2.w);
+        s[6] = par ? make_float2(U3.z, U3.w) : make_float2(U3.x, U3.y);
+        s[7] = par ? make_float2(U4.x, U4.y) : make_float2(U3.z, U3.w);
+    } else {
+        // sample k of the lane sits at byte ((k >> 1) * 32) * 16 + (k & 1) * 8 of its column
+        const unsigned char *col = reinterpret_cast<const unsigned char *>(ring4);
+        const unsigned char *q0 = col + (rpos >> 1) * 512 + (rpos & 1) * 8; // sample rpos
+        const unsigned char *q1 = col + ((rpos + 1) >> 1) * 512 + ((rpos + 1) & 1) * 8; // sample rpos + 1
+        s[0] = *reinterpret_cast<const float2 *>(q0);
+        s[1] = *reinterpret_cast<const float2 *>(q1);
+        s[2] = *reinterpret_cast<const float2 *>(q0 + 512);
+        s[3] = *reinterpret_cast<const float2 *>(q1 + 512);
+        s[4] = *reinterpret_cast<const float2 *>(q0 + 1024);
+        s[5] = *reinterpret_cast<const float2 *>(q1 + 1024);
+        s[6] = *reinterpret_cast<const float2 *>(q0 + 1536);
+        s[7] = *reinterpret_cast<const float2 *>(q1 + 1536);
+    }
+}
+
+// One half-symbol step from the row index imu (:170-201 without the tag test) on the eight
+// samples s[] = in[iidx .. iidx+7]: interpolate, error detector, loop filter on odd steps, output
+// on even steps.  Returns x = mu + omega before the floor.  The arithmetic is packed FP32 on the
+// (re, im) pairs (device_math.cuh): same roundings as the scalar forms in the comments.
+// DEFER: the caller stores the symbols (the straight-line round: one symbol per two steps).
+template <bool kDebug, bool PAIR, bool DEFER = false>
+__device__ __forceinline__ float msk_core(MskLane &L, int imu_c, const float2 (&s)[8],
                                           const float *__restrict__ s_mmse, const MskParams &p,
                                           float *oe, float *om)
 {
-    // mmse_fir_interpolator_cc::interpolate: in[0..7] . reversed row.  The 8 samples start at
-    // ring sample rpos (conflict-free: the lane picks the banks).
+    // mmse_fir_interpolator_cc::interpolate: in[0..7] . reversed row.
     // the table is kept as two arrays of half rows (16 bytes each): a row index then spreads the
     // lanes over all eight 16-byte bank groups instead of four
     const float4 ta = reinterpret_cast<const float4 *>(s_mmse)[imu_c];
     const float4 tb = reinterpret_cast<const float4 *>(s_mmse)[132 + imu_c];
-    float2 s0, s1, s2, s3, s4, s5, s6, s7;
-    if (WIDE) {
-        const int u0 = L.rpos >> 1;
-        const bool par = L.rpos & 1;
-        const float4 U0 = ring4[(u0 + 0) * 32], U1 = ring4[(u0 + 1) * 32], U2 = ring4[(u0 + 2) * 32];
-        const float4 U3 = ring4[(u0 + 3) * 32], U4 = ring4[(u0 + 4) * 32];
-        s0 = par ? make_float2(U0.z, U0.w) : make_float2(U0.x, U0.y);
-        s1 = par ? make_float2(U1.x, U1.y) : make_float2(U0.z, U0.w);
-        s2 = par ? make_float2(U1.z, U1.w) : make_float2(U1.x, U1.y);
-        s3 = par ? make_float2(U2.x, U2.y) : make_float2(U1.z, U1.w);
-        s4 = par ? make_float2(U2.z, U2.w) : make_float2(U2.x, U2.y);
-        s5 = par ? make_float2(U3.x, U3.y) : make_float2(U2.z, U2.w);
-        s6 = par ? make_float2(U3.z, U3.w) : make_float2(U3.x, U3.y);
-        s7 = par ? make_float2(U4.x, U4.y) : make_float2(U3.z, U3.w);
-    } else {
-        // sample k of the lane sits at byte ((k >> 1) * 32) * 16 + (k & 1) * 8 of its column
-        const unsigned char *col = reinterpret_cast<const unsigned char *>(ring4);
-        const unsigned char *q0 = col + (L.rpos >> 1) * 512 + (L.rpos & 1) * 8; // sample rpos
-        const unsigned char *q1 = col + ((L.rpos + 1) >> 1) * 512 + ((L.rpos + 1) & 1) * 8; // sample rpos + 1
-        s0 = *reinterpret_cast<const float2 *>(q0);
-        s1 = *reinterpret_cast<const float2 *>(q1);
-        s2 = *reinterpret_cast<const float2 *>(q0 + 512);
-        s3 = *reinterpret_cast<const float2 *>(q1 + 512);
-        s4 = *reinterpret_cast<const float2 *>(q0 + 1024);
-        s5 = *reinterpret_cast<const float2 *>(q1 + 1024);
-        s6 = *reinterpret_cast<const float2 *>(q0 + 1536);
-        s7 = *reinterpret_cast<const float2 *>(q1 + 1536);
-    }
+    const float2 s0 = s[0], s1 = s[1], s2 = s[2], s3 = s[3], s4 = s[4], s5 = s[5], s6 = s[6], s7 = s[7];
     // p_j = in[j]*T[7-j] (+fused) in[j+4]*T[3-j]; v = (p0+p1)+(p2+p3), re and im side by side
     const float2 p0 = f2_fma(s4, make_float2(ta.w, ta.w), f2_mul(s0, make_float2(tb.w, tb.w)));
     const float2 p1 = f2_fma(s5, make_float2(ta.z, ta.z), f2_mul(s1, make_float2(tb.z, tb.z)));
@@ -175,8 +192,21 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
     const float mu_n = L.mu + p.gain * err_c;
     L.omega = odd ? om_n : L.omega;
     L.mu = odd ? mu_n : L.mu;
-    if (!odd || p.osps == 2) {
-        *L.op = v;
+    if (!DEFER && (!odd || p.osps == 2)) {
+        // a lane's symbols go to its own row, one 32-byte sector per store whatever its size: two
+        // symbols per store halve the requests the SM sends to L2
+        if (PAIR) {
+            const bool al = (reinterpret_cast<uintptr_t>(L.op) & 15) == 0;
+            const bool st4 = L.have_hold, st2 = !L.have_hold && !al;
+            if (st4)
+                *reinterpret_cast<float4 *>(L.op - 1) = make_float4(L.hold.x, L.hold.y, v.x, v.y);
+            if (st2)
+                *L.op = v;
+            L.hold = v;
+            L.have_hold = !st4 && !st2;
+        } else {
+            *L.op = v;
+        }
         L.op++;
         if (kDebug) {
             if (oe)
@@ -193,6 +223,17 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
     L.diff1_re = nl_re;
     L.diff1_im = nl_im;
     return L.mu + L.omega;
+}
+
+// ring4: this lane's column of the 16-byte-unit ring (conflict-free: the lane picks the banks).
+template <bool kDebug, bool WIDE, bool PAIR>
+__device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *__restrict__ ring4,
+                                          const float *__restrict__ s_mmse, const MskParams &p,
+                                          float *oe, float *om)
+{
+    float2 s[8];
+    msk_load_window<WIDE>(ring4, L.rpos, s);
+    return msk_core<kDebug, PAIR>(L, imu_c, s, s_mmse, p, oe, om);
 }
 
 // The serial core of msk_timing_recovery_cc: one lane per channel.  A channel's loop is a
@@ -338,14 +379,19 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     L.rpos = mis;
     L.oidx = 0;
     L.op = oc;
+    L.hold = make_float2(0.0f, 0.0f);
+    L.have_hold = false;
     L.bad_imu = false;
 
     int issue_end = 0; // samples [0, issue_end) of this lane's channel have been requested
     int issue_u = 0;   // ring unit the next chunk goes to (0, 8, 16)
     int ready_end = 0; // samples [0, ready_end) are known to have landed
+    bool in_last = false; // this lane has a chunk in the newest cp.async group
     int err_code = 0;
     bool active = true;
-    const unsigned FULL = __activemask(); // the lanes that own a channel (a prefix of the warp)
+    const unsigned FULL = __activemask(); // the lanes that run the loop
+    const bool pair_ok = p.pair_fetch && ((FULL >> (lane ^ 1)) & 1u); // the neighbour lane runs it too
+    const unsigned pair_m = __ballot_sync(FULL, pair_ok);
 
     // One step advances the read index by floor(mu + omega) <= advmax items.  A round may touch
     // kMskNeed samples: the straight-line round needs kMskFast steps' worth of them, the careful
@@ -354,6 +400,10 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     const int fast_in = kMskFast * advmax;
     const bool fast_ok = advmax >= 1 && fast_in + 8 <= kMskNeed && 3.0f * p.gain < 0.5f;
     const int inner = max(1, min(kMskInner, (kMskNeed - 8) / max(advmax, 1)));
+    // every straight-line step advances by exactly 2 or 3 items (x = mu + omega after the loop
+    // filter lies in [sps/2 - limit - 3 gain, 1 + 3 gain + sps/2 + limit)): the sliding-window round
+    const bool slide_ok = fast_ok && advmax == 3 && p.sps_half - fabsf(p.limit) - 3.0f * p.gain >= 2.001f &&
+                          p.osps == 1 && !p.no_slide;
 
     // cp.async groups are tracked per warp, not per lane, so requests and waits happen in
     // warp-wide rounds, decided by one warp-wide OR per round: a round first waits (only for
@@ -378,16 +428,57 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             break;
         bool starved = false;
         if (any & 2u) {
-            cp_async_wait_all();
-            ready_end = issue_end;
-            starved = __any_sync(FULL, active && (L.iidx + kMskNeed > ready_end));
+            // all but the newest group (the last round's requests, which may still be on their
+            // way from DRAM): a lane asks for a chunk a round before it reads it, so that is
+            // nearly always enough
+            cp_async_wait_but_last();
+            ready_end = in_last ? issue_end - kMskChunk : issue_end;
+            if (__any_sync(FULL, active && (L.iidx + kMskNeed > ready_end))) {
+                cp_async_wait_all();
+                ready_end = issue_end;
+                in_last = false;
+                starved = __any_sync(FULL, active && (L.iidx + kMskNeed > ready_end));
+            }
         }
         if (any & 4u) {
+            // Lanes 2k and 2k+1 fetch their chunks together: one instruction moves one 32-byte
+            // sector of the even lane's chunk (16 bytes per lane), the next one of the odd
+            // lane's, so the SM sends one request per sector to L2 instead of two -- the
+            // L1 -> crossbar request port is what a full wave of this kernel fills.
+            const bool coop = want && row16 && issue_end + kMskChunk <= ninput_items;
+            const unsigned coop_m = __ballot_sync(FULL, coop);
+            const bool mc = pair_ok && coop;
+            if (p.pair_fetch && (coop_m & pair_m)) {
+                const float2 *my_src = row + issue_end;
+                const unsigned long long sp = __shfl_xor_sync(FULL, (unsigned long long)(uintptr_t)my_src, 1);
+                const int pu = __shfl_xor_sync(FULL, issue_u, 1);
+                const bool pc = pair_ok && ((coop_m >> (lane ^ 1)) & 1u);
+                const int half = lane & 1;
+#pragma unroll
+                for (int w = 0; w < 2; w++) { // w = 0: the even lane's chunk, 1: the odd lane's
+                    const bool mine = half == w;
+                    if (mine ? mc : pc) {
+                        const float2 *src = mine ? my_src : reinterpret_cast<const float2 *>((uintptr_t)sp);
+                        const int u0 = mine ? issue_u : pu;
+                        const unsigned col = mine ? my_s : (half ? my_s - 16 : my_s + 16);
+#pragma unroll
+                        for (int i = 0; i < kMskChunk / 4; i++)
+                            cp_async_16(col + (u0 + 2 * i + half) * 512, src + 2 * (2 * i + half), 16);
+                        if (u0 == 0) {
+#pragma unroll
+                            for (int i = 0; i < kMskMirror / 4; i++)
+                                cp_async_16(col + (kMskRing / 2 + 2 * i + half) * 512, src + 2 * (2 * i + half), 16);
+                        }
+                    }
+                }
+            }
             if (want) {
                 const unsigned dst = my_s + issue_u * 512;
                 const float2 *src = row + issue_end;
                 const bool first = issue_u == 0; // also feeds the mirror units
-                if (row16 && issue_end + kMskChunk <= ninput_items) {
+                if (mc) {
+                    // fetched with the partner lane below
+                } else if (row16 && issue_end + kMskChunk <= ninput_items) {
 #pragma unroll
                     for (int u = 0; u < kMskChunk / 2; u++)
                         cp_async_16(dst + 512 * u, src + 2 * u, 16);
@@ -408,6 +499,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 issue_end += kMskChunk;
                 issue_u = issue_u + kMskChunk / 2 == kMskRing / 2 ? 0 : issue_u + kMskChunk / 2;
             }
+            in_last = want;
             cp_async_commit();
         }
         if (starved)
@@ -415,11 +507,95 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
         if (!(any & 8u)) {
             // ---- straight-line round: every lane runs kMskFast steps ----
             int imu = __float2int_rn(L.mu * 128.0f);
+            if (slide_ok) {
+                // Every step advances by 2 or 3 items here, so the eight samples stay in
+                // registers: a step shifts the window by its advance and takes the two or three
+                // new samples from loads issued BEFORE the step (they depend on the old index
+                // only).  The ring is read once per sample instead of ~3 times, and the
+                // advance -> address -> load round trip leaves the loop's critical path.
+                float2 W[8];
+                msk_load_window<KIND != 0>(ring4, L.rpos, W);
+                const unsigned char *col = reinterpret_cast<const unsigned char *>(ring4);
+                // Of two consecutive steps exactly one gives a symbol (the one whose count is
+                // even), so the round stores one symbol per two steps, picked by the lane's
+                // parity: no test per step.  (Debug builds keep the per-step form: they also
+                // write the error and mu streams.)
+                constexpr bool kDefer = !kDebug;
+                const bool odd0 = L.div & 1;
+                float2 vprev = make_float2(0.0f, 0.0f), e0 = vprev;
+#pragma unroll
+                for (int it = 0; it < kMskFast; it++) {
+                    float2 N0 = W[7], N1 = W[7], N2 = W[7];
+                    if (it + 1 < kMskFast) {
+                        int p8 = L.rpos + 8;
+                        p8 = p8 >= kMskRing ? p8 - kMskRing : p8; // p8 + 2 stays inside the mirror
+                        const unsigned char *q0 = col + (p8 >> 1) * 512 + (p8 & 1) * 8;
+                        const unsigned char *q1 = col + ((p8 + 1) >> 1) * 512 + ((p8 + 1) & 1) * 8;
+                        N0 = *reinterpret_cast<const float2 *>(q0);
+                        N1 = *reinterpret_cast<const float2 *>(q1);
+                        N2 = *reinterpret_cast<const float2 *>(q0 + 512);
+                    }
+                    const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
+                    L.bad_imu |= (imu_c != (unsigned)imu);
+                    const float x = msk_core<kDebug, KIND == 2, kDefer>(L, (int)imu_c, W, s_mmse, p, oe, om);
+                    if (kDefer) {
+                        if (it & 1) {
+                            // the symbol of steps it-1, it
+                            const float2 e = odd0 ? L.vlast : vprev;
+                            if (KIND != 2) {
+                                *L.op = e;
+                                L.op++;
+                            } else if ((it & 3) == 1) {
+                                e0 = e;
+                            } else {
+                                // two symbols, one 16-byte store where the row allows it:
+                                //   holding one:      (hold, e0) -> op - 1, keep e
+                                //   aligned, no hold: (e0, e)    -> op
+                                //   neither:          e0 -> op (8 bytes), keep e
+                                const bool al = (reinterpret_cast<uintptr_t>(L.op) & 15) == 0;
+                                const bool hv = L.have_hold;
+                                const bool wide = hv || al;
+                                const float2 a = hv ? L.hold : e0, b = hv ? e0 : e;
+                                float2 *dst = hv ? L.op - 1 : L.op;
+                                if (wide)
+                                    *reinterpret_cast<float4 *>(dst) = make_float4(a.x, a.y, b.x, b.y);
+                                else
+                                    *dst = a;
+                                L.hold = e;
+                                L.have_hold = hv || !al;
+                                L.op += 2;
+                            }
+                        } else {
+                            vprev = L.vlast;
+                        }
+                    }
+                    const int fl_i = __float2int_rd(x);
+                    imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
+                    L.iidx += fl_i;
+                    const int rp = L.rpos + fl_i;
+                    L.rpos = rp >= kMskRing ? rp - kMskRing : rp;
+                    L.mu = x - floorf(x);
+                    if (it + 1 < kMskFast) {
+                        const bool three = fl_i == 3;
+                        L.bad_imu |= ((unsigned)(fl_i - 2) > 1u); // finite input never gets here
+#pragma unroll
+                        for (int k = 0; k < 5; k++)
+                            W[k] = three ? W[k + 3] : W[k + 2];
+                        W[5] = three ? N0 : W[7];
+                        W[6] = three ? N1 : N0;
+                        W[7] = three ? N2 : N1;
+                    }
+                }
+                if (kDefer)
+                    L.oidx += kMskFast / 2;
+                active = (L.oidx < noutput_items) && (L.iidx < ninp);
+                continue;
+            }
 #pragma unroll
             for (int it = 0; it < kMskFast; it++) {
                 const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
                 L.bad_imu |= (imu_c != (unsigned)imu);
-                const float x = msk_step<kDebug, KIND != 0>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug, KIND != 0, KIND == 2>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
                 const int fl_i = __float2int_rd(x);
                 imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
                 L.iidx += fl_i;
@@ -456,7 +632,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 const int imu = __float2int_rn(L.mu * 128.0f);
                 const int imu_c = min(max(imu, 0), 128);
                 L.bad_imu |= (imu != imu_c);
-                const float x = msk_step<kDebug, KIND != 0>(L, imu_c, ring4, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug, KIND != 0, KIND == 2>(L, imu_c, ring4, s_mmse, p, oe, om);
                 const float fl = floorf(x);
                 L.iidx += (int)fl;
                 L.rpos = ring_pos<kMskRing>(L.iidx);
@@ -465,6 +641,8 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             }
         }
     }
+    if (L.have_hold)
+        L.op[-1] = L.hold;
     if (L.bad_imu)
         err_code = B200AIS_E_INTERP;
     cp_async_wait_all();
@@ -744,6 +922,20 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
                   "half-symbol step; this build supports up to %d", 2.0 * p.sps_half, p.gain, p.limit,
                   advmax, MskCfg<1>::Need - 8);
         return B200AIS_E_INVALID;
+    }
+    {
+        static int no_slide = -1;
+        if (no_slide < 0) {
+            const char *e = getenv("B200AIS_MSK_NO_SLIDE");
+            no_slide = (e && *e && atoi(e)) ? 1 : 0;
+        }
+        p.no_slide = no_slide;
+        static int no_pf = -1;
+        if (no_pf < 0) {
+            const char *e = getenv("B200AIS_MSK_NO_PAIR_FETCH");
+            no_pf = (e && *e && atoi(e)) ? 1 : 0;
+        }
+        p.pair_fetch = (no_pf || kind == 0) ? 0 : 1; // a lone warp per scheduler: the extra instructions cost more
     }
     const bool dbg = out_err || out_mu;
 #define B200_MSK(DBG, KIND, W)                                                                     \
