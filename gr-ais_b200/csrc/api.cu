@@ -672,6 +672,7 @@ namespace {
 constexpr int kKeep = 32;     // stream mode: corr_est output-0 items kept for the timing loop
 constexpr int kSeg = 16;      // NCO phase checkpoint spacing (samples)
 constexpr int kMaxGroups = 8; // channel groups pipelined over internal streams
+constexpr long kPipeMaxChannels = 53248; // larger batches run enqueue_dev in stream order (see there)
 } // namespace
 
 struct b200ais_demod {
@@ -721,6 +722,7 @@ struct b200ais_demod {
     int *d_ntags_alt = nullptr;
     cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_back[2] = { nullptr, nullptr };
     bool back_pending[2] = { false, false };
+    bool inorder_pending = false; // records enqueued in stream order (full-wave batches) since the last join
     unsigned pipe_calls = 0;
     // ---- stream mode (b200ais_demod_stream_*): what every block keeps between calls ----
     bool st_ready = false;     // state allocated and reset
@@ -1121,6 +1123,7 @@ static int demod_join(b200ais_demod *h, cudaStream_t s);
 // own streams cannot be ordered behind them any other way
 static int demod_drain(b200ais_demod *h)
 {
+    h->inorder_pending = false;
     if (h->back_pending[0] || h->back_pending[1]) {
         B200_CU(cudaStreamSynchronize(h->back_stream));
         h->back_pending[0] = h->back_pending[1] = false;
@@ -1218,6 +1221,7 @@ extern "C" int b200ais_demod_work_dev(b200ais_demod *h, const float *iq, int nsa
 // make `s` wait for every back half still in flight
 static int demod_join(b200ais_demod *h, cudaStream_t s)
 {
+    h->inorder_pending = false;
     for (int k = 0; k < 2; k++)
         if (h->back_pending[k]) {
             B200_CU(cudaStreamWaitEvent(s, h->ev_back[k], 0));
@@ -1245,6 +1249,41 @@ extern "C" int b200ais_demod_enqueue_dev(b200ais_demod *h, const float *iq, int 
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t C = (size_t)h->channels;
+    // A batch that fills the GPU on its own (the timing loop at 14 warps per SM) leaves the side
+    // stream nothing to hide under: both halves then slow each other down and the record takes
+    // longer than in stream order (65 536 channels: 52.4 ms against 50.3).  Such batches run the
+    // whole record on the caller's stream; B200AIS_PIPE_MAX_CH overrides the limit (experiments).
+    static long pipe_max = -1;
+    if (pipe_max < 0) {
+        const char *e = getenv("B200AIS_PIPE_MAX_CH");
+        pipe_max = (e && *e) ? atol(e) : kPipeMaxChannels;
+    }
+    if ((long)h->channels > pipe_max) {
+        if (h->back_pending[0] || h->back_pending[1]) {
+            int rc = demod_join(h, s);
+            if (rc)
+                return rc;
+        }
+        if (h->t_sym.cap < C * (size_t)max_bits * sizeof(float2) || h->pad_dirty || h->taps_enabled)
+            B200_CU(cudaStreamSynchronize(s));
+        int rc = demod_prepare(h, nsamples, max_bits);
+        if (rc)
+            return rc;
+        if (!h->inorder_pending) // the first record since the last join: the flags start clean
+            B200_CU(cudaMemsetAsync(h->d_status, 0, sizeof(int) * (kMaxGroups + 1), s));
+        h->inorder_pending = true;
+        rc = demod_launch_group(h, 0, h->channels, reinterpret_cast<const float2 *>(iq), (size_t)nsamples,
+                                nsamples, 0, bits, max_bits, nbits, h->d_tags, h->d_ntags, h->d_status, s);
+        if (rc)
+            return rc;
+        h->pipe_calls++;
+        if (tags)
+            B200_CU(cudaMemcpyAsync(tags, h->d_tags, sizeof(b200ais_tag) * (size_t)h->max_tags * C,
+                                    cudaMemcpyDeviceToDevice, s));
+        if (ntags)
+            B200_CU(cudaMemcpyAsync(ntags, h->d_ntags, sizeof(int) * C, cudaMemcpyDeviceToDevice, s));
+        return B200AIS_OK;
+    }
     if (!h->back_stream) {
         int lo = 0, hi = 0;
         B200_CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));

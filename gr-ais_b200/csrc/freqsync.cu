@@ -111,21 +111,6 @@ k_sqfft_freqest(const float2 *__restrict__ x, size_t x_stride, int vstride, int 
         raw[(size_t)c * vstride + b] = (best.j == 0x7fffffff) ? -1 : best.j + offset / 2;
 }
 
-// ---- 1024-point fast path: 64 threads, 16 values per thread, three register passes ----
-//
-// Same radix-2 decimation-in-time graph as the generic kernel (and the oracle): stage s
-// combines X[e] and X[e + 2^(s-1)] with W[(e mod 2^(s-1)) * 1024/2^s].  Stages 1-4 touch
-// index bits 0-3, stages 5-7 bits 4-6, stages 8-10 bits 7-9, so a thread can hold all the
-// elements that differ only in those bits and run the stages in registers; shared memory
-// is crossed twice instead of ten times.  W = 1 and W = -i (exact table entries) skip the
-// multiply: fma(1,b,-0) = b and fma(0,x,y) = y are exact.
-constexpr int kFast = 64;
-
-// 1-in-16 padding plus one slot per 64 elements: conflict-free for the pass-A writers (thread
-// tid owns the 16 elements of group bitrev6(tid), so that its loads are coalesced) and for the
-// pass-B / pass-C accesses (16 consecutive `lo` per half-warp)
-__device__ __forceinline__ int fphys(int e) { return e + (e >> 4) + (e >> 6); }
-
 // butterflies in packed FP32 (FFMA2 / FADD2 / FMUL2 on the (re, im) pair, device_math.cuh):
 // the same roundings as the scalar forms, half the issue slots
 __device__ __forceinline__ void bf(float2 &a, float2 &b, const float2 w)
@@ -147,144 +132,183 @@ __device__ __forceinline__ void bf_mi(float2 &a, float2 &b) // W = (0, -1): t = 
     b = f2_add(a0, make_float2(-b0.y, b0.x));
 }
 
-// three radix-2 stages on 8 register values whose pair distances are 1, 2, 4
-__device__ __forceinline__ void pass8(float2 (&u)[8], const float2 w1, const float2 (&w2)[2],
-                                      const float2 (&w3)[4])
+// ---- 1024-point path, one warp per transform: 32 values per thread, two register passes ----
+//
+// The same radix-2 decimation-in-time graph as the generic kernel and the oracle (every butterfly
+// is the oracle's, with the oracle's twiddle: stage s combines X[e] and X[e + 2^(s-1)] with
+// W[(e mod 2^(s-1)) * 1024/2^s]; W = 1 and W = -i, exact table entries, skip the multiply:
+// fma(1,b,-0) = b and fma(0,x,y) = y are exact): stages 1-5 touch index bits 0-4 and stages 6-10 bits 5-9, so a thread that
+// holds the 32 elements differing only in those bits runs five stages in registers and shared
+// memory is crossed once.  No block-wide barrier: a transform belongs to one warp.
+//   pass A: lane t holds e = 32 t + q, q = 0..31, loaded from x[bitrev10(e)] = x[bitrev5(q)*32 +
+//           bitrev5(t)] (a warp's load covers 256 consecutive bytes).  The twiddles W_32^j do not
+//           depend on the lane: constant memory (c_w32, filled from the table by get_twiddles).
+//   pass B: lane lo holds e = 32 q + lo; stage 6..9 twiddles from the [slot][lo] copies behind the
+//           table, stage 10 from the table itself (tw[lo + 32 j]); the result is X[k], k = 32 q + lo.
+//   freqest: the |X| estimates stay in registers; only the partner bin k + offset comes through
+//           shared memory.
+constexpr int kTwWarp = 512; // first [slot][lo] entry of this kernel's copies (get_twiddles)
+__constant__ float4 c_w32[16]; // W_1024^(32 j) = W_32^j as (re, re, im, im)
+
+__device__ __forceinline__ void bf_c32(float2 &a, float2 &b, int j)
 {
-#pragma unroll
-    for (int q = 0; q < 8; q += 2)
-        bf(u[q], u[q + 1], w1);
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-        if (!(q & 2))
-            bf(u[q], u[q + 2], w2[q & 1]);
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-        bf(u[q], u[q + 4], w3[q]);
+    const float4 w = c_w32[j];
+    // cmul_fma2(w, b)
+    const float2 t = f2_fma(b, make_float2(w.x, w.y), f2_mul(make_float2(-b.y, b.x), make_float2(w.z, w.w)));
+    const float2 a0 = a;
+    a = f2_add(a0, t);
+    b = f2_sub(a0, t);
 }
 
-__global__ void __launch_bounds__(kFast)
+template <int S> __device__ __forceinline__ void warpfft_stage_a(float2 (&v)[32])
+{
+    constexpr int h = 1 << (S - 1);
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        if (q & h)
+            continue;
+        const int j = (q & (h - 1)) * (16 >> (S - 1)); // W_2^S^(q mod h) = W_32^j
+        if (j == 0)
+            bf_one(v[q], v[q + h]);
+        else if (j == 8)
+            bf_mi(v[q], v[q + h]);
+        else
+            bf_c32(v[q], v[q + h], j);
+    }
+}
+
+template <int B> __device__ __forceinline__ void warpfft_stage_b(float2 (&u)[32], const float2 *__restrict__ twl)
+{
+    constexpr int h = 1 << B;
+    float2 w[h];
+#pragma unroll
+    for (int j = 0; j < h; j++)
+        w[j] = B < 4 ? twl[kTwWarp + ((h - 1) + j) * 32] : twl[32 * j];
+#pragma unroll
+    for (int q = 0; q < 32; q++)
+        if (!(q & h))
+            bf(u[q], u[q + h], w[q & (h - 1)]);
+}
+
+// v[q] for a warp-uniform q (a jump table over the 32 registers; the array stays in registers)
+__device__ __forceinline__ float2 warpfft_pick(const float2 (&v)[32], int q)
+{
+    float2 r = v[0];
+#define B200_PICK(Q) case Q: r = v[Q]; break;
+    switch (q) {
+        B200_PICK(1) B200_PICK(2) B200_PICK(3) B200_PICK(4) B200_PICK(5) B200_PICK(6) B200_PICK(7)
+        B200_PICK(8) B200_PICK(9) B200_PICK(10) B200_PICK(11) B200_PICK(12) B200_PICK(13) B200_PICK(14)
+        B200_PICK(15) B200_PICK(16) B200_PICK(17) B200_PICK(18) B200_PICK(19) B200_PICK(20) B200_PICK(21)
+        B200_PICK(22) B200_PICK(23) B200_PICK(24) B200_PICK(25) B200_PICK(26) B200_PICK(27) B200_PICK(28)
+        B200_PICK(29) B200_PICK(30) B200_PICK(31)
+    default:
+        break;
+    }
+#undef B200_PICK
+    return r;
+}
+
+constexpr int kWarpCx = 1024 + 64; // 2 pad slots per 32 elements: 16-byte stores and 8-byte loads without conflicts
+
+__global__ void __launch_bounds__(32, 16)
 k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
-                     const float2 *__restrict__ tw, int offset, int *__restrict__ raw, int channels)
+                      const float2 *__restrict__ tw, int offset, int *__restrict__ raw, int channels)
 {
     constexpr int N = 1024;
     if (channel_index() >= channels)
         return;
-    __shared__ float2 cx[N + N / 16 + N / 64];
-    __shared__ float hs[N];
-    __shared__ Best sh[kFast / 32];
-    __shared__ float s_max[kFast / 32];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) float2 cx[kWarpCx];
+    const int lane = threadIdx.x;
     const int b = blockIdx.x, c = channel_index();
     const float2 *src = x + (size_t)c * x_stride + (size_t)b * N;
+    const int r5 = (int)(__brev((unsigned)lane) >> 27); // bitrev5(lane)
 
-    // ---- pass A: stages 1-4 on elements e = 16*t6 + q, loaded from x[bitrev10(e)] =
-    // x[bitrev4(q)*64 + bitrev6(t6)]; thread tid takes the group t6 = bitrev6(tid), so that the
-    // threads of a warp read consecutive items ----
+    float2 v[32];
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+        const int rq = ((q & 1) << 4) | ((q & 2) << 2) | (q & 4) | ((q & 8) >> 2) | ((q & 16) >> 4);
+        v[q] = src[rq * 32 + r5];
+    }
+#pragma unroll
+    for (int q = 0; q < 32; q++)
+        v[q] = cmul_fma2(v[q], v[q]); // blocks.multiply_cc(x, x)
+    warpfft_stage_a<1>(v);
+    warpfft_stage_a<2>(v);
+    warpfft_stage_a<3>(v);
+    warpfft_stage_a<4>(v);
+    warpfft_stage_a<5>(v);
     {
-        float2 v[16];
-        const int t6 = (int)(__brev((unsigned)tid) >> 26); // bitrev6(tid)
+        float4 *dst = reinterpret_cast<float4 *>(cx + 34 * lane);
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int r4 = ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3);
-            const float2 in = src[r4 * 64 + tid];
-            v[q] = cmul_fma2(in, in); // blocks.multiply_cc(x, x)
-        }
-        const float2 w128 = tw[128], w384 = tw[384];
-        const float2 w64 = tw[64], w192 = tw[192], w320 = tw[320], w448 = tw[448];
-#pragma unroll
-        for (int q = 0; q < 16; q += 2)
-            bf_one(v[q], v[q + 1]);
-#pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-            bf_one(v[q], v[q + 2]);
-            bf_mi(v[q + 1], v[q + 3]);
-        }
-#pragma unroll
-        for (int q = 0; q < 16; q += 8) {
-            bf_one(v[q], v[q + 4]);
-            bf(v[q + 1], v[q + 5], w128);
-            bf_mi(v[q + 2], v[q + 6]);
-            bf(v[q + 3], v[q + 7], w384);
-        }
-        bf_one(v[0], v[8]);
-        bf(v[1], v[9], w64);
-        bf(v[2], v[10], w128);
-        bf(v[3], v[11], w192);
-        bf_mi(v[4], v[12]);
-        bf(v[5], v[13], w320);
-        bf(v[6], v[14], w384);
-        bf(v[7], v[15], w448);
-        const int base = 17 * t6 + (t6 >> 2); // fphys(16*t6 + q) = base + q
-#pragma unroll
-        for (int q = 0; q < 16; q++)
-            cx[base + q] = v[q];
+        for (int q = 0; q < 32; q += 2)
+            dst[q >> 1] = make_float4(v[q].x, v[q].y, v[q + 1].x, v[q + 1].y);
     }
-    __syncthreads();
-    // ---- pass B: stages 5-7 on e = hi*128 + q*16 + lo ----
-    // tw[lo << 5], tw[(lo + 16 j) << 4], tw[(lo + 16 j) << 3] from the [slot][lo] copies
-    // behind the table (get_twiddles): a warp's read covers 128 consecutive bytes.  Both of a
-    // thread's groups (g = tid, tid + 64) have the same lo: one set of loads serves them.
-    const int loB = tid & 15;
-    const float2 wB1 = tw[512 + loB];
-    const float2 wB2[2] = { tw[528 + loB], tw[544 + loB] };
-    const float2 wB3[4] = { tw[560 + loB], tw[576 + loB], tw[592 + loB], tw[608 + loB] };
-#pragma unroll 1
-    for (int g = tid; g < 128; g += kFast) {
-        const int hi = g >> 4, lo = g & 15;
-        float2 u[8];
+    __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-            u[q] = cx[fphys(hi * 128 + q * 16 + lo)];
-        pass8(u, wB1, wB2, wB3);
+    for (int q = 0; q < 32; q++)
+        v[q] = cx[34 * q + lane];
+    const float2 *twl = tw + lane;
+    warpfft_stage_b<0>(v, twl);
+    warpfft_stage_b<1>(v, twl);
+    warpfft_stage_b<2>(v, twl);
+    warpfft_stage_b<3>(v, twl);
+    warpfft_stage_b<4>(v, twl);
+    __syncwarp(); // every lane has read its pass-B inputs: the buffer now takes the |X| estimates
+    // float estimates of |X[k]| for the pre-filter; hs in fft-shifted order: hs[j] = |X[(j + N/2) mod N]|
+    float *hs = reinterpret_cast<float *>(cx);
+    float est[32];
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-            cx[fphys(hi * 128 + q * 16 + lo)] = u[q];
+    for (int q = 0; q < 32; q++) {
+        // MUFU.SQRT: 2^-22 relative, well inside the pre-filter's margin (below)
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(est[q]) : "f"(__fmaf_rn(v[q].x, v[q].x, v[q].y * v[q].y)));
+        hs[((q * 32 + lane) + N / 2) & (N - 1)] = est[q];
     }
-    __syncthreads();
-    // ---- pass C: stages 8-10 on e = q*128 + lo; output bin k = e (natural order) ----
-#pragma unroll 1
-    for (int lo = tid; lo < 128; lo += kFast) {
-        float2 u[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            u[q] = cx[fphys(q * 128 + lo)];
-        const float2 w1 = tw[624 + lo];                               // tw[lo << 2]
-        const float2 w2[2] = { tw[752 + lo], tw[880 + lo] };          // tw[(lo + 128 j) << 1]
-        const float2 w3[4] = { tw[lo], tw[lo + 128], tw[lo + 256], tw[lo + 384] };
-        pass8(u, w1, w2, w3);
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int k = q * 128 + lo;
-            cx[fphys(k)] = u[q];
-            // float estimate of |X[k]| for the pre-filter, stored in fft-shifted order
-            hs[(k + N / 2) & (N - 1)] = sqrtf(__fmaf_rn(u[q].x, u[q].x, u[q].y * u[q].y));
-        }
-    }
-    __syncthreads();
+    __syncwarp();
     // ---- freqest: argmax_j |S[j]| + |S[j+offset]| with strict '>' in ascending j ----
-    // The float estimates are within 3e-7 relative of the canonical (double-evaluated) sums,
-    // so only bins within 2e-6 of the estimated maximum can be the canonical argmax; those
-    // few are re-evaluated canonically.  Degenerate spectra take the exact path for every bin.
+    // The float estimates are within 5e-7 relative of the canonical (double-evaluated) sums
+    // (sum of squares 1e-7, approximate root 2.4e-7, the add 6e-8), so only bins within 2e-6 of
+    // the estimated maximum can be the canonical argmax; those few are re-evaluated canonically.
+    // Degenerate spectra take the exact path for every bin.
+    // Lane `lane` takes j = 32 i + lane: hs[j] is its own est[(i + 16) & 31].
     float m_est = 0.0f;
-    for (int j = tid; j < N - offset; j += kFast)
-        m_est = fmaxf(m_est, hs[j] + hs[j + offset]);
+    float e_est[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const int j = 32 * i + lane;
+        const bool in = j < N - offset;
+        e_est[i] = in ? est[(i + 16) & 31] + hs[in ? j + offset : 0] : -1.0f;
+        m_est = fmaxf(m_est, e_est[i]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         m_est = fmaxf(m_est, __shfl_xor_sync(0xffffffffu, m_est, o));
-    if ((tid & 31) == 0)
-        s_max[tid >> 5] = m_est;
-    __syncthreads();
-    m_est = fmaxf(s_max[0], s_max[1]);
     const bool exact_all = !(m_est > 1e-12f && m_est < 1e30f);
-    const float cut = m_est * (1.0f - 2e-6f);
+    const float cut = exact_all ? 0.0f : m_est * (1.0f - 2e-6f); // valid sums are >= 0 (NaN: never the argmax)
+    unsigned cand = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+        cand |= (e_est[i] >= cut ? 1u : 0u) << i;
+    // The candidates (one or two per transform, every bin of a degenerate one), one at a time for
+    // the whole warp in ascending (i, lane) order per lane: the spectrum is still in registers, so
+    // the two lanes that own X[k0] and X[k1] pick them with a warp-uniform index.
     Best best;
     best.e = 0.0f;
     best.j = 0x7fffffff;
-    for (int j = tid; j < N - offset; j += kFast) {
-        if (exact_all || hs[j] + hs[j + offset] >= cut) {
-            const float2 p = cx[fphys((j + N / 2) & (N - 1))];
-            const float2 q2 = cx[fphys((j + offset + N / 2) & (N - 1))];
+    if (exact_all) {
+        // every bin is a candidate (an all-zero or non-finite spectrum): through shared memory,
+        // every lane on its own bins
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 32; q++)
+            cx[34 * q + lane] = v[q];
+        __syncwarp();
+        while (cand) { // ascending j within the lane
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int j = 32 * i + lane;
+            const int k0 = (j + N / 2) & (N - 1), k1 = (j + offset + N / 2) & (N - 1);
+            const float2 p = cx[34 * (k0 >> 5) + (k0 & 31)];
+            const float2 q2 = cx[34 * (k1 >> 5) + (k1 & 31)];
             const float e = hypot_canon(p.x, p.y) + hypot_canon(q2.x, q2.y);
             if (e > best.e) {
                 best.e = e;
@@ -292,8 +316,33 @@ k_sqfft_freqest_1024(const float2 *__restrict__ x, size_t x_stride, int vstride,
             }
         }
     }
-    best = block_argmax(best, sh);
-    if (tid == 0)
+    for (;;) {
+        const unsigned who = __ballot_sync(0xffffffffu, cand != 0);
+        if (!who)
+            break;
+        const int leader = __ffs(who) - 1;
+        const int i = __shfl_sync(0xffffffffu, __ffs(cand) - 1, leader);
+        if (lane == leader)
+            cand &= cand - 1;
+        const int j = 32 * i + leader;
+        const int k0 = (j + N / 2) & (N - 1), k1 = (j + offset + N / 2) & (N - 1);
+        const float2 p = warpfft_pick(v, k0 >> 5), q2 = warpfft_pick(v, k1 >> 5);
+        const float h0 = __shfl_sync(0xffffffffu, hypot_canon(p.x, p.y), k0 & 31);
+        const float h1 = __shfl_sync(0xffffffffu, hypot_canon(q2.x, q2.y), k1 & 31);
+        const float e = h0 + h1;
+        if (lane == leader && e > best.e) { // the leader's candidates come in ascending j
+            best.e = e;
+            best.j = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best w;
+        w.e = __shfl_xor_sync(0xffffffffu, best.e, o);
+        w.j = __shfl_xor_sync(0xffffffffu, best.j, o);
+        best = better(best, w);
+    }
+    if (lane == 0)
         raw[(size_t)c * vstride + b] = (best.j == 0x7fffffff) ? -1 : best.j + offset / 2;
 }
 
@@ -394,6 +443,17 @@ __global__ void k_nco_phase(const int *__restrict__ raw, int channels, int nvec,
 
 } // namespace
 
+// get_twiddles(1024): the lane-independent twiddles of k_sqfft_freqest_1024's first pass, from
+// the table itself (so both sides of the parity contract use the same sixteen values)
+int sqfft_set_w32(const float2 *tw_host)
+{
+    float4 h[16];
+    for (int j = 0; j < 16; j++)
+        h[j] = make_float4(tw_host[32 * j].x, tw_host[32 * j].x, tw_host[32 * j].y, tw_host[32 * j].y);
+    B200_CU(cudaMemcpyToSymbol(c_w32, h, sizeof(h)));
+    return B200AIS_OK;
+}
+
 static int ilog2_exact(int n)
 {
     int lg = 0;
@@ -419,7 +479,7 @@ int launch_sqfft_freqest(const float2 *x, size_t x_stride, int channels, int nve
     size_t smem = (size_t)fftlen * (sizeof(float2) + sizeof(float));
     dim3 grid = channel_grid(nvec, channels);
     if (fftlen == 1024) {
-        k_sqfft_freqest_1024<<<grid, kFast, 0, s>>>(x, x_stride, vstride, tw, offset, raw, channels);
+        k_sqfft_freqest_1024<<<grid, 32, 0, s>>>(x, x_stride, vstride, tw, offset, raw, channels);
     } else {
         if (smem > 40 * 1024) // static shared memory counts towards the 48 KB default limit
             B200_CU(cudaFuncSetAttribute(k_sqfft_freqest, cudaFuncAttributeMaxDynamicSharedMemorySize,

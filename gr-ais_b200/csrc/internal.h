@@ -143,6 +143,7 @@ size_t corr_mask_stride_bytes(int L, int n);
 int make_corr_spectrum(const float *taps_iq, int L, float2 *hbr_host /* [fftsize] */);
 // the kernel's immediates for the 16th roots of unity against a host twiddle table of length n
 int corr_check_w16(const float2 *tw_host, int n);
+int sqfft_set_w32(const float2 *tw_host);
 // sparse != 0: corr_out only has to serve k_detect (blocks without a sample above the threshold
 // write their first and last item only).  in_readable: items readable from `in` in every row
 // (>= n; the bulk-copy path rounds an odd n up to the next 16 bytes).

@@ -51,6 +51,9 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
 // in shared memory (a table row read through L1 misses often enough to show on the critical
 // path).  Small batches run one warp per CTA so that every SM gets its share of the warps; the
 // large ones pack 7 warps behind one table (7 or 14 warps per SM).
+#ifndef MSK2_CHUNK
+#define MSK2_CHUNK 8
+#endif
 template <int KIND> struct MskCfg;
 template <> struct MskCfg<0> {
     static constexpr int Chunk = 32, Ring = 128, Fast = 8, Need = 32, TagCap = 32;
@@ -59,7 +62,10 @@ template <> struct MskCfg<1> {
     static constexpr int Chunk = 16, Ring = 96, Fast = 8, Need = 32, TagCap = 8;
 };
 template <> struct MskCfg<2> {
-    static constexpr int Chunk = 16, Ring = 48, Fast = 4, Need = 20, TagCap = 4;
+    // 8-sample chunks: a lane may ask for the next one as soon as 9 ring slots are free, 1.1 to
+    // 1.9 rounds before it reads it (16-sample chunks: 0.2 to 1.1 rounds, i.e. every round
+    // waited for DRAM and the loop ran at the memory latency, 1050 cycles per step)
+    static constexpr int Chunk = MSK2_CHUNK, Ring = 48, Fast = 4, Need = 20, TagCap = 4;
 };
 constexpr int kMskMirror = 8;   // samples 0..7 repeated after the ring: 10-sample reads never wrap
 constexpr int kMskInner = 4;    // half-symbol steps per careful round (fewer when sps is large)

@@ -188,6 +188,31 @@ def test_square_and_fft_sync_stage(oracle):
         assert np.array_equal(fhat[c], r["fhat"]) and np.array_equal(y[c], r["mixed"])
 
 
+def test_square_and_fft_sync_edge_cases(oracle):
+    """the spectrum argmax on degenerate and tied spectra: silence and a vanishing level (every
+    bin goes through the canonical evaluation), a real-valued record (mirror-symmetric spectrum:
+    tied sums), a pure tone (one line, leakage-free) and a record that starts silent"""
+    from gr_ais_b200.ais_demod import square_and_fft_sync_cc
+    n = 8192
+    rng = np.random.default_rng(77)
+    base = synth.make_record(5, n=n, nbursts=2, snr_db=12, cfo_hz=-450.0)[0]
+    rows = [np.zeros(n, np.complex64),
+            (base * 1e-9).astype(np.complex64),
+            (base * 3e-7).astype(np.complex64),
+            rng.standard_normal(n).astype(np.float32).astype(np.complex64),
+            np.exp(2j * np.pi * 37.0 * np.arange(n) / 1024.0).astype(np.complex64),
+            np.concatenate([np.zeros(3072, np.complex64), base[:n - 3072]])]
+    x = np.stack(rows)
+    blk = square_and_fft_sync_cc(48000.0, 9600.0, 1024, channels=len(rows), max_samples=n)
+    y, fhat = blk.work(x)
+    for c in range(len(rows)):
+        r = oracle.demod_chain(x[c], np.ones(8, np.complex64), oracle.chain_cfg(stages=oracle.STAGE_FREQSYNC),
+                               debug=True)
+        assert np.array_equal(fhat[c], r["fhat"], equal_nan=True), "channel %d" % c
+        assert np.array_equal(y[c].view(np.uint32), r["mixed"].view(np.uint32)) or \
+            np.array_equal(y[c], r["mixed"], equal_nan=True), "channel %d" % c
+
+
 @pytest.mark.parametrize("L", [5, 8, 9, 16, 17, 33, 64, 65, 100, 128, 129, 256, 300, 513, 1024, 1025, 2048])
 def test_corr_est_every_fft_size(oracle, L):
     """fft sizes 16 .. 4096 (every template instantiation of the overlap-add filter), random
