@@ -763,7 +763,8 @@ extern "C" int b200ais_demod_default_config(b200ais_demod_config *cfg)
 
 static int demod_max_bits(const b200ais_demod *h, int nsamples)
 {
-    return (int)((double)nsamples / (double)h->cfg.sps * (double)h->cfg.osps * 1.05) + 64;
+    // a multiple of 4: word-aligned bit rows let the timing loop write the bits itself
+    return ((int)((double)nsamples / (double)h->cfg.sps * (double)h->cfg.osps * 1.05) + 64 + 3) & ~3;
 }
 
 extern "C" int b200ais_demod_max_bits(const b200ais_demod *h, int nsamples)
@@ -1026,6 +1027,16 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     }
     if ((rc = launch_msk_reset(h->d_state + c0, cn, h->mp.sps_half, s)))
         return rc;
+    static int no_fuse = -1; // B200AIS_NO_FUSE_TAIL=1: separate k_tail always (experiment)
+    if (no_fuse < 0) {
+        const char *e = getenv("B200AIS_NO_FUSE_TAIL");
+        no_fuse = (e && *e && atoi(e)) ? 1 : 0;
+    }
+    // the loop writes the bits itself when nobody reads the symbols (no taps): no symbol stream in
+    // HBM and no k_tail (65 536 channels: 50.5 -> 48.0 ms).  It makes every step a little longer,
+    // which a batch too small to fill the schedulers pays in full (4096 channels: 5.2 -> 5.9 ms)
+    const bool fuse_tail = !h->taps_enabled && !no_fuse && cn >= 8192 &&
+                           (reinterpret_cast<uintptr_t>(bits) & 3) == 0 && (max_bits & 3) == 0;
     float2 *t_sym = h->t_sym.as<float2>() + (size_t)c0 * max_bits;
     float *t_err = h->taps_enabled ? h->t_err.as<float>() + (size_t)c0 * max_bits : nullptr;
     float *t_mu = h->taps_enabled ? h->t_mu.as<float>() + (size_t)c0 * max_bits : nullptr;
@@ -1037,9 +1048,11 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
                     // pipelined submission: the loop shares the SMs with the next record's front
                     // kernels.  The small ring that lets them in costs a lone warp ~7 ms whatever
                     // the batch, so it only pays when that front is longer (whole chain, >= 12 k channels)
-                    back != nullptr && cn >= 12288 && fs && (cfg.stages & B200AIS_STAGE_AGC));
+                    back != nullptr && cn >= 12288 && fs && (cfg.stages & B200AIS_STAGE_AGC),
+                    // without taps nobody reads the symbols: the loop writes the bits itself
+                    fuse_tail ? bits : nullptr, (size_t)max_bits);
     B200_MARK(B200AIS_STAGE_T_MSK);
-    if (!rc)
+    if (!rc && !fuse_tail)
         rc = launch_tail(t_sym, (size_t)max_bits, nbits, cn, max_bits, bits, (size_t)max_bits, t_soft, nullptr, s);
     B200_MARK(B200AIS_STAGE_T_TAIL);
 #undef B200_MARK

@@ -158,13 +158,17 @@ int launch_detect(const float2 *corr, size_t corr_stride, int channels, int n_to
                   int max_tags, int *ntags, int *status, int append, cudaStream_t s);
 // A7: the timing-loop recurrence, one lane per channel (symbols out).
 // share_sm: the kernel will run beside other kernels of the chain (prefer the smallest ring).
+// bits (nullable): the bit tail of a fresh chain (quadrature demod -> slicer -> diff decoder ->
+// invert, k_tail's arithmetic) fused into the loop: one byte per symbol to bits[c * bits_stride + k]
+// and NO symbol output (out is not written; out_err / out_mu must be null).
 // unconsumed (nullable, stream mode): [channels] items in front of `in` that the last call left
 // unconsumed (read, then updated); the rows must hold them and one more item in front.
 int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_items,
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
                const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
                float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
-               int require_unbounded, int *status, int *unconsumed, cudaStream_t s, int share_sm = 0);
+               int require_unbounded, int *status, int *unconsumed, cudaStream_t s, int share_sm = 0,
+               uint8_t *bits = nullptr, size_t bits_stride = 0);
 // G4-G6 + A9: quadrature demod -> slicer -> diff decoder -> invert on the symbol stream.
 int launch_tail(const float2 *sym, size_t sym_stride, const int *nsym, int channels, int max_sym,
                 uint8_t *bits, size_t bits_stride, float *soft, TailCarry *carry, cudaStream_t s);

@@ -90,6 +90,28 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
+// binary_slicer_fb(quadrature_demod_cf): (pi/2) * fast_atan2f(y, x) >= 0.  Only the sign reaches
+// the bit stream, and for finite arguments fast_atan2f's sign is y's -- its result is -base_angle,
+// base_angle - pi or -pi/2 +- base_angle (base_angle in [0, pi/4]) for y < 0 and non-negative for
+// y >= 0 (also -0 and (0, 0)) -- with one exception: y < 0 < x and |y| / |x| rounding to zero
+// gives -0, which passes `>= 0`.  That corner (|y| < |x| * 2^-100 is a superset of it) and
+// non-finite arguments take the table path.
+// the corner cases, out of line: the loop's straight-line rounds stay short (their cost is their
+// length, and a lone warp cannot hide an instruction-cache miss)
+static __device__ __noinline__ unsigned slicer_bit_rare(float y, float x, const float *__restrict__ tab)
+{
+    return (1.57079632679489661923f * fast_atan2f_tab(y, x, tab)) >= 0 ? 1u : 0u;
+}
+__device__ __forceinline__ unsigned slicer_bit(float y, float x, const float *__restrict__ tab)
+{
+    const float ya = fabsf(y), xa = fabsf(x);
+    const bool plain = xa <= 3.402823466e+38f && ya <= 3.402823466e+38f &&
+                       !(y < 0.0f && x > 0.0f && ya < xa * 7.8886090522101181e-31f);
+    if (plain)
+        return y >= 0.0f ? 1u : 0u;
+    return slicer_bit_rare(y, x, tab);
+}
+
 // Loop registers of one channel (lib/msk_timing_recovery_cc_impl.h:37-46), in registers.
 struct MskLane {
     float mu, omega;
@@ -102,7 +124,40 @@ struct MskLane {
     float2 hold;              // a symbol waiting for its neighbour: pairs go out as one 16-byte store
     bool have_hold;
     bool bad_imu;
+    // fused bit tail (FUSE): the symbol in front of the next one, the last slicer decision, the
+    // bytes of the 32-bit word being filled, the next bit slot
+    float2 tprev;
+    unsigned tb, pack;
+    uint8_t *bp;
+    const float *atab;
 };
+
+// G4-G6 + A9 on one symbol (the arithmetic of k_tail below): quadrature_demod_cf(pi/2) ->
+// binary_slicer_fb -> diff_decoder_bb(2) -> invert, one byte per symbol, four bytes per store
+__device__ __forceinline__ void msk_emit_bit(MskLane &L, float2 v)
+{
+    const float2 cur = L.tprev;
+    const float re = __fmaf_rn(v.x, cur.x, v.y * cur.y);
+    const float im = __fmaf_rn(v.y, cur.x, -(v.x * cur.y));
+    L.tprev = v;
+    const unsigned b = slicer_bit(im, re, L.atab);
+    const unsigned d = (b - L.tb) % 2u; // diff_decoder_bb(2)
+    L.tb = b;
+    // rows start on a 32-bit word (launch_msk checks): a word goes out when its fourth byte is in
+    const unsigned sh = ((unsigned)reinterpret_cast<uintptr_t>(L.bp) & 3u) * 8u;
+    L.pack |= ((d ^ 0x01u) & 0x01u) << sh; // lib/invert_impl.cc:63
+    if (sh == 24u)
+        *reinterpret_cast<unsigned *>(L.bp - 3) = L.pack;
+    L.pack = sh == 24u ? 0u : L.pack;
+    L.bp++;
+}
+__device__ __forceinline__ void msk_flush_bits(MskLane &L)
+{
+    const int nb = (int)(reinterpret_cast<uintptr_t>(L.bp) & 3u); // bytes of an unfinished word
+    for (int q = 0; q < nb; q++)
+        (L.bp - nb)[q] = (uint8_t)((L.pack >> (8 * q)) & 0xffu);
+    L.pack = 0;
+}
 
 template <int RING> __device__ __forceinline__ int ring_pos(int iidx)
 {
@@ -160,7 +215,7 @@ __device__ __forceinline__ void msk_load_window(const float4 *__restrict__ ring4
 // on even steps.  Returns x = mu + omega before the floor.  The arithmetic is packed FP32 on the
 // (re, im) pairs (device_math.cuh): same roundings as the scalar forms in the comments.
 // DEFER: the caller stores the symbols (the straight-line round: one symbol per two steps).
-template <bool kDebug, bool PAIR, bool DEFER = false>
+template <bool kDebug, bool PAIR, bool DEFER = false, bool FUSE = false>
 __device__ __forceinline__ float msk_core(MskLane &L, int imu_c, const float2 (&s)[8],
                                           const float *__restrict__ s_mmse, const MskParams &p,
                                           float *oe, float *om)
@@ -201,7 +256,9 @@ __device__ __forceinline__ float msk_core(MskLane &L, int imu_c, const float2 (&
     if (!DEFER && (!odd || p.osps == 2)) {
         // a lane's symbols go to its own row, one 32-byte sector per store whatever its size: two
         // symbols per store halve the requests the SM sends to L2
-        if (PAIR) {
+        if (FUSE) {
+            msk_emit_bit(L, v);
+        } else if (PAIR) {
             const bool al = (reinterpret_cast<uintptr_t>(L.op) & 15) == 0;
             const bool st4 = L.have_hold, st2 = !L.have_hold && !al;
             if (st4)
@@ -232,14 +289,14 @@ __device__ __forceinline__ float msk_core(MskLane &L, int imu_c, const float2 (&
 }
 
 // ring4: this lane's column of the 16-byte-unit ring (conflict-free: the lane picks the banks).
-template <bool kDebug, bool WIDE, bool PAIR>
+template <bool kDebug, bool WIDE, bool PAIR, bool FUSE>
 __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *__restrict__ ring4,
                                           const float *__restrict__ s_mmse, const MskParams &p,
                                           float *oe, float *om)
 {
     float2 s[8];
     msk_load_window<WIDE>(ring4, L.rpos, s);
-    return msk_core<kDebug, PAIR>(L, imu_c, s, s_mmse, p, oe, om);
+    return msk_core<kDebug, PAIR, false, FUSE>(L, imu_c, s, s_mmse, p, oe, om);
 }
 
 // The serial core of msk_timing_recovery_cc: one lane per channel.  A channel's loop is a
@@ -255,7 +312,7 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
 // needed, so no step waits on HBM.  Up to 4 of the lane's time_est tags are staged in shared
 // memory and refilled from the list when they run out (a tag fetched on the loop's critical
 // path costs a DRAM round trip; a burst carries about six).
-template <bool kDebug, int KIND, int WARPS>
+template <bool kDebug, int KIND, int WARPS, bool FUSE>
 __global__ void __launch_bounds__(32 * WARPS)
 k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput_items,
       int ninput_items, uint64_t nitems_read, const b200ais_tag *__restrict__ tags, int max_tags,
@@ -263,7 +320,8 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
       const float *__restrict__ g_mmse, float2 *__restrict__ out, float *__restrict__ out_err,
       float *__restrict__ out_mu, size_t out_stride, int *__restrict__ nproduced,
       int *__restrict__ nconsumed, int require_unbounded, int *__restrict__ status,
-      int *__restrict__ unconsumed)
+      int *__restrict__ unconsumed, uint8_t *__restrict__ bits, size_t bits_stride,
+      const float *__restrict__ g_atan)
 {
     using Cfg = MskCfg<KIND>;
     constexpr int kMskChunk = Cfg::Chunk, kMskRing = Cfg::Ring, kMskFast = Cfg::Fast, kMskNeed = Cfg::Need;
@@ -388,6 +446,11 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     L.hold = make_float2(0.0f, 0.0f);
     L.have_hold = false;
     L.bad_imu = false;
+    L.tprev = make_float2(0.0f, 0.0f); // quadrature_demod / diff_decoder history of a fresh chain
+    L.tb = 0;
+    L.pack = 0;
+    L.bp = FUSE ? bits + (size_t)c * bits_stride : nullptr;
+    L.atab = g_atan;
 
     int issue_end = 0; // samples [0, issue_end) of this lane's channel have been requested
     int issue_u = 0;   // ring unit the next chunk goes to (0, 8, 16)
@@ -543,12 +606,14 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                     }
                     const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
                     L.bad_imu |= (imu_c != (unsigned)imu);
-                    const float x = msk_core<kDebug, KIND == 2, kDefer>(L, (int)imu_c, W, s_mmse, p, oe, om);
+                    const float x = msk_core<kDebug, KIND == 2, kDefer, FUSE>(L, (int)imu_c, W, s_mmse, p, oe, om);
                     if (kDefer) {
                         if (it & 1) {
                             // the symbol of steps it-1, it
                             const float2 e = odd0 ? L.vlast : vprev;
-                            if (KIND != 2) {
+                            if (FUSE) {
+                                msk_emit_bit(L, e);
+                            } else if (KIND != 2) {
                                 *L.op = e;
                                 L.op++;
                             } else if ((it & 3) == 1) {
@@ -601,7 +666,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
             for (int it = 0; it < kMskFast; it++) {
                 const unsigned imu_c = min((unsigned)imu, 128u); // mu in [0, 1): never clamps
                 L.bad_imu |= (imu_c != (unsigned)imu);
-                const float x = msk_step<kDebug, KIND != 0, KIND == 2>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug, KIND != 0, KIND == 2, FUSE>(L, (int)imu_c, ring4, s_mmse, p, oe, om);
                 const int fl_i = __float2int_rd(x);
                 imu = __float2int_rn(x * 128.0f) - 128 * fl_i;
                 L.iidx += fl_i;
@@ -638,7 +703,7 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
                 const int imu = __float2int_rn(L.mu * 128.0f);
                 const int imu_c = min(max(imu, 0), 128);
                 L.bad_imu |= (imu != imu_c);
-                const float x = msk_step<kDebug, KIND != 0, KIND == 2>(L, imu_c, ring4, s_mmse, p, oe, om);
+                const float x = msk_step<kDebug, KIND != 0, KIND == 2, FUSE>(L, imu_c, ring4, s_mmse, p, oe, om);
                 const float fl = floorf(x);
                 L.iidx += (int)fl;
                 L.rpos = ring_pos<kMskRing>(L.iidx);
@@ -649,6 +714,8 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     }
     if (L.have_hold)
         L.op[-1] = L.hold;
+    if (FUSE)
+        msk_flush_bits(L);
     if (L.bad_imu)
         err_code = B200AIS_E_INTERP;
     cp_async_wait_all();
@@ -673,22 +740,6 @@ k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput
     nconsumed[c] = L.iidx - mis;
     if (unconsumed)
         unconsumed[c] = navail - (L.iidx - mis);
-}
-
-// binary_slicer_fb(quadrature_demod_cf): (pi/2) * fast_atan2f(y, x) >= 0.  Only the sign reaches
-// the bit stream, and for finite arguments fast_atan2f's sign is y's -- its result is -base_angle,
-// base_angle - pi or -pi/2 +- base_angle (base_angle in [0, pi/4]) for y < 0 and non-negative for
-// y >= 0 (also -0 and (0, 0)) -- with one exception: y < 0 < x and |y| / |x| rounding to zero
-// gives -0, which passes `>= 0`.  That corner (|y| < |x| * 2^-100 is a superset of it) and
-// non-finite arguments take the table path.
-__device__ __forceinline__ unsigned slicer_bit(float y, float x, const float *__restrict__ tab)
-{
-    const float ya = fabsf(y), xa = fabsf(x);
-    const bool plain = xa <= 3.402823466e+38f && ya <= 3.402823466e+38f &&
-                       !(y < 0.0f && x > 0.0f && ya < xa * 7.8886090522101181e-31f);
-    if (plain)
-        return y >= 0.0f ? 1u : 0u;
-    return (1.57079632679489661923f * fast_atan2f_tab(y, x, tab)) >= 0 ? 1u : 0u;
 }
 
 // G4-G6 + A9 on the symbol stream: quadrature_demod_cf(pi/2) -> binary_slicer_fb ->
@@ -881,7 +932,8 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
                int ninput_items, uint64_t nitems_read, const b200ais_tag *tags, int max_tags,
                const int *ntags, MskParams p, MskState *state, float2 *out, float *out_err,
                float *out_mu, size_t out_stride, int *nproduced, int *nconsumed,
-               int require_unbounded, int *status, int *unconsumed, cudaStream_t s, int share_sm)
+               int require_unbounded, int *status, int *unconsumed, cudaStream_t s, int share_sm,
+               uint8_t *bits, size_t bits_stride)
 {
     if (channels <= 0)
         return B200AIS_OK;
@@ -944,41 +996,47 @@ int launch_msk(const float2 *in, size_t in_stride, int channels, int noutput_ite
         p.pair_fetch = (no_pf || kind == 0) ? 0 : 1; // a lone warp per scheduler: the extra instructions cost more
     }
     const bool dbg = out_err || out_mu;
-#define B200_MSK(DBG, KIND, W)                                                                     \
+#define B200_MSK(DBG, KIND, W, FUSE)                                                               \
     do {                                                                                           \
         const int per_cta = 32 * W;                                                                \
         const int blocks = (channels + per_cta - 1) / per_cta;                                     \
         const size_t smem = (size_t)kMskTable + (size_t)W * msk_warp_smem<KIND>();                 \
         static bool attr_set = false;                                                              \
         if (!attr_set) { /* all the shared memory the SM has: occupancy is the throughput */       \
-            B200_CU(cudaFuncSetAttribute(k_msk<DBG, KIND, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem));                                              \
-            B200_CU(cudaFuncSetAttribute(k_msk<DBG, KIND, W>,                                      \
+            B200_CU(cudaFuncSetAttribute(k_msk<DBG, KIND, W, FUSE>,                                \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            B200_CU(cudaFuncSetAttribute(k_msk<DBG, KIND, W, FUSE>,                                \
                                          cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
             attr_set = true;                                                                       \
         }                                                                                          \
-        k_msk<DBG, KIND, W><<<blocks, per_cta, smem, s>>>(                                         \
+        k_msk<DBG, KIND, W, FUSE><<<blocks, per_cta, smem, s>>>(                                   \
             in, in_stride, channels, noutput_items, ninput_items, nitems_read, tags, max_tags, ntags, \
             p, state, tb.mmse, out, out_err, out_mu, out_stride, nproduced, nconsumed,             \
-            require_unbounded, status, unconsumed);                                                \
+            require_unbounded, status, unconsumed, bits, bits_stride, tb.atan);                    \
     } while (0)
-#define B200_MSK_KIND(DBG)                                                                         \
+#define B200_MSK_KIND(DBG, FUSE)                                                                   \
     do {                                                                                           \
         if (kind == 0)                                                                             \
-            B200_MSK(DBG, 0, 1);                                                                   \
+            B200_MSK(DBG, 0, 1, FUSE);                                                             \
         else if (kind == 1 && !packed)                                                             \
-            B200_MSK(DBG, 1, 1);                                                                   \
+            B200_MSK(DBG, 1, 1, FUSE);                                                             \
         else if (kind == 1)                                                                        \
-            B200_MSK(DBG, 1, 7);                                                                   \
+            B200_MSK(DBG, 1, 7, FUSE);                                                             \
         else if (small_spread)                                                                     \
-            B200_MSK(DBG, 2, 1);                                                                   \
+            B200_MSK(DBG, 2, 1, FUSE);                                                             \
         else                                                                                       \
-            B200_MSK(DBG, 2, 7);                                                                   \
+            B200_MSK(DBG, 2, 7, FUSE);                                                             \
     } while (0)
+    if (bits && (dbg || (reinterpret_cast<uintptr_t>(bits) & 3) || (bits_stride & 3))) {
+        set_error("msk: the fused bit tail needs word-aligned rows and has no error / mu outputs");
+        return B200AIS_E_INVALID;
+    }
     if (dbg)
-        B200_MSK_KIND(true);
+        B200_MSK_KIND(true, false);
+    else if (bits)
+        B200_MSK_KIND(false, true);
     else
-        B200_MSK_KIND(false);
+        B200_MSK_KIND(false, false);
 #undef B200_MSK_KIND
 #undef B200_MSK
     B200_LAUNCH_CHECK("k_msk");
