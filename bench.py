@@ -543,8 +543,9 @@ def run_b200(args):
         "stage_ms_per_step": per,
         "serialized_ms_per_step": serial_ms_step, "overlap_groups": args.overlap,
         "submission": ("strictly ordered work_dev calls" if args.strict else
-                       "enqueue_dev x K + join: msk_timing + bit tail of record k on a high-priority side "
-                       "stream under the front half of record k+1; all K results complete before the closing event"),
+                       "enqueue_dev x K + join; all K results complete before the closing event.  Up to 53 248 "
+                       "channels the timing loop of record k runs on a high-priority side stream under the front "
+                       "half of record k+1; a larger batch fills the GPU by itself and stays in stream order"),
         "symbols_per_channel": int(nbits_host[0]),
     }
     if coherent:

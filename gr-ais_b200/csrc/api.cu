@@ -1035,7 +1035,12 @@ static int demod_launch_group(b200ais_demod *h, int c0, int cn, const float2 *iq
     // the loop writes the bits itself when nobody reads the symbols (no taps): no symbol stream in
     // HBM and no k_tail (65 536 channels: 50.5 -> 48.0 ms).  It makes every step a little longer,
     // which a batch too small to fill the schedulers pays in full (4096 channels: 5.2 -> 5.9 ms)
-    const bool fuse_tail = !h->taps_enabled && !no_fuse && cn >= 8192 &&
+    static int fuse_min = -1; // B200AIS_FUSE_TAIL_MIN_CH: the smallest batch that fuses (tests, sanitizer runs)
+    if (fuse_min < 0) {
+        const char *e = getenv("B200AIS_FUSE_TAIL_MIN_CH");
+        fuse_min = (e && *e) ? atoi(e) : 8192;
+    }
+    const bool fuse_tail = !h->taps_enabled && !no_fuse && cn >= fuse_min &&
                            (reinterpret_cast<uintptr_t>(bits) & 3) == 0 && (max_bits & 3) == 0;
     float2 *t_sym = h->t_sym.as<float2>() + (size_t)c0 * max_bits;
     float *t_err = h->taps_enabled ? h->t_err.as<float>() + (size_t)c0 * max_bits : nullptr;

@@ -149,3 +149,25 @@ def test_pipelined_submission_with_the_small_ring_equals_strict_calls():
             assert np.array_equal(bits[c, :nb[c]], rb[c, :nb[c]]), (k, c)
             assert np.array_equal(tg[c, :nt[c]], rt[c, :nt[c]]), (k, c)
     d.close()
+
+
+@pytest.mark.parametrize("env", [
+    {"B200AIS_MSK_KIND": "2", "B200AIS_FUSE_TAIL_MIN_CH": "1"},
+    {"B200AIS_MSK_KIND": "1", "B200AIS_FUSE_TAIL_MIN_CH": "1"},
+    {"B200AIS_MSK_KIND": "0", "B200AIS_FUSE_TAIL_MIN_CH": "1"},
+    {"B200AIS_MSK_KIND": "2", "B200AIS_NO_FUSE_TAIL": "1", "B200AIS_MSK_NO_PAIR_FETCH": "1"},
+    {"B200AIS_MSK_NO_SLIDE": "1"},
+])
+def test_full_occupancy_code_paths_on_a_small_batch(env):
+    """the timing-loop variants a large batch selects (48-sample ring, paired fetch, bits written by
+    the loop) forced on the smoke batch in a fresh process (the switches are read once): bits,
+    symbol counts and tags against the oracle"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=e,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "smoke ok" in r.stdout, r.stdout[-2000:]

@@ -21,5 +21,7 @@ done
 ncu --set full --clock-control none --import-source on -k "regex:^k_msk$" -s 2 -c 1 -o $O/ncu_k_msk_65536ch python tools/prof_corr.py 65536 > $O/ncu_k_msk_65536.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:^k_msk$" -s 2 -c 1 -o $O/ncu_k_msk_16384ch python tools/prof_corr.py 16384 > $O/ncu_k_msk_16384.log 2>&1
 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/sanitizer_memcheck_smoke.log 2>&1
+# the full-occupancy paths on a small batch: 48-sample ring, paired fetch, bits written by the loop
+B200AIS_MSK_KIND=2 B200AIS_FUSE_TAIL_MIN_CH=1 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/sanitizer_memcheck_smoke_kind2_fused.log 2>&1
 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/sanitizer_racecheck_smoke.log 2>&1
 ls -la $O
