@@ -22,7 +22,8 @@ def main():
     for f in sorted(glob.glob(os.path.join(SRC, "bench_*.json")) + glob.glob(os.path.join(SRC, "rx_*.json"))):
         if os.path.getsize(f):
             shutil.copy(f, os.path.join(DST, "r02_" + os.path.basename(f)))
-    for f in ("launches_65536ch.csv", "sanitizer_memcheck_smoke.log", "sanitizer_racecheck_smoke.log"):
+    for f in ("launches_65536ch.csv", "sanitizer_memcheck_smoke.log", "sanitizer_memcheck_smoke_kind2_fused.log",
+              "sanitizer_racecheck_smoke.log"):
         p = os.path.join(SRC, f)
         if os.path.exists(p):
             shutil.copy(p, os.path.join(DST, "r02_" + f))

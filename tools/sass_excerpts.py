@@ -24,8 +24,8 @@ KERNELS = [
     ("agc.o", r"k_mix_agc512_tma<false>", "k_mix_agc512_tma"),
     ("agc.o", r"k_mix_agc512<false>", "k_mix_agc512_ldg"),
     ("freqsync.o", r"k_sqfft_freqest_1024", "k_sqfft_freqest_1024"),
-    ("msk.o", r"k_msk<false, 2, 7>", "k_msk_kind2"),
-    ("msk.o", r"k_msk<false, 0, 1>", "k_msk_kind0"),
+    ("msk.o", r"k_msk<false, 2, 7, true>", "k_msk_kind2"),
+    ("msk.o", r"k_msk<false, 0, 1, true>", "k_msk_kind0"),
     ("channelizer.o", r"k_xlat_fir<64, 16", "k_xlat_fir_64_16"),
 ]
 HILITE = re.compile(r"\b(UBLKCP|UTMALDG|UTMASTG|UTMAPF|UTMACMDFLUSH|SYNCS|LDGSTS|LDGDEPBAR|DEPBAR|"
