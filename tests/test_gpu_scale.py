@@ -105,12 +105,14 @@ def test_timing_loop_geometries_between_the_configs(oracle, C):
                          oracle.STAGE_FREQSYNC | oracle.STAGE_AGC)
 
 
-def test_pipelined_submission_with_the_small_ring_equals_strict_calls():
+@pytest.mark.parametrize("C,n", [(12320, 8192), (53280, 8192)])
+def test_pipelined_submission_with_the_small_ring_equals_strict_calls(C, n):
     """enqueue_dev on >= 12 288 channels runs the timing loop with the 48-sample ring on the side
     stream (it shares the SMs with the next record's front kernels); work_dev on the same handle
-    takes the 128-sample ring.  Record by record the bits, counts and tags must be the same."""
+    takes the 128-sample ring.  Above 53 248 channels enqueue_dev stays on the caller's stream.
+    Record by record the bits, counts and tags must be the same."""
     torch = pytest.importorskip("torch")
-    C, n, K = 12320, 8192, 3
+    K = 3
     tmpl = preamble_template("north_star")
     recs = [build_batch(C, n, 16, 700 + k, snr_db=18.0)[0] for k in range(K)]
     d = ais_demod(channels=C, max_samples=n, template=tmpl)
