@@ -24,11 +24,15 @@
 //    issue, not by HBM, and a radix-2 butterfly drops from 8 issue slots to 4 with identical bits.
 //    The twiddles of the lowest pass are the 16th roots of unity, whatever F is: they are
 //    immediates; the upper passes read (wr, wr, wi, wi) entries, one 16-byte load per butterfly.
-//  * Input: when the rows are 16-byte aligned a CTA streams its blocks through a two-stage
-//    shared-memory ring filled by the bulk-copy engine (cp.async.bulk.shared::cluster.global +
-//    mbarrier complete_tx; UBLKCP / SYNCS in the SASS), one elected thread issuing the copy of
-//    round r+2 while round r computes.  No load instruction, address arithmetic or staging
-//    register is spent on the IQ.  Unaligned rows take the register-prefetch path (LDG.64).
+//  * Input: when the rows are 16-byte aligned a CTA streams its blocks through a shared-memory
+//    buffer filled by the bulk-copy engine (cp.async.bulk.shared::cluster.global + mbarrier
+//    complete_tx; UBLKCP / SYNCS in the SASS).  A "full" / "empty" pair of mbarriers hands the
+//    buffer back and forth: the threads copy the round's items into registers and arrive on
+//    "empty", the elected thread then issues the copy of round r+1, which has the whole of
+//    round r to land.  One buffer, not two: the 9 KB it frees (with the transformed taps read
+//    through L1 instead of staged) make room for a fifth CTA per SM.  No load instruction,
+//    address arithmetic or staging register is spent on the IQ.  Unaligned rows take the
+//    register-prefetch path (LDG.64).
 //  * The correlator stream (8 B/sample) is only needed by the detector around samples above
 //    the threshold: in `sparse` mode a block is written only when it holds such a sample (plus
 //    the first and last item of every block, the detector's neighbours across a block edge).
@@ -239,7 +243,7 @@ __device__ __forceinline__ void block_filter(float2 (&v)[16], int t, const float
         static_assert(elem<SL, RL>(3, 5 >> RL, 5 & ((1 << RL) - 1)) == 16 * 3 + 5, "slot order");
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const float4 hh = h4[k * NT + t];
+            const float4 hh = __ldg(h4 + k * NT + t);
             v[2 * k] = cmul_fma2(v[2 * k], make_float2(hh.x, hh.y));
             v[2 * k + 1] = cmul_fma2(v[2 * k + 1], make_float2(hh.z, hh.w));
         }
@@ -291,6 +295,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
                  "r"(parity)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -328,7 +336,7 @@ template <int LOGF> __device__ __forceinline__ bool group_any(bool p)
 // north-star's 120 taps every `element < ns` test on a slot other than q = 8 folds away.
 // TMA: input through the bulk-copy ring (rows 16-byte aligned), else register prefetch.
 template <int LOGF, int LT, bool TMA>
-__global__ void __launch_bounds__(Plan<LOGF>::THREADS, (LOGF <= 8 ? 4 : (LOGF <= 10 ? 3 : 1)))
+__global__ void __launch_bounds__(Plan<LOGF>::THREADS, (LOGF <= 8 ? 5 : (LOGF <= 10 ? 3 : 1)))
 k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_rt, int nb_per_cta,
            const float2 *__restrict__ tw, const float2 *__restrict__ hbr, float thresh,
            const float2 *__restrict__ tail_in, float2 *__restrict__ tail_out,
@@ -344,9 +352,8 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
     const int stage_items = (GROUPS * ns + 3) & ~1; // one round of input, +1 item of alignment slack, even
     extern __shared__ float4 smem_raw[];
     float4 *s_twp = smem_raw;                                               // [TWP] (wr, wr, wi, wi)
-    float2 *s_h = reinterpret_cast<float2 *>(s_twp + P::TWP);               // [F] as float4 pairs [8][NT]
-    float2 *s_in = s_h + F;                                                 // [2][stage_items] (TMA)
-    float2 *s_x = s_in + (TMA ? 2 * stage_items : 0);                       // [GROUPS][F + F/16]
+    float2 *s_in = reinterpret_cast<float2 *>(s_twp + P::TWP);              // [stage_items] (TMA)
+    float2 *s_x = s_in + (TMA ? stage_items : 0);                           // [GROUPS][F + F/16]
     // block tails: groups 0 .. GROUPS-2 hand theirs to the next group of the same round (two
     // rotating sets), the last group to group 0 of the next round (three rotating slots)
     float2 *s_tail = s_x + GROUPS * (F + F / 16);                           // [2][GROUPS-1][L-1]
@@ -372,20 +379,15 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
         const int i1 = min(first + (r + 1) * GROUPS, last) * ns;
         const int lo = i0 & ~1, hi = (i1 + 1) & ~1;
         const unsigned bytes = (unsigned)(hi - lo) * 8u;
-        const unsigned bar = bar0 + 8u * (r & 1);
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(in0 + (unsigned)((r & 1) * stage_items) * 8u, xc + lo, bytes, bar);
+        mbar_expect_tx(bar0, bytes);
+        bulk_g2s(in0, xc + lo, bytes, bar0);
     };
     if constexpr (TMA) {
         if (threadIdx.x == 0) {
-            mbar_init(bar0, 1);
-            mbar_init(bar0 + 8, 1);
+            mbar_init(bar0, 1);               // "full": the round's bytes have landed
+            mbar_init(bar0 + 8, blockDim.x);  // "empty": every thread has copied its items out
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-    }
-    for (int i = threadIdx.x; i < F; i += blockDim.x) { // H[16 t + s] -> pair k = s/2 of thread t
-        const int tt = i >> 4, sl = i & 15;
-        s_h[(((sl >> 1) * NT + tt) << 1) | (sl & 1)] = hbr[i];
     }
     for (int i = threadIdx.x; i < P::TWP; i += blockDim.x) {
         const bool mid = i >= P::TWP_TOP;
@@ -400,11 +402,8 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
         s_mask[i] = 0u;
     __syncthreads();
     if constexpr (TMA) {
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0)
             issue(0);
-            if (rounds > 1)
-                issue(1);
-        }
     }
 
     float2 *xb = s_x + g * (F + F / 16);
@@ -435,12 +434,19 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
         const bool valid = b < last;
         float2 v[16];
         if constexpr (TMA) {
-            mbar_wait(bar0 + 8u * (r & 1), (unsigned)((r >> 1) & 1));
-            const float2 *src = s_in + (r & 1) * stage_items + (((first + r * GROUPS) * ns) & 1) + g * ns;
+            mbar_wait(bar0, (unsigned)(r & 1));
+            const float2 *src = s_in + (((first + r * GROUPS) * ns) & 1) + g * ns;
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 const int e = t + NT * q;
                 v[q] = (valid && e < ns) ? src[e] : make_float2(0.0f, 0.0f);
+            }
+            // the round's items are in registers: hand the buffer back; the elected thread
+            // refills it with the next round as soon as everybody has, a whole round ahead of use
+            mbar_arrive(bar0 + 8);
+            if (threadIdx.x == 0 && r + 1 < rounds) {
+                mbar_wait(bar0 + 8, (unsigned)(r & 1));
+                issue(r + 1);
             }
         } else if constexpr (PREFETCH) {
 #pragma unroll
@@ -453,7 +459,7 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
         }
         // slots whose smallest element t + NT q is zero padding for every thread: q >= ns / NT
         constexpr int ZQ = LT ? ((P::F - LT + 1) + NT - 1) / NT : 16;
-        block_filter<LOGF, ZQ>(v, t, s_twp, twr, reinterpret_cast<const float4 *>(s_h), xb);
+        block_filter<LOGF, ZQ>(v, t, s_twp, twr, reinterpret_cast<const float4 *>(hbr), xb);
         // stash this block's tail (outputs ns .. F-1) for the next block
         float2 *my_tail = g < GROUPS - 1 ? s_tail + ((r & 1) * (GROUPS - 1) + g) * tl : s_last + (r % 3) * tl;
 #pragma unroll
@@ -471,10 +477,6 @@ k_corr_fft(const float2 *__restrict__ in, size_t in_stride, int nblocks, int L_r
             }
         }
         __syncthreads();
-        if constexpr (TMA) { // every thread has read stage r & 1: refill it with round r + 2
-            if (threadIdx.x == 0 && r + 2 < rounds)
-                issue(r + 2);
-        }
         const bool emit = valid && b >= b0;
         bool hit = false;
         if (emit) {
@@ -535,7 +537,7 @@ int launch_one(const float2 *in, size_t in_stride, int channels, int nblocks, in
     const int ns = P::F - L + 1;
     const int stage_items = (P::GROUPS * ns + 3) & ~1;
     size_t smem = sizeof(float4) * (size_t)P::TWP +
-                  sizeof(float2) * (size_t)(P::F + (TMA ? 2 * stage_items : 0) +
+                  sizeof(float2) * (size_t)((TMA ? stage_items : 0) +
                                             P::GROUPS * (P::F + P::F / 16) +
                                             (2 * (P::GROUPS - 1) + 3) * (L > 1 ? L - 1 : 1)) +
                   sizeof(uint32_t) * (size_t)(((nb * ns) >> 5) + 1) + 32;
@@ -635,7 +637,7 @@ int launch_corr_fft(const float2 *in, size_t in_stride, int channels, int n, int
         const char *e = getenv("B200AIS_CORR_NO_TMA");
         no_tma = (e && atoi(e)) ? 1 : 0;
     }
-    // ... and the two-stage ring must fit beside the rest (it does up to fftsize 2048)
+    // ... and the round buffer must fit beside the rest (tested up to fftsize 2048)
     const bool tma = !no_tma && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (in_stride & 1) == 0 &&
                      ((n & 1) == 0 || in_readable > n) && F <= 2048;
 #define B200_CASE(LG)                                                                             \
