@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200ais.so")
+# B200AIS_LIB: another build of the same library (kernel experiments); the default is the in-tree one
+LIB_PATH = os.environ.get("B200AIS_LIB") or os.path.join(_PKG, "libb200ais.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0

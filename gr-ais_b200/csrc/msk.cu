@@ -52,7 +52,7 @@ __device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const fl
 // path).  Small batches run one warp per CTA so that every SM gets its share of the warps; the
 // large ones pack 7 warps behind one table (7 or 14 warps per SM).
 #ifndef MSK2_CHUNK
-#define MSK2_CHUNK 8
+#define MSK2_CHUNK 12
 #endif
 template <int KIND> struct MskCfg;
 template <> struct MskCfg<0> {
@@ -62,9 +62,10 @@ template <> struct MskCfg<1> {
     static constexpr int Chunk = 16, Ring = 96, Fast = 8, Need = 32, TagCap = 8;
 };
 template <> struct MskCfg<2> {
-    // 8-sample chunks: a lane may ask for the next one as soon as 9 ring slots are free, 1.1 to
-    // 1.9 rounds before it reads it (16-sample chunks: 0.2 to 1.1 rounds, i.e. every round
-    // waited for DRAM and the loop ran at the memory latency, 1050 cycles per step)
+    // 12-sample chunks (96 bytes, four to the ring): a 4-step round reads ~10 samples, so one
+    // chunk per round keeps up (8-sample chunks fell behind and spent a quarter of the loop's
+    // iterations waiting), and a lane may ask for the next one 0.4 to 1.5 rounds before it reads it
+    // (16-sample chunks: 0.2 to 1.1).  65 536 channels: 10.3 / 10.0 / 10.2 ms with 8 / 12 / 16.
     static constexpr int Chunk = MSK2_CHUNK, Ring = 48, Fast = 4, Need = 20, TagCap = 4;
 };
 constexpr int kMskMirror = 8;   // samples 0..7 repeated after the ring: 10-sample reads never wrap

@@ -1,8 +1,8 @@
 #!/bin/bash
-# Scratch A/B driver for gpurun: GPU tests, then bench lines for "VAR=VAL ..." variants.
+# Scratch A/B driver for gpurun: bench lines for "VAR=VAL ..." variants (SKIP_TESTS=1 skips pytest).
 #   bash tools/ab_run.sh "16384 65536" "" "B200AIS_MSK_NO_SLIDE=1"
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+[ -n "$SKIP_TESTS" ] || python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 chs="$1"; shift
 for ch in $chs; do
   for v in "$@"; do
