@@ -202,6 +202,8 @@ B200AIS_API int b200ais_demod_create(b200ais_demod **h, const b200ais_demod_conf
                                      const float *symbols_iq, int nsymbols, int channels,
                                      int max_samples, int max_tags);
 B200AIS_API int b200ais_demod_destroy(b200ais_demod *h);
+/* bits a record of nsamples can produce per channel (5 % over the nominal rate + 64), rounded up
+ * to a multiple of 4: with word-aligned bit rows the timing loop writes the bits itself */
 B200AIS_API int b200ais_demod_max_bits(const b200ais_demod *h, int nsamples);
 /* corr_est_cc::set_symbols (lib/corr_est_cc_impl.cc:132-162) on the chain's correlator: the taps
  * are replaced verbatim (no conjugate / reversal, unlike the constructor) and d_thresh keeps its
@@ -235,7 +237,9 @@ B200AIS_API int b200ais_demod_status(b200ais_demod *h);
  * tail to an internal high-priority stream, where they run under the front half of the NEXT
  * enqueue (corr_est input rows and tags are double-buffered).  tags / ntags are complete in
  * `stream` order; bits / nbits are complete once a later b200ais_demod_join(h, stream) has
- * been reached in `stream` order (any other b200ais_demod_* work call joins by itself). */
+ * been reached in `stream` order (any other b200ais_demod_* work call joins by itself).
+ * A handle with more than 53 248 channels fills the GPU with its timing loop alone; its
+ * records run entirely on `stream` (the contract above still holds, join is then a no-op). */
 B200AIS_API int b200ais_demod_enqueue_dev(b200ais_demod *h, const float *iq, int nsamples,
                                           uint8_t *bits, int max_bits, int *nbits,
                                           b200ais_tag *tags, int *ntags, void *stream);
