@@ -18,35 +18,14 @@ namespace b200ais {
 
 namespace {
 
-// mmse_fir_interpolator_cc::interpolate: imu = rint(mu*128), dot product of in[0..7] with
-// the reversed row.  Canonical summation: p_j = in[j]*t[j] (+) in[j+4]*t[j+4] fused,
-// result (p0+p1)+(p2+p3).
-__device__ __forceinline__ bool interp8(const float2 (&s)[8], float mu, const float *mmse,
-                                        float2 *v)
-{
-    const int imu = (int)rintf(mu * 128.0f);
-    if (imu < 0 || imu > 128)
-        return false;
-    const float *row = mmse + imu * 8;
-    float pr[4], pi[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float t0 = row[7 - j], t1 = row[3 - j];
-        pr[j] = __fmaf_rn(s[j + 4].x, t1, s[j].x * t0);
-        pi[j] = __fmaf_rn(s[j + 4].y, t1, s[j].y * t0);
-    }
-    v->x = (pr[0] + pr[1]) + (pr[2] + pr[3]);
-    v->y = (pi[0] + pi[1]) + (pi[2] + pi[3]);
-    return true;
-}
-
-// Ring geometry.  The loop's throughput is the number of warps an SM holds (a lone warp issues
-// one instruction every ~3 cycles), and what bounds that is the shared memory of the per-lane
-// rings; but a small ring leaves less room to request samples ahead of the DRAM latency
-// (~2 us under load = ~2 rounds).  Three geometries, picked by the channel count (launch_msk):
+// Ring geometry.  A warp of the loop is one dependent instruction stream (an instruction every
+// ~6 cycles whatever else the SM holds), so the kernel's throughput is the number of warps an SM
+// holds, and what bounds that is the shared memory of the per-lane rings; but a small ring leaves
+// less room to request samples ahead of the DRAM latency (~2 us under load = ~2 rounds).  Three
+// geometries, picked by the channel count (launch_msk):
 //   kind 0: 128-sample ring, 32-sample chunks, 8-step rounds, 43 KB/warp ->  4 warps/SM (18 944 ch)
 //   kind 1:  96-sample ring, 16-sample chunks, 8-step rounds, 29 KB/warp ->  7 warps/SM (33 152 ch)
-//   kind 2:  48-sample ring, 16-sample chunks, 4-step rounds, 15 KB/warp -> 14 warps/SM (66 304 ch)
+//   kind 2:  48-sample ring, 12-sample chunks, 4-step rounds, 15 KB/warp -> 14 warps/SM (66 304 ch)
 // The warps of a CTA are on their own; they share the 4 KB interpolator table, which has to sit
 // in shared memory (a table row read through L1 misses often enough to show on the critical
 // path).  Small batches run one warp per CTA so that every SM gets its share of the warps; the
@@ -301,18 +280,18 @@ __device__ __forceinline__ float msk_step(MskLane &L, int imu_c, const float4 *_
 }
 
 // The serial core of msk_timing_recovery_cc: one lane per channel.  A channel's loop is a
-// recurrence on (mu, omega, iidx, div, previous interpolant): a lone warp issues one
-// instruction every ~3 cycles and a step takes ~450 cycles however many channels run, so the
-// kernel's throughput is the number of warps an SM can hold.  What bounds that is shared
-// memory: each lane streams its own channel through a private ring (3 chunks of 16 samples +
-// 8 mirrored, stored as 16-byte units interleaved across lanes so that a lane's reads never
-// meet another lane's banks) filled by cp.async, 15 KB per warp -> 14 warps per SM, 2072
-// warps = 66 304 channels in flight on 148 SMs (BASELINE configs[2]'s 65 536 in one wave; the
-// previous 128-sample ring + table + 32 staged tags held 4 warps per SM, 18 944 channels).
-// A lane requests a 128-byte chunk at least one round (4 steps, ~10 samples) before it is
-// needed, so no step waits on HBM.  Up to 4 of the lane's time_est tags are staged in shared
-// memory and refilled from the list when they run out (a tag fetched on the loop's critical
-// path costs a DRAM round trip; a burst carries about six).
+// recurrence on (mu, omega, iidx, div, previous interpolant): a warp is one dependent instruction
+// stream, a step costs (its instructions) x ~6 cycles however many channels run, and the kernel's
+// throughput is the number of warps an SM can hold.  What bounds that is shared memory: each lane
+// streams its own channel through a private ring (stored as 16-byte units interleaved across
+// lanes so that a lane's reads never meet another lane's banks, 8 samples mirrored behind it so
+// that reads never wrap) filled by cp.async; the smallest geometry is 15 KB per warp -> 14 warps
+// per SM, 2072 warps = 66 304 channels in flight on 148 SMs (BASELINE configs[2]'s 65 536 in one
+// wave).  A lane requests a chunk a round before it is needed.  Up to TagCap of the lane's
+// time_est tags are staged in shared memory and refilled from the list when they run out (a tag
+// fetched on the loop's critical path costs a DRAM round trip; a burst carries about six).
+// FUSE: the bit tail (quadrature demod -> slicer -> diff decoder -> invert) runs on every symbol
+// as it is produced and the kernel writes bits instead of symbols.
 template <bool kDebug, int KIND, int WARPS, bool FUSE>
 __global__ void __launch_bounds__(32 * WARPS)
 k_msk(const float2 *__restrict__ in, size_t in_stride, int channels, int noutput_items,
