@@ -299,12 +299,15 @@ def run_b200(args):
     from gr_ais_b200.ais_demod import ais_demod, preamble_template
 
     rank, local_rank, world = dist_env()
+    # stdout carries the one JSON line: while the communicator comes up (NCCL prints its
+    # "NCCL version ..." banner on file descriptor 1) it points at stderr
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the one JSON line: NCCL's own banner ("NCCL version ...", printed when the
-        # environment asks for NCCL_DEBUG=VERSION/INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     B.set_device(local_rank)
@@ -315,6 +318,11 @@ def run_b200(args):
     # rank 0 owns the preamble template; the other ranks receive it over NCCL (the only collective)
     tmpl = sharding.broadcast_template(preamble_template(args.template) if rank == 0 else None,
                                        src=0, device=dev)
+    if saved_stdout is not None:
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     C = default_channels(args, world)
     n = int(round(args.seconds * FS))
