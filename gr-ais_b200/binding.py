@@ -54,7 +54,7 @@ EXPORTS = [
     "b200ais_rx_default_config", "b200ais_rx_create", "b200ais_rx_destroy", "b200ais_rx_reset",
     "b200ais_rx_decimation", "b200ais_rx_channels", "b200ais_rx_samples_per_symbol",
     "b200ais_rx_sentence_slot", "b200ais_rx_work", "b200ais_rx_work_dev", "b200ais_rx_status",
-    "b200ais_rx_tag_overflows",
+    "b200ais_rx_tag_overflows", "b200ais_selftest_div",
     "b200ais_rx_replay_file", "b200ais_rx_serve_udp",
 ]
 FRAME_MAX = 248
@@ -202,6 +202,7 @@ def lib():
     L.b200ais_rx_samples_per_symbol.restype = C.c_float
     L.b200ais_rx_tag_overflows.argtypes = [vp]
     L.b200ais_rx_tag_overflows.restype = u64
+    L.b200ais_selftest_div.argtypes = [C.c_float, C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong)]
     L.b200ais_rx_work.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, C.POINTER(i)]
     L.b200ais_rx_work_dev.argtypes = [vp, vp, sz, i, vp, vp, i, vp, i, vp, vp]
     L.b200ais_rx_replay_file.argtypes = [vp, C.c_char_p, i, i, RX_SINK, vp, C.POINTER(u64)]

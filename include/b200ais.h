@@ -443,6 +443,13 @@ B200AIS_API int b200ais_rx_status(b200ais_rx *h);
 /* calls in which some channel met more corr_est tags than its row holds (the extra tags were
  * dropped, i.e. some timing resets were missed; the call's messages are delivered all the same) */
 B200AIS_API uint64_t b200ais_rx_tag_overflows(const b200ais_rx *h);
+
+/* ---- self-test hooks (tests/ only) ----
+ * The AGC kernel's straight-line IEEE division (device_math.cuh: div_rn_inrange) against the `/`
+ * operator on the device, for the dividend a and every float b whose bit pattern lies in
+ * [b_lo_bits, b_hi_bits]: *mismatches = the number of b with different quotient bits. */
+B200AIS_API int b200ais_selftest_div(float a, uint32_t b_lo_bits, uint32_t b_hi_bits,
+                                     unsigned long long *mismatches);
 /* Recorded-IQ replay: blocks.file_source(gr.sizeof_gr_complex, path) (python/radio.py:211-213)
  * feeding every source of the receiver with the same capture.  The file (raw interleaved
  * float32 IQ) is read in chunks of chunk_items through two pinned buffers, the read of the next

@@ -248,3 +248,24 @@ def test_corr_est_rejects_unsupported_tap_counts():
     for L in (1, 4, 2049):
         with pytest.raises(B.B200AisError):
             blocks.corr_est_cc.make(np.ones(L, np.complex64), 5.0, 1, 0.9)
+
+
+def test_agc_gain_division_is_the_ieee_quotient():
+    """the AGC kernel's straight-line division (reciprocal estimate, Newton step, quotient,
+    remainder, correction: nvcc's own fast path without its range check) against the `/` operator
+    on the device: every float divisor in [1e-4, 1e15] -- the range the kernel uses it in -- for
+    the reference level 2 and dividends across its allowed range"""
+    import ctypes
+    import struct
+
+    def bits(x):
+        return struct.unpack("<I", struct.pack("<f", x))[0]
+    lo, hi = bits(1e-4) - 1, bits(1e15) + 1
+    L = B.lib()
+    total = 0
+    for a in (2.0, 1.0, 0.75, 3.1415927, 1.9999999, 1e-10, 1e10, 123456.7):
+        bad = ctypes.c_ulonglong(1)
+        B.check(L.b200ais_selftest_div(ctypes.c_float(a), lo, hi, ctypes.byref(bad)))
+        assert bad.value == 0, (a, bad.value)
+        total += hi - lo + 1
+    assert total > 4_000_000_000
