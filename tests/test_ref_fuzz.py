@@ -102,3 +102,31 @@ def test_freqest_random_spectra(oracle, seed):
     a = R.freqest_work(spec, 48000.0, 9600, fftlen)
     b = oracle.freqest_work(spec, 48000.0, 9600, fftlen)[0]
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_chain_and_stream_random_configurations(oracle, seed):
+    """the whole chain and its stream form on the reference's classes against the restated blocks:
+    random template kind, threshold, mark delay, loop gain, fftlen, stages, record and piece sizes"""
+    from gr_ais_b200 import synth
+    from gr_ais_b200.ais_demod import preamble_template
+    rng = np.random.default_rng(3000 + seed)
+    tmpl = preamble_template(str(rng.choice(["north_star", "north_star", "intended", "reference"])))
+    stages = int(rng.choice([oracle.STAGE_FREQSYNC | oracle.STAGE_AGC, oracle.STAGE_AGC, 0]))
+    cfg = oracle.chain_cfg(fftlen=int(rng.choice([256, 1024])), threshold=float(rng.choice([0.5, 0.8, 0.9])),
+                           mark_delay=int(rng.integers(0, 4)), gain=float(rng.choice([0.04, 0.1, 0.175])),
+                           limit=float(rng.choice([0.01, 0.05])), stages=stages)
+    n = int(rng.integers(6000, 20000))
+    x, _ = synth.make_record(400 + seed, n=n, nbursts=int(rng.integers(1, 4)),
+                             snr_db=float(rng.uniform(6.0, 25.0)), random_impairments=True)
+    a = oracle.demod_chain(x, tmpl, cfg, blocks=R.blocks())
+    b = oracle.demod_chain(x, tmpl, cfg)
+    assert np.array_equal(a["bits"], b["bits"])
+    same_tags(a["tags"], b["tags"])
+    if stages & oracle.STAGE_AGC:   # the stream form needs the reference's AGC window
+        sa, sb = oracle.DemodStream(tmpl, cfg, blocks=R.blocks()), oracle.DemodStream(tmpl, cfg)
+        cuts = np.unique(np.concatenate([[0, n], rng.integers(0, n, int(rng.integers(1, 7)))]))
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            (ab, at), (bb, bt) = sa.work(x[lo:hi]), sb.work(x[lo:hi])
+            assert np.array_equal(ab, bb), (seed, lo, hi)
+            same_tags(at, bt)
