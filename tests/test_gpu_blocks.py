@@ -269,3 +269,46 @@ def test_agc_gain_division_is_the_ieee_quotient():
         assert bad.value == 0, (a, bad.value)
         total += hi - lo + 1
     assert total > 4_000_000_000
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_msk_random_rates_tags_and_call_sizes(oracle, seed):
+    """the timing loop far from the directed cases: rate, gain, limit, osps, tag list (stale,
+    off-key, NaN, negative centres) and ragged call sizes drawn at random; with the error / mu
+    outputs connected (the per-step kernel) and without them (the straight-line rounds)"""
+    rng = np.random.default_rng(9000 + seed)
+    sps = float(rng.choice([5.0, 5.0, 5.208, 5.5, 6.0, 8.0]))   # >= 16/3: DESIGN.md section 4
+    gain = float(rng.choice([0.01, 0.04, 0.1, 0.175]))
+    limit = float(rng.choice([0.005, 0.01, 0.05, 0.2]))
+    osps = int(rng.integers(1, 3))
+    x = synth.gmsk_modulate(rng.integers(0, 2, 500)).astype(np.complex64)
+    x += (0.05 * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))).astype(np.complex64)
+    if sps != 5.0:
+        t = np.arange(0, len(x) - 1, 5.0 / sps)
+        i = t.astype(int)
+        f = (t - i).astype(np.float32)
+        x = ((1 - f) * x[i] + f * x[i + 1]).astype(np.complex64)
+    n = len(x)
+    offs = np.sort(rng.integers(0, n, int(rng.integers(0, 14))))
+    tags = _tags([(int(o), 2 if rng.random() < 0.75 else int(rng.integers(0, 4)),
+                   float(rng.uniform(-0.999, 0.999)) if rng.random() < 0.9 else float("nan")) for o in offs])
+    calls = [(int(rng.integers(0, 900)), int(rng.integers(1, 400))) for _ in range(40)]
+    for taps in (True, False):
+        blk = blocks.msk_timing_recovery_cc.make(sps, gain, limit, osps)
+        ref = oracle.MskBlock(sps, gain, limit, osps)
+        pos = 0
+        for step, nout in calls:
+            chunk = x[pos:min(n, pos + step)]
+            out = np.zeros((1, nout), np.complex64)
+            err = np.zeros((1, nout), np.float32)
+            mu = np.zeros((1, nout), np.float32)
+            k = blk.general_work(nout, [len(chunk)], [chunk], [out, err, mu] if taps else [out], tags=[tags])
+            r_out, r_err, r_mu, r_cons = ref.general_work(nout, chunk, tags, nitems_read=pos)
+            assert k == len(r_out) and blk.consumed[0] == r_cons, (seed, taps, pos)
+            assert np.array_equal(out[0, :k].view(np.uint32), r_out.view(np.uint32)), (seed, taps, pos)
+            if taps:
+                assert np.array_equal(err[0, :k].view(np.uint32), r_err.view(np.uint32)), (seed, pos)
+                assert np.array_equal(mu[0, :k].view(np.uint32), r_mu.view(np.uint32)), (seed, pos)
+            pos += r_cons
+            if pos >= n:
+                break
