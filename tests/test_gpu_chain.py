@@ -199,3 +199,31 @@ def test_pipelined_enqueue_equals_strict_calls(oracle, templates):
     assert np.array_equal(outs[0][1].cpu().numpy(), ref_n[0])
     b0, _, _, _ = d.work(recs[2])  # host path drains the pipeline too
     d.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_chain_random_configurations_without_taps(oracle, templates, seed):
+    """the production path (no taps: the straight-line timing-loop kernel) at random template,
+    threshold, mark delay, loop gain / limit, fftlen, stages and record length: bits and tags"""
+    rng = np.random.default_rng(3000 + seed)
+    tmpl = templates[int(rng.choice([120, 120, 140, 1120]))]
+    stages = int(rng.choice([B.STAGE_FREQSYNC | B.STAGE_AGC, B.STAGE_AGC, 0]))
+    opts = {"fftlen": int(rng.choice([256, 1024])), "clockrec_gain": float(rng.choice([0.04, 0.1, 0.175])),
+            "omega_relative_limit": float(rng.choice([0.01, 0.05]))}
+    thr, md = float(rng.choice([0.5, 0.8, 0.9])), int(rng.integers(0, 4))
+    C, n = 5, int(rng.integers(6000, 20000))
+    x = np.stack([synth.make_record(400 + 10 * seed + c, n=n, nbursts=int(rng.integers(1, 4)),
+                                    snr_db=float(rng.uniform(6.0, 25.0)), random_impairments=True)[0]
+                  for c in range(C)])
+    d = ais_demod(opts, channels=C, max_samples=n, template=tmpl, stages=stages, threshold=thr,
+                  mark_delay=md, max_tags=1024)
+    bits, nbits, tags, ntags = d.work(x)
+    cfg = oracle.chain_cfg(stages=stages, threshold=thr, mark_delay=md, fftlen=opts["fftlen"],
+                           gain=opts["clockrec_gain"], limit=opts["omega_relative_limit"])
+    for c in range(C):
+        r = oracle.demod_chain(x[c], tmpl, cfg, max_tags=4096)
+        assert nbits[c] == len(r["bits"]) and ntags[c] == len(r["tags"]), (seed, c)
+        assert np.array_equal(bits[c, :nbits[c]], r["bits"]), (seed, c)
+        for f in ("offset", "key", "port", "value"):
+            assert np.array_equal(tags[c, :ntags[c]][f], r["tags"][f], equal_nan=(f == "value")), (seed, c, f)
+    d.close()
